@@ -1,0 +1,179 @@
+/*
+ * stackrl_b200 -- C ABI of the B200-native observation + placement-scoring path.
+ *
+ * The reference (menezesandre/stackrl) is pure Python and has no FFI of its own;
+ * its extension points are Python constructor injection and duck typing
+ * (SURVEY.md section 8b).  Each entry point below replaces the arithmetic of one
+ * reference function and is what a reference-side ctypes binding would call
+ * (INTEGRATION.md shows the stubs).  Citations are relative to the reference
+ * tree root.
+ *
+ * Conventions (all entry points)
+ *   - return 0 on success, a negative SRL_E_* code on failure; never throws.
+ *     srl_last_error() returns a thread-local description of the last failure.
+ *   - every pointer is a DEVICE pointer unless the parameter is named host_*;
+ *     the caller owns all buffers (the library neither allocates nor frees
+ *     device memory) and has made the right device current.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream) and the call returns without synchronising.
+ *   - layouts are dense row-major; "planar" maps are [count, rows, cols].
+ *   - P = (H-h+1)*(W-h+1) candidate positions per map, row-major (the reference
+ *     only defines square rocks, baselines.py:39 -- SURVEY quirk Q3).
+ */
+#ifndef STACKRL_B200_H_
+#define STACKRL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRL_OK            0
+#define SRL_E_INVALID    -1   /* bad argument (null pointer, size, alignment) */
+#define SRL_E_UNSUPPORTED -2  /* shape outside what the kernels are built for */
+#define SRL_E_CUDA       -3   /* a CUDA runtime call failed (see srl_last_error) */
+
+typedef void* srl_stream_t;   /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define SRL_API __attribute__((visibility("default")))
+#else
+#define SRL_API
+#endif
+
+/* Library ABI version (major*10000 + minor*100 + patch). */
+SRL_API int srl_version(void);
+/* Thread-local message for the last non-zero return on this thread. */
+SRL_API const char* srl_last_error(void);
+/* Number of SMs of the current device (148 on B200). */
+SRL_API int srl_device_sm_count(int* host_out);
+
+/* ---- a5: baselines.get_inputs + baselines.height (baselines.py:21-43) -------
+ * out[e,r,i,j] = max_{u,v}( n > threshold ? o[e,i+u,j+v] + n : 0 ),
+ *   o = walls[e]/level[e],  n = rocks[e,r,u,v]/level[e]   (IEEE float32 div, add)
+ * level == NULL skips the normalisation (o = wall, n = rock), which with
+ * threshold = 1e-4 is the Observer.pose mask (observer.py:405-409).
+ * A masked cell contributes 0 (not -inf): baselines.py:37-41, quirk Q2.
+ *   walls [E,H,W] f32, rocks [E,R,h,h] f32, level [E] f32 or NULL,
+ *   out [E,R,H-h+1,W-h+1] f32.  Bit-exact with the reference's float32 path. */
+SRL_API int srl_maxplus_f32(const float* walls, const float* rocks, const float* level,
+                    float* out, int E, int R, int H, int W, int h,
+                    float threshold, srl_stream_t stream);
+
+#ifdef SRL_NEXT   /* declared as the next entry points land */
+/* Same for uint8 observations (registered Stack-v0/1/2 dtype): the reference
+ * divides uint8 by uint8 -> float64, so this evaluates IEEE float64
+ * a/g + b/g per cell.  level [E] u8 (goal.max()), out f64. */
+SRL_API int srl_maxplus_u8(const uint8_t* walls, const uint8_t* rocks,
+                   const uint8_t* level, double* out, int E, int R, int H,
+                   int W, int h, srl_stream_t stream);
+
+/* ---- a4: Observer.pose drop height (observer.py:401-409) --------------------
+ * z[e] = max( (walls[e, i:i+h, j:j+h] + rocks[e, r])[rocks[e, r] > 1e-4] ),
+ * (r, i, j) = picks[e] (int32 triples).  out [E] f32. */
+SRL_API int srl_drop_height_f32(const float* walls, const float* rocks,
+                        const int32_t* picks, float* out, int E, int R, int H,
+                        int W, int h, float threshold, srl_stream_t stream);
+
+/* ---- a7: baselines.goal_overlap counts (baselines.py:152-155) ---------------
+ * counts[e,r,i,j] = sum_{u,v} (walls[e,i+u,j+v] < goals[e,i+u,j+v]) *
+ *                             (rocks[e,r,u,v] > 0)        (exact int32)
+ * The >= threshold*max compare is part of srl_select. */
+SRL_API int srl_goal_overlap_f32(const float* walls, const float* goals,
+                         const float* rocks, int32_t* counts, int E, int R,
+                         int H, int W, int h, srl_stream_t stream);
+SRL_API int srl_goal_overlap_u8(const uint8_t* walls, const uint8_t* goals,
+                        const uint8_t* rocks, int32_t* counts, int E, int R,
+                        int H, int W, int h, srl_stream_t stream);
+
+/* ---- a9/a10: Baseline.call + PyGreedy batchwise (baselines.py:201-217,
+ *      agents/policies.py:57-91) ----------------------------------------------
+ * Per map (e,r): mask = counts >= overlap_threshold*max(counts) (float64
+ * compare, quirk Q7); minima = mask & (minimum_filter(values, 1+2*minorder,
+ * zero padded) == values); action = first-index argmin over minima if any, else
+ * over mask; shown = -where(mask, values, max(values[mask]) + 0.001).
+ * counts == NULL is the goal=False branch: action = argmin(values), shown =
+ * -values.  Then per env: best_r = first argmax_r shown[e,r,action[e,r]].
+ *   values [E,R,P] (f32 or f64), counts [E,R,P] i32 or NULL,
+ *   actions [E,R] i64, shown [E,R,P] (same type as values; may be NULL),
+ *   best [E,2] i64 = (r*, action[e,r*]) or NULL. */
+SRL_API int srl_select_f32(const float* values, const int32_t* counts, int64_t* actions,
+                   float* shown, int64_t* best, int E, int R, int Ph, int Pw,
+                   int minorder, double overlap_threshold, srl_stream_t stream);
+SRL_API int srl_select_f64(const double* values, const int32_t* counts, int64_t* actions,
+                   double* shown, int64_t* best, int E, int R, int Ph, int Pw,
+                   int minorder, double overlap_threshold, srl_stream_t stream);
+
+/* ---- a6: baselines.difference (baselines.py:45-77), exponents (2, 2|0) -------
+ * f = sum_{u,v} w[u,v] * |h0 - (o+n)|^p  in numpy's order: float32 lift and
+ * residual, float64 weights/product, pairwise summation over the contiguous
+ * [h,h] block.  p in {1, 2}.  weights [E,R,h,h] f64 come from
+ * srl_difference_weights.  out [E,R,P] f64; top (h0) [E,R,P] f32 or NULL. */
+SRL_API int srl_difference_weights(const float* rocks, const float* level,
+                           double* weights, int E, int R, int h,
+                           int weights_exponent, srl_stream_t stream);
+SRL_API int srl_difference_f32(const float* walls, const float* rocks,
+                       const float* level, const double* weights, double* out,
+                       float* top, int E, int R, int H, int W, int h,
+                       int difference_exponent, srl_stream_t stream);
+
+/* ---- a2/a3: Observer.__call__ rasterisation + depth->elevation
+ *      (observer.py:252-260, 267-277; pybullet.getCameraImage) ----------------
+ * One job = one image: a camera (column-major GL view and projection matrices,
+ * as computeViewMatrix / computeProjectionMatrix return them), an image size,
+ * and a contiguous range of world-space triangles.  Depth follows the GL
+ * convention the reference inverts (observer.py:259-260); `mode` selects the
+ * fused conversion:
+ *   SRL_RASTER_DEPTH  out = depth in [0,1] (background 1)
+ *   SRL_RASTER_WALL   out = far - far*(far-zr)/(far - zr*d)            (:259-260)
+ *   SRL_RASTER_ROCK   out = (far + zr/2 - (far^2-(zr/2)^2)/(far+zr*(1/2-d)))
+ *                           with columns mirrored                       (:274-277)
+ *   verts [nverts,3] f32 world space; tris [ntris,3] i32 vertex indices;
+ *   jobs [njobs] srl_raster_job; out [njobs, rows, cols] f32. */
+#define SRL_RASTER_DEPTH 0
+#define SRL_RASTER_WALL  1
+#define SRL_RASTER_ROCK  2
+typedef struct srl_raster_job {
+  float view[16];        /* column-major */
+  float proj[16];        /* column-major */
+  int32_t tri_begin;     /* first triangle of this image */
+  int32_t tri_count;
+  int32_t ground;        /* 1: an infinite z=0 ground plane is part of the scene */
+  float zrange;          /* zr above: max_z (wall) or object_z (rock) */
+} srl_raster_job;
+SRL_API int srl_raster(const float* verts, const int32_t* tris,
+               const srl_raster_job* jobs, float* out, int njobs, int rows,
+               int cols, int mode, double far_plane, srl_stream_t stream);
+
+/* ---- a11: Rewarder._intersection/_union (rewarder.py:297-307) ---------------
+ * inter[e] = sum(min(walls[e][goal != 0], goal_z[e])), uni[e] = sum(max(walls[e],
+ * goals[e])), vol[e] = sum(goals[e]); float32 accumulation in numpy's pairwise
+ * order is NOT reproduced (tolerance 1e-6 relative). */
+SRL_API int srl_reward_sums_f32(const float* walls, const float* goals,
+                        const float* goal_z, float* inter, float* uni,
+                        float* vol, int E, int H, int W, srl_stream_t stream);
+
+/* ---- a14: StackEnv.observation/_return (env.py:171-180, 226-231, 472-480) ---
+ * wall_goal[e,(r),i,j,0:2] = cast(walls[e,i,j], goals[e,i,j]); rock[e,r,u,v,0] =
+ * cast(rocks[e,r,u,v]).  dtype_code: 0 float32 (copy), 1 uint8: trunc(x*255/
+ * scale) evaluated in float32 like numpy (quirk Q11).  repeat_wall != 0 writes
+ * the TestStackEnv layout ([E,R,H,W,2]), else [E,H,W,2]. */
+SRL_API int srl_pack_obs(const float* walls, const float* goals, const float* rocks,
+                 void* wall_goal, void* rock, int E, int R, int H, int W, int h,
+                 int dtype_code, float scale, int repeat_wall,
+                 srl_stream_t stream);
+
+#endif  /* SRL_NEXT */
+
+/* ---- measurement helpers (not part of the reference's surface) --------------
+ * Issue-rate micro-benchmark used to fix the FP32 roofline of the max-plus
+ * kernel: runs `iters` dependent rounds of (add, max) cells on every lane of a
+ * full-chip grid and reports cells/s.  variant 0: FADD+FMNMX, 1: FADD+FMNMX3,
+ * 2: FADD2+FMNMX3 (the kernel's mix).  Synchronises the device. */
+SRL_API int srl_microbench_addmax(int variant, int iters, double* host_cells_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* STACKRL_B200_H_ */

@@ -1,0 +1,118 @@
+"""ctypes binding of libstackrl_b200.so (include/stackrl_b200.h).
+
+PyTorch is used only as the device-buffer interchange: every wrapper takes
+contiguous CUDA tensors, passes ``data_ptr()`` and the current stream to the
+C ABI, and returns the output tensor.  There is no CPU fallback: if the library
+is missing this module raises ImportError at import time, and every entry point
+raises on a non-CUDA tensor.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libstackrl_b200.so')
+
+
+class SrlError(RuntimeError):
+  """A C-ABI call returned a negative code."""
+  def __init__(self, code, message):
+    super(SrlError, self).__init__('srl error {}: {}'.format(code, message))
+    self.code = code
+
+
+if not os.path.exists(LIB_PATH):
+  raise ImportError(
+    '{} is missing: build it with `python -m stackrl_b200.build` (nvcc, sm_100a). '
+    'stackrl_b200 has no CPU fallback.'.format(LIB_PATH))
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_c = ctypes
+_P = _c.c_void_p
+_I = _c.c_int
+
+_SIGNATURES = {
+  'srl_version': (_I, []),
+  'srl_last_error': (_c.c_char_p, []),
+  'srl_device_sm_count': (_I, [_c.POINTER(_I)]),
+  'srl_maxplus_f32': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_float, _P]),
+  'srl_maxplus_u8': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+  'srl_drop_height_f32': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_float, _P]),
+  'srl_goal_overlap_f32': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+  'srl_goal_overlap_u8': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+  'srl_select_f32': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_double, _P]),
+  'srl_select_f64': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_double, _P]),
+  'srl_difference_weights': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+  'srl_difference_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+  'srl_raster': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _P]),
+  'srl_reward_sums_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+  'srl_pack_obs': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_float, _I, _P]),
+  'srl_microbench_addmax': (_I, [_I, _I, _c.POINTER(_c.c_double)]),
+}
+
+for _name, (_res, _args) in _SIGNATURES.items():
+  try:
+    _fn = getattr(lib, _name)
+  except AttributeError:
+    continue          # tests/test_capi_symbols.py checks the header <-> export match
+  _fn.restype = _res
+  _fn.argtypes = _args
+
+
+def _check(code):
+  if code != 0:
+    raise SrlError(code, lib.srl_last_error().decode('utf-8', 'replace'))
+
+
+def _dev(t, dtype, name):
+  if not isinstance(t, torch.Tensor) or not t.is_cuda:
+    raise TypeError('{} must be a CUDA tensor (stackrl_b200 has no CPU path)'.format(name))
+  if t.dtype != dtype:
+    raise TypeError('{} must be {}, got {}'.format(name, dtype, t.dtype))
+  if not t.is_contiguous():
+    raise ValueError('{} must be contiguous'.format(name))
+  return _P(t.data_ptr())
+
+
+def _opt(t, dtype, name):
+  return _P(None) if t is None else _dev(t, dtype, name)
+
+
+def _stream():
+  return _P(torch.cuda.current_stream().cuda_stream)
+
+
+def version():
+  return lib.srl_version()
+
+
+def sm_count():
+  n = _I(0)
+  _check(lib.srl_device_sm_count(ctypes.byref(n)))
+  return n.value
+
+
+def maxplus_f32(walls, rocks, level=None, threshold=0., out=None):
+  """walls [E,H,W], rocks [E,R,h,h], level [E] or None -> [E,R,H-h+1,W-h+1]."""
+  E, H, W = walls.shape
+  E2, R, h, h2 = rocks.shape
+  if E2 != E or h != h2:
+    raise ValueError('rocks must be [E, R, h, h] matching walls [E, H, W]')
+  if out is None:
+    out = torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.float32,
+                      device=walls.device)
+  with torch.cuda.device(walls.device):
+    _check(lib.srl_maxplus_f32(
+      _dev(walls, torch.float32, 'walls'), _dev(rocks, torch.float32, 'rocks'),
+      _opt(level, torch.float32, 'level'), _dev(out, torch.float32, 'out'),
+      E, R, H, W, h, float(threshold), _stream()))
+  return out
+
+
+def microbench_addmax(variant, iters=2000):
+  """(add, max) cells per second of the issue-rate micro-benchmark."""
+  v = _c.c_double(0.)
+  _check(lib.srl_microbench_addmax(int(variant), int(iters), ctypes.byref(v)))
+  return v.value

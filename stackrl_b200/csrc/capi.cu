@@ -1,0 +1,70 @@
+// extern "C" surface of libstackrl_b200.so (include/stackrl_b200.h) and the
+// error plumbing shared by the kernels' host-side dispatchers.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace srl {
+
+namespace {
+thread_local char g_error[512] = "";
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(SRL_E_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  return SRL_OK;
+}
+
+int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return 0;
+  return n;
+}
+
+}  // namespace srl
+
+using srl::fail;
+
+extern "C" {
+
+int srl_version(void) { return 100; }  // 0.1.0
+
+const char* srl_last_error(void) { return srl::g_error; }
+
+int srl_device_sm_count(int* host_out) {
+  SRL_REQUIRE(host_out != nullptr, SRL_E_INVALID, "srl_device_sm_count: null");
+  const int n = srl::sm_count();
+  SRL_REQUIRE(n > 0, SRL_E_CUDA, "srl_device_sm_count: no CUDA device");
+  *host_out = n;
+  return SRL_OK;
+}
+
+int srl_maxplus_f32(const float* walls, const float* rocks, const float* level,
+                    float* out, int E, int R, int H, int W, int h,
+                    float threshold, srl_stream_t stream) {
+  int variant = 1;
+  if (const char* s = getenv("SRL_MAXPLUS_VARIANT")) variant = atoi(s);
+  return srl::maxplus_f32(walls, rocks, level, out, E, R, H, W, h, threshold,
+                          variant, (cudaStream_t)stream);
+}
+
+int srl_microbench_addmax(int variant, int iters, double* host_cells_per_s) {
+  return srl::microbench_addmax(variant, iters, host_cells_per_s);
+}
+
+}  // extern "C"

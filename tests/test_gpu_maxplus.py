@@ -1,0 +1,127 @@
+"""Parity of the CUDA max-plus path (through the C ABI) with the reference:
+golden vectors produced by the reference's own ``height`` and the numpy oracle
+on seeded inputs.  Bit-exact (integer/float32 max-plus is order independent and
+every add is a single IEEE add)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import scoring_np as S
+from stackrl_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+F32_CASES = ['c2like_f32', 'nonsquare_wall_f32', 'dense_rock_f32', 'empty_rock_f32',
+             'ties_f32', 'flat_wall_f32', 'c4like_f32', 'c5like_f32',
+             'full_rock_window_f32']
+
+
+@pytest.fixture(scope='module')
+def capi():
+  from stackrl_b200 import capi
+  return capi
+
+
+def _oracle_maps(walls, rocks, level):
+  """Loop the oracle's ``height`` over a planar batch -> [E,R,Ph,Pw] float32."""
+  E, R = rocks.shape[:2]
+  out = []
+  for e in range(E):
+    goal = np.full(walls.shape[1:], level[e], dtype='float32')
+    wg = np.stack([walls[e], goal], axis=-1)
+    out.append([S.height((wg, rocks[e, r][..., None])) for r in range(R)])
+  return np.asarray(out).astype('float32')
+
+
+@pytest.mark.parametrize('case', F32_CASES)
+def test_height_matches_reference_golden(scoring_golden, case):
+  from stackrl_b200 import baselines
+  got = baselines.height(scoring_golden.obs(case))
+  want = scoring_golden[case + '/height']
+  assert got.dtype == want.dtype and got.shape == want.shape
+  assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize('variant', ['0', '1'])
+@pytest.mark.parametrize('shape', [
+  # E, R, H, W, h
+  (5, 8, 32, 32, 16),      # config 2 geometry, ragged last CTA group
+  (3, 3, 64, 64, 16),      # config 4 geometry
+  (2, 2, 128, 128, 32),    # config 1/5 geometry
+  (4, 1, 20, 28, 6),       # rock side not a multiple of 4 (no TMA rows)
+  (3, 2, 17, 19, 5),       # wall width not a multiple of 4 (no TMA)
+  (2, 5, 40, 24, 12),
+  (1, 1, 9, 9, 9),         # single candidate position
+  (7, 36, 48, 48, 16),     # many rotations (rotation chunking)
+])
+def test_batched_matches_oracle(capi, monkeypatch, shape, variant):
+  monkeypatch.setenv('SRL_MAXPLUS_VARIANT', variant)
+  E, R, H, W, h = shape
+  walls, rocks, level = synth.placement_batch(11, E, R, H, W, h)
+  level = (level * np.linspace(0.5, 1.5, E)).astype('float32')
+  dev = torch.device('cuda')
+  got = capi.maxplus_f32(torch.from_numpy(walls).to(dev),
+                         torch.from_numpy(rocks).to(dev),
+                         torch.from_numpy(level).to(dev)).cpu().numpy()
+  want = _oracle_maps(walls, rocks, level)
+  assert np.array_equal(got, want)
+
+
+def test_no_level_and_pose_threshold(capi):
+  """level=None, threshold=1e-4: the Observer.pose mask (observer.py:405-409)."""
+  E, R, H, W, h = 3, 2, 24, 24, 8
+  walls, rocks, _ = synth.placement_batch(5, E, R, H, W, h)
+  rocks[rocks > 0] -= np.float32(0.0624)    # push some cells under 1e-4
+  rocks = np.maximum(rocks, 0).astype('float32')
+  dev = torch.device('cuda')
+  got = capi.maxplus_f32(torch.from_numpy(walls).to(dev),
+                         torch.from_numpy(rocks).to(dev), None,
+                         threshold=1e-4).cpu().numpy()
+  for e in range(E):
+    for r in range(R):
+      live = rocks[e, r] > np.float32(1e-4)
+      for i in (0, 7, H - h):
+        for j in (0, 3, W - h):
+          lifted = walls[e, i:i + h, j:j + h] + rocks[e, r]
+          want = np.where(live, lifted, 0).max()
+          assert got[e, r, i, j] == want
+
+
+def test_full_size_config2_properties(capi):
+  """BASELINE config 2 at full size (4096 envs x 8 rotations, 32x32 / 16x16):
+  size-independent properties + an oracle check on a seeded subsample."""
+  E, R, H, W, h = 4096, 8, 32, 32, 16
+  walls, rocks, level = synth.placement_batch(0, E, R, H, W, h)
+  dev = torch.device('cuda')
+  w_d, r_d, l_d = (torch.from_numpy(x).to(dev) for x in (walls, rocks, level))
+  out = capi.maxplus_f32(w_d, r_d, l_d)
+  assert out.shape == (E, R, 17, 17)
+  # (1) translation equivariance: shifting the wall by one row shifts the map.
+  shifted = torch.roll(w_d, shifts=1, dims=1)
+  out_s = capi.maxplus_f32(shifted, r_d, l_d)
+  assert torch.equal(out_s[:, :, 1:, :], out[:, :, :-1, :])
+  # (2) monotone in the wall: raising the wall never lowers a drop height.
+  out_up = capi.maxplus_f32(w_d + 0.25, r_d, l_d)
+  assert bool((out_up >= out).all())
+  # (3) lower bound: at least the rock's own maximum over the level.
+  rock_top = (r_d / l_d[:, None, None, None]).amax(dim=(2, 3))
+  assert bool((out >= rock_top[:, :, None, None]).all())
+  # (4) idempotent launch (no state between calls).
+  assert torch.equal(out, capi.maxplus_f32(w_d, r_d, l_d))
+  # (5) oracle on a subsample of environments.
+  pick = np.random.default_rng(0).choice(E, 24, replace=False)
+  want = _oracle_maps(walls[pick], rocks[pick], level[pick])
+  assert np.array_equal(out[torch.from_numpy(pick).to(dev)].cpu().numpy(), want)
+
+
+def test_empty_batch_and_bad_arguments(capi):
+  dev = torch.device('cuda')
+  out = capi.maxplus_f32(torch.empty((0, 8, 8), device=dev),
+                         torch.empty((0, 1, 4, 4), device=dev))
+  assert out.shape == (0, 1, 5, 5)
+  with pytest.raises(TypeError):
+    capi.maxplus_f32(torch.zeros((1, 8, 8)), torch.zeros((1, 1, 4, 4)))
+  with pytest.raises(capi.SrlError):
+    capi.maxplus_f32(torch.zeros((1, 4, 4), device=dev),
+                     torch.zeros((1, 1, 8, 8), device=dev),
+                     out=torch.zeros((1, 1, 1, 1), device=dev))
