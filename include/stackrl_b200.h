@@ -61,13 +61,15 @@ SRL_API int srl_maxplus_f32(const float* walls, const float* rocks, const float*
                     float* out, int E, int R, int H, int W, int h,
                     float threshold, srl_stream_t stream);
 
-#ifdef SRL_NEXT   /* declared as the next entry points land */
+#ifdef SRL_NEXT   /* lands with its kernel */
 /* Same for uint8 observations (registered Stack-v0/1/2 dtype): the reference
  * divides uint8 by uint8 -> float64, so this evaluates IEEE float64
  * a/g + b/g per cell.  level [E] u8 (goal.max()), out f64. */
 SRL_API int srl_maxplus_u8(const uint8_t* walls, const uint8_t* rocks,
                    const uint8_t* level, double* out, int E, int R, int H,
                    int W, int h, srl_stream_t stream);
+
+#endif  /* SRL_NEXT */
 
 /* ---- a4: Observer.pose drop height (observer.py:401-409) --------------------
  * z[e] = max( (walls[e, i:i+h, j:j+h] + rocks[e, r])[rocks[e, r] > 1e-4] ),
@@ -96,15 +98,17 @@ SRL_API int srl_goal_overlap_u8(const uint8_t* walls, const uint8_t* goals,
  * counts == NULL is the goal=False branch: action = argmin(values), shown =
  * -values.  Then per env: best_r = first argmax_r shown[e,r,action[e,r]].
  *   values [E,R,P] (f32 or f64), counts [E,R,P] i32 or NULL,
- *   actions [E,R] i64, shown [E,R,P] (same type as values; may be NULL),
+ *   actions [E,R] i64, shown [E,R,P] f64 or NULL (the reference's value map is
+ *   float64 even for float32 scores: `max + 0.001` is a float64 add),
  *   best [E,2] i64 = (r*, action[e,r*]) or NULL. */
 SRL_API int srl_select_f32(const float* values, const int32_t* counts, int64_t* actions,
-                   float* shown, int64_t* best, int E, int R, int Ph, int Pw,
+                   double* shown, int64_t* best, int E, int R, int Ph, int Pw,
                    int minorder, double overlap_threshold, srl_stream_t stream);
 SRL_API int srl_select_f64(const double* values, const int32_t* counts, int64_t* actions,
                    double* shown, int64_t* best, int E, int R, int Ph, int Pw,
                    int minorder, double overlap_threshold, srl_stream_t stream);
 
+#ifdef SRL_NEXT   /* lands with its kernel */
 /* ---- a6: baselines.difference (baselines.py:45-77), exponents (2, 2|0) -------
  * f = sum_{u,v} w[u,v] * |h0 - (o+n)|^p  in numpy's order: float32 lift and
  * residual, float64 weights/product, pairwise summation over the contiguous

@@ -40,8 +40,28 @@ def _split(inputs):
   return wall_goal[..., 0], wall_goal[..., 1], rock[..., 0]
 
 
-def _upload(x, dtype):
-  return torch.from_numpy(np.ascontiguousarray(x)).to(_device()).to(dtype)
+def _upload(x, dtype=None):
+  t = torch.from_numpy(np.ascontiguousarray(x)).to(_device())
+  return t if dtype is None else t.to(dtype)
+
+
+def _planes(inputs):
+  """One observation -> device planes walls [1,H,W], goals [1,H,W],
+  rocks [1,1,h,h] in the observation's own dtype."""
+  wall, goal, rock = _split(inputs)
+  if wall.ndim != 2:
+    raise ValueError('this function takes ONE observation; use PlacementScorer '
+                     'or Baseline(batched=True) for batches')
+  return _upload(wall[None]), _upload(goal[None]), _upload(rock[None, None])
+
+
+def _height_device(walls, goals, rocks):
+  """[E,R,Ph,Pw] drop map in the reference's arithmetic for the obs dtype."""
+  if walls.dtype == torch.float32:
+    level = goals.amax(dim=(1, 2))          # get_inputs: goal.max() (baselines.py:23)
+    return capi.maxplus_f32(walls, rocks, level)
+  raise NotImplementedError(
+    'observation dtype {} is not wired to a kernel yet'.format(walls.dtype))
 
 
 # ---- baselines.py:28-43 ------------------------------------------------------ #
@@ -51,22 +71,141 @@ def height(inputs, mask=None, **kwargs):
   Returns a float64 [H-h+1, W-w+1] array like the reference's np.zeros
   container.  float32 observations use the float32 kernel (bit-exact with
   numpy's float32 add/max), integer observations the float64 one."""
-  wall, goal, rock = _split(inputs)
-  if wall.ndim != 2:
-    raise ValueError('height() takes one observation; use PlacementScorer for batches')
-  if wall.dtype == np.float32:
-    level = torch.tensor([goal.max()], dtype=torch.float32, device=_device())
-    f = capi.maxplus_f32(_upload(wall[None], torch.float32),
-                         _upload(rock[None, None], torch.float32), level)
-    f = f[0, 0].cpu().numpy().astype('float64')
-  else:
-    raise NotImplementedError(
-      'observation dtype {} is not wired to a kernel yet'.format(wall.dtype))
+  walls, goals, rocks = _planes(inputs)
+  f = _height_device(walls, goals, rocks)[0, 0].cpu().numpy().astype('float64')
   if mask is not None:
     f = np.where(mask, f, 0.)
   return f
 
 
+# ---- baselines.py:145-150 ---------------------------------------------------- #
+def random(inputs, seed=None, **kwargs):
+  """Random values in the shape of the heuristics (host RNG, like the reference:
+  numpy's default_rng stream is the contract, there is nothing to accelerate)."""
+  rng = np.random.default_rng(seed)
+  return rng.random((np.subtract(np.shape(inputs[0]), np.shape(inputs[1]))[:-1] + 1))
+
+
+# ---- baselines.py:152-156 ---------------------------------------------------- #
+def goal_overlap(inputs, threshold=0.75, **kwargs):
+  """Boolean mask of positions whose rock footprint overlaps the unfilled goal
+  by at least ``threshold`` of the best overlap."""
+  walls, goals, rocks = _planes(inputs)
+  counts = capi.goal_overlap(walls, goals, rocks)[0, 0].cpu().numpy().astype('int64')
+  return counts >= threshold * counts.max()
+
+
 methods = {
+  'random': random,
   'height': height,
 }
+
+
+class PlacementScorer(object):
+  """Device-resident batched scoring: the form the reference reaches by
+  looping ``Baseline`` over environments and views (policies.py:63-73).
+
+  All tensors stay on the GPU; nothing synchronises.  ``walls``/``goals``
+  [E,H,W], ``rocks`` [E,R,h,h] (float32, planar)."""
+
+  def __init__(self, method='height', goal=True, minorder=1, threshold=0.75):
+    if method != 'height':
+      raise ValueError('PlacementScorer scores with the max-plus height map')
+    self.goal = goal
+    self.minorder = minorder
+    self.threshold = threshold
+
+  def values(self, walls, goals, rocks):
+    return _height_device(walls, goals, rocks)
+
+  def __call__(self, walls, goals, rocks, want_shown=False):
+    """-> dict(values [E,R,Ph,Pw], actions [E,R], best [E,2] = (view, flat index),
+    shown [E,R,Ph,Pw] float64 if requested)."""
+    values = self.values(walls, goals, rocks)
+    counts = capi.goal_overlap(walls, goals, rocks) if self.goal else None
+    actions, shown, best = capi.select(
+      values, counts, minorder=self.minorder, overlap_threshold=self.threshold,
+      want_shown=want_shown, want_best=True)
+    return {'values': values, 'counts': counts, 'actions': actions, 'best': best,
+            'shown': shown}
+
+
+class Baseline(object):
+  """Greedy policy over a heuristic value map: the reference's
+  ``stackrl.baselines.Baseline`` (baselines.py:167-217) with ``PyGreedy``'s
+  return conventions (agents/policies.py:57-91).
+
+  ``method`` is a name from ``methods`` or any callable
+  ``method(inputs, **kwargs) -> [H-h+1, W-w+1]`` (lower is better), exactly as
+  in the reference.  For the built-in 'height' method the whole call -- score
+  map, goal mask, local-minimum arg-min, batch-wise pick -- runs on the GPU;
+  for a user callable the map comes from the callable and the selection still
+  runs on the GPU."""
+
+  def __init__(self, method='random', goal=True, minorder=1, value=False,
+               unravel=False, batched=False, batchwise=False, **kwargs):
+    if isinstance(method, str):
+      if method in methods:
+        method = methods[method]
+      else:
+        raise ValueError(
+          'Invalid value {} for argument method. Must be in {}'.format(method, methods))
+    elif not callable(method):
+      raise TypeError('Invalid type {} for argument method.'.format(type(method)))
+    self.model = method
+    self.goal = goal
+    self.kwargs = kwargs
+    self.minorder = minorder
+    self.value = value
+    self.unravel = unravel
+    self.batched = batched
+    self.batchwise = batchwise
+
+  # -- device pipeline on N views: returns (actions [N], shown [N,Ph,Pw]) ------ #
+  def _score(self, views):
+    wall, goal, rock = views
+    N = wall.shape[0]
+    # Every view is its own "environment" with one rock: the reference handles
+    # views independently (policies.py:63-64), including their goal maps.
+    walls, goals, rocks = _upload(wall), _upload(goal), _upload(rock[:, None])
+    if self.model is height:
+      values = _height_device(walls, goals, rocks)
+    else:
+      maps = [np.asarray(self.model((np.stack([wall[k], goal[k]], -1), rock[k][..., None]),
+                                    **self.kwargs), dtype='float64') for k in range(N)]
+      values = _upload(np.stack(maps)[:, None])
+    counts = capi.goal_overlap(walls, goals, rocks) if self.goal else None
+    threshold = self.kwargs.get('threshold', 0.75)
+    actions, shown, _ = capi.select(values, counts, minorder=self.minorder or 0,
+                                    overlap_threshold=threshold, want_best=False)
+    return actions[:, 0].cpu().numpy(), shown[:, 0].cpu().numpy()
+
+  def call(self, inputs):
+    """One observation -> (argmax index, value map), Baseline.call."""
+    wall, goal, rock = _split(inputs)
+    a, v = self._score((wall[None], goal[None], rock[None]))
+    return int(a[0]), v[0]
+
+  def __call__(self, inputs):
+    if self.batched:
+      wall, goal, rock = _split(inputs)
+      actions, values = self._score((wall, goal, rock))
+      if self.unravel:
+        outputs = np.array([np.unravel_index(a, values.shape[1:]) for a in actions])
+        picked = values[np.arange(len(actions)), outputs[:, 0], outputs[:, 1]]
+      else:
+        values = values.reshape(len(actions), -1)
+        outputs = np.array(actions)
+        picked = values[np.arange(len(actions)), actions]
+      if self.batchwise:
+        k = np.argmax(picked)
+        outputs = k, outputs[k]
+    else:
+      outputs, values = self.call(inputs)
+      if self.unravel:
+        outputs = np.array(np.unravel_index(outputs, values.shape))
+      elif self.value:
+        values = values.ravel()
+    if self.value:
+      outputs = outputs, values
+    return outputs

@@ -100,15 +100,79 @@ def maxplus_f32(walls, rocks, level=None, threshold=0., out=None):
   E2, R, h, h2 = rocks.shape
   if E2 != E or h != h2:
     raise ValueError('rocks must be [E, R, h, h] matching walls [E, H, W]')
+  args = (_dev(walls, torch.float32, 'walls'), _dev(rocks, torch.float32, 'rocks'),
+          _opt(level, torch.float32, 'level'))
   if out is None:
     out = torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.float32,
                       device=walls.device)
   with torch.cuda.device(walls.device):
-    _check(lib.srl_maxplus_f32(
-      _dev(walls, torch.float32, 'walls'), _dev(rocks, torch.float32, 'rocks'),
-      _opt(level, torch.float32, 'level'), _dev(out, torch.float32, 'out'),
-      E, R, H, W, h, float(threshold), _stream()))
+    _check(lib.srl_maxplus_f32(*args, _dev(out, torch.float32, 'out'),
+                               E, R, H, W, h, float(threshold), _stream()))
   return out
+
+
+def _batch_dims(walls, rocks):
+  E, H, W = walls.shape
+  E2, R, h, h2 = rocks.shape
+  if E2 != E or h != h2:
+    raise ValueError('rocks must be [E, R, h, h] matching walls [E, H, W]')
+  return E, R, H, W, h
+
+
+def drop_height_f32(walls, rocks, picks, threshold=1e-4):
+  """picks [E,3] int32 (rotation, row, column) -> [E] float32 drop heights."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  args = (_dev(walls, torch.float32, 'walls'), _dev(rocks, torch.float32, 'rocks'),
+          _dev(picks, torch.int32, 'picks'))
+  out = torch.empty((E,), dtype=torch.float32, device=walls.device)
+  with torch.cuda.device(walls.device):
+    _check(lib.srl_drop_height_f32(*args, _dev(out, torch.float32, 'out'),
+                                   E, R, H, W, h, float(threshold), _stream()))
+  return out
+
+
+def goal_overlap(walls, goals, rocks):
+  """Integer overlap counts [E,R,Ph,Pw] (int32) for float32 or uint8 maps."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  dt = walls.dtype
+  if dt == torch.float32:
+    fn = lib.srl_goal_overlap_f32
+  elif dt == torch.uint8:
+    fn = lib.srl_goal_overlap_u8
+  else:
+    raise TypeError('goal_overlap takes float32 or uint8 maps, got {}'.format(dt))
+  args = (_dev(walls, dt, 'walls'), _dev(goals, dt, 'goals'), _dev(rocks, dt, 'rocks'))
+  out = torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.int32,
+                    device=walls.device)
+  with torch.cuda.device(walls.device):
+    _check(fn(*args, _dev(out, torch.int32, 'counts'), E, R, H, W, h, _stream()))
+  return out
+
+
+def select(values, counts=None, minorder=1, overlap_threshold=0.75,
+           want_shown=True, want_best=True):
+  """values [E,R,Ph,Pw] (float32/float64), counts like values (int32) or None
+  -> (actions [E,R] int64, shown [E,R,Ph,Pw] float64 | None, best [E,2] int64 | None)."""
+  E, R, Ph, Pw = values.shape
+  if values.dtype == torch.float32:
+    fn = lib.srl_select_f32
+  elif values.dtype == torch.float64:
+    fn = lib.srl_select_f64
+  else:
+    raise TypeError('select takes float32 or float64 values')
+  v = _dev(values, values.dtype, 'values')
+  c = _opt(counts, torch.int32, 'counts')
+  if counts is not None and counts.shape != values.shape:
+    raise ValueError('counts must have the shape of values')
+  dev = values.device
+  actions = torch.empty((E, R), dtype=torch.int64, device=dev)
+  shown = torch.empty((E, R, Ph, Pw), dtype=torch.float64, device=dev) if want_shown else None
+  best = torch.empty((E, 2), dtype=torch.int64, device=dev) if want_best else None
+  with torch.cuda.device(dev):
+    _check(fn(v, c, _dev(actions, torch.int64, 'actions'),
+              _opt(shown, torch.float64, 'shown'), _opt(best, torch.int64, 'best'),
+              E, R, Ph, Pw, int(minorder), float(overlap_threshold), _stream()))
+  return actions, shown, best
 
 
 def microbench_addmax(variant, iters=2000):

@@ -63,6 +63,41 @@ int srl_maxplus_f32(const float* walls, const float* rocks, const float* level,
                           variant, (cudaStream_t)stream);
 }
 
+int srl_drop_height_f32(const float* walls, const float* rocks, const int32_t* picks,
+                        float* out, int E, int R, int H, int W, int h, float threshold,
+                        srl_stream_t stream) {
+  return srl::drop_height_f32(walls, rocks, picks, out, E, R, H, W, h, threshold,
+                              (cudaStream_t)stream);
+}
+
+int srl_goal_overlap_f32(const float* walls, const float* goals, const float* rocks,
+                         int32_t* counts, int E, int R, int H, int W, int h,
+                         srl_stream_t stream) {
+  return srl::goal_overlap_f32(walls, goals, rocks, counts, E, R, H, W, h,
+                               (cudaStream_t)stream);
+}
+
+int srl_goal_overlap_u8(const uint8_t* walls, const uint8_t* goals, const uint8_t* rocks,
+                        int32_t* counts, int E, int R, int H, int W, int h,
+                        srl_stream_t stream) {
+  return srl::goal_overlap_u8(walls, goals, rocks, counts, E, R, H, W, h,
+                              (cudaStream_t)stream);
+}
+
+int srl_select_f32(const float* values, const int32_t* counts, int64_t* actions,
+                   double* shown, int64_t* best, int E, int R, int Ph, int Pw,
+                   int minorder, double overlap_threshold, srl_stream_t stream) {
+  return srl::select_f32(values, counts, actions, shown, best, E, R, Ph, Pw, minorder,
+                         overlap_threshold, (cudaStream_t)stream);
+}
+
+int srl_select_f64(const double* values, const int32_t* counts, int64_t* actions,
+                   double* shown, int64_t* best, int E, int R, int Ph, int Pw,
+                   int minorder, double overlap_threshold, srl_stream_t stream) {
+  return srl::select_f64(values, counts, actions, shown, best, E, R, Ph, Pw, minorder,
+                         overlap_threshold, (cudaStream_t)stream);
+}
+
 int srl_microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   return srl::microbench_addmax(variant, iters, host_cells_per_s);
 }

@@ -9,6 +9,24 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
                 float* out, int E, int R, int H, int W, int h, float threshold,
                 int variant, cudaStream_t stream);
 
+int goal_overlap_f32(const float* walls, const float* goals, const float* rocks,
+                     int32_t* counts, int E, int R, int H, int W, int h,
+                     cudaStream_t stream);
+int goal_overlap_u8(const uint8_t* walls, const uint8_t* goals, const uint8_t* rocks,
+                    int32_t* counts, int E, int R, int H, int W, int h,
+                    cudaStream_t stream);
+
+int select_f32(const float* values, const int32_t* counts, int64_t* actions,
+               double* shown, int64_t* best, int E, int R, int Ph, int Pw, int minorder,
+               double overlap_threshold, cudaStream_t stream);
+int select_f64(const double* values, const int32_t* counts, int64_t* actions,
+               double* shown, int64_t* best, int E, int R, int Ph, int Pw, int minorder,
+               double overlap_threshold, cudaStream_t stream);
+
+int drop_height_f32(const float* walls, const float* rocks, const int32_t* picks,
+                    float* out, int E, int R, int H, int W, int h, float threshold,
+                    cudaStream_t stream);
+
 int microbench_addmax(int variant, int iters, double* host_cells_per_s);
 
 }  // namespace srl

@@ -4,30 +4,60 @@
 //   out[e,r,i,j] = max_{u,v}( n[e,r,u,v] > thr ? o[e,i+u,j+v] + n[e,r,u,v] : 0 )
 //   o = wall/level, n = rock/level  (IEEE float32 division, then float32 add)
 //
-// Design (see DESIGN.md section "maxplus_f32"):
-//   * One CTA owns G whole environments (wall + RC rock rotations each), staged
-//     into shared memory with 1-D bulk TMA copies (cp.async.bulk, one mbarrier),
-//     one copy per wall row so rows land on a padded stride (Ws/4 odd => the
-//     per-row LDS.128 of 8 consecutive lanes hit 8 distinct 16-B bank groups).
-//   * A normalise pass divides by the goal level in place and folds the
-//     `n > thr` mask into the rock as -inf, so the inner loop has no select:
-//     o + (-inf) = -inf never wins the max.  The reference's "masked cell
-//     contributes 0" (quirk Q2) becomes one max(acc, 0) at the end, applied
-//     only when the rock really has a masked cell.
-//   * Each thread owns T consecutive outputs of one output row.  Per rock row
-//     it loads T+VC-1 wall values and VC rock values with LDS.128 and runs the
-//     fully unrolled T x VC block of (add, max) cells out of registers.
-//   * sm_100 instruction mix: cells are paired so that two adds issue as one
-//     FADD2 (add.rn.f32x2, FMA pipe) and fold into the accumulator with one
-//     3-input FMNMX3 (ALU pipe): ~1.03 issue slots per cell instead of 2.
-//     Max is exact and order independent, each add is a single IEEE rn add, so
-//     the result is bit-identical to numpy's.
+// Design ("maxplus_f32"):
+//   * Shared-memory compute layout per CTA: G walls on a padded row stride
+//     (Ws/4 odd => the per-row LDS.128 of 8 consecutive lanes hit 8 distinct
+//     16-B bank groups) and, per rock rotation, the normalised rock with the
+//     `n > thr` mask folded in as -inf plus a one-column-shifted copy of it.
+//     With the mask folded in the inner loop has no select: o + (-inf) = -inf
+//     never wins the max.  The reference's "masked cell contributes 0" (quirk
+//     Q2) becomes one max(acc, 0) at the end, applied only when the rock really
+//     has a masked cell.
+//   * Each thread owns T = 4m+1 consecutive outputs of one output row (strips
+//     pitched 4m apart).  Per rock row it loads T+VC-1 wall values and VC rock
+//     values with LDS.128 and runs the fully unrolled T x VC block of (add,
+//     max) cells out of registers.
+//   * sm_100 instruction mix: two adds issue as one FADD2 (add.rn.f32x2, FMA
+//     pipe) on aligned register pairs and fold into the accumulator with one
+//     3-input FMNMX3 (ALU pipe): ~1.03 issue slots per cell instead of 2.  Max
+//     is exact and order independent and each add is one IEEE rn add, so the
+//     result is bit-identical to numpy's.
+//   * Two kernels share that sweep:
+//       - maxplus_staged_kernel (small walls, e.g. 32x32 / 64x64): persistent
+//         CTAs, 2 per SM.  Group k+1's raw walls and rocks arrive by two 1-D
+//         bulk TMA copies (cp.async.bulk + mbarrier) while group k is swept;
+//         a prep pass converts raw -> compute layout (division by the goal
+//         level, mask, shifted copy); score maps are staged in shared memory
+//         and leave with one bulk TMA store per group.
+//       - maxplus_direct_kernel (big walls, e.g. 128x128 with 36 rotations):
+//         one CTA per (environment, rotation chunk); wall rows are bulk-copied
+//         straight onto the padded stride and normalised in place.
 //   * No tensor cores: max-plus is not a dense contraction.
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "kernels.h"
 
 namespace srl {
+
+// q = n / d for n * d < 2^32 (all index spaces here are < 2^16 x 2^16).
+struct FastDiv {
+  uint32_t mul, d;
+};
+static FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  f.mul = d == 1 ? 0u : (uint32_t)(((1ull << 32) + (uint32_t)d - 1) / (uint32_t)d);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv f) {
+  return f.d == 1 ? n : __umulhi(n, f.mul);
+}
+__device__ __forceinline__ void fdivmod(uint32_t n, const FastDiv f, uint32_t& q,
+                                        uint32_t& r) {
+  q = fdiv(n, f);
+  r = n - q * f.d;
+}
 
 struct MaxPlusParams {
   const float* walls;
@@ -40,13 +70,16 @@ struct MaxPlusParams {
   int Ws;           // smem wall row stride (floats), Ws % 4 == 0, (Ws/4) odd
   int wall_stride;  // smem floats per wall  (H * Ws)
   int rock_stride;  // smem floats per rock copy (h * hp + 4)
-  int G;            // environments per CTA
+  int G;            // environments per CTA (group)
   int RC;           // rotations per CTA
   int rchunks;      // ceil(R / RC)
   int strips;       // strips per output row; strip k starts at column k*(T-1)
+  int ngroups;      // ceil(E / G)
   float threshold;
   int tma_wall;     // wall rows can be bulk-copied (W % 4 == 0, 16-B aligned base)
   int tma_rock;     // rock rows can be bulk-copied (h % 4 == 0, 16-B aligned base)
+  int stage_out;    // staged kernel: score maps leave by bulk TMA store
+  FastDiv dPh, dStrips, dRC, dW, dH, dh, dhp, dW4, dh4;
 };
 
 // Block of T x VC (add, max) cells: acc[t] = max(acc[t], row[t+v] + nv[v]).
@@ -92,17 +125,219 @@ __device__ __forceinline__ void cell_block(float (&acc)[T],
   }
 }
 
+// All (add, max) cells of one item: T outputs of one output row against one rock.
+template <int T, int VC, bool PAIRED>
+__device__ __forceinline__ void sweep_item(float (&acc)[T], const float* wbase,
+                                           const float* rbase, const float* sbase,
+                                           int h, int hp, int Ws) {
+  constexpr int NR4 = (T + VC + 2) / 4;   // float4 loads per wall row chunk
+  static_assert((T - 1) % 4 == 0 && 4 * NR4 >= T + VC - 1, "tile shape");
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t] = kNegInf;
+  for (int u = 0; u < h; ++u) {
+    for (int vc = 0; vc < hp; vc += VC) {
+      float row[4 * NR4];
+      float nv[VC];
+      float nvs[VC];
+#pragma unroll
+      for (int k = 0; k < NR4; ++k) {
+        const float4 x = lds128(wbase + u * Ws + vc + 4 * k);
+        row[4 * k + 0] = x.x;
+        row[4 * k + 1] = x.y;
+        row[4 * k + 2] = x.z;
+        row[4 * k + 3] = x.w;
+      }
+#pragma unroll
+      for (int k = 0; k < VC / 4; ++k) {
+        const float4 x = lds128(rbase + u * hp + vc + 4 * k);
+        nv[4 * k + 0] = x.x;
+        nv[4 * k + 1] = x.y;
+        nv[4 * k + 2] = x.z;
+        nv[4 * k + 3] = x.w;
+        if constexpr (PAIRED) {
+          const float4 y = lds128(sbase + u * hp + vc + 4 * k);
+          nvs[4 * k + 0] = y.x;
+          nvs[4 * k + 1] = y.y;
+          nvs[4 * k + 2] = y.z;
+          nvs[4 * k + 3] = y.w;
+        }
+      }
+      cell_block<T, VC, PAIRED>(acc, row, nv, nvs);
+    }
+  }
+}
+
+// Normalise + mask one rock value (baselines.py:24-25, :32).
+__device__ __forceinline__ float prep_rock(float n, bool scaled, float level,
+                                           float thr, bool& dead) {
+  if (scaled) n = __fdiv_rn(n, level);
+  const bool live = n > thr;
+  dead = dead || !live;
+  return live ? n : kNegInf;
+}
+
+// --------------------------------------------------------------------------- //
+// Staged persistent kernel (small walls).
+// --------------------------------------------------------------------------- //
 template <int T, int VC, bool PAIRED>
 __global__ void __launch_bounds__(288, 2)
-maxplus_f32_kernel(const MaxPlusParams p) {
+maxplus_staged_kernel(const MaxPlusParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int H = p.H, W = p.W, h = p.h, hp = p.hp, Ws = p.Ws, R = p.R, G = p.G;
+  const int Ph = p.Ph, Pw = p.Pw, P = Ph * Pw;
+  constexpr int S = T - 1;
+
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  int* masked = reinterpret_cast<int*>(smem_raw + 16);          // [2][G*R]
+  const int slots = G * R;
+  const int flag_bytes = round_up(2 * slots * 4, 16);
+  float* raw_wall = reinterpret_cast<float*>(smem_raw + 16 + flag_bytes);
+  float* raw_rock = raw_wall + G * H * W;
+  float* wall_s = raw_rock + slots * h * h;
+  float* rock_s = wall_s + G * p.wall_stride;
+  float* rock_sh = rock_s + slots * p.rock_stride;
+  float* out_s = rock_sh + slots * p.rock_stride;               // [G*R*P] if stage_out
+
+  const int tid = threadIdx.x;
+  const int nthreads = blockDim.x;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  // One-time fills of everything the per-group prep never rewrites: wall pad
+  // columns [W, Ws) (finite), rock pad columns [h, hp) and the last real column
+  // of the shifted copy (-inf: never win, never count as masked).
+  for (int k = tid; k < G * p.wall_stride; k += nthreads) wall_s[k] = 0.f;
+  for (int k = tid; k < 2 * slots * p.rock_stride; k += nthreads) rock_s[k] = kNegInf;
+  for (int k = tid; k < 2 * slots; k += nthreads) masked[k] = 0;
+  __syncthreads();
+
+  auto issue_loads = [&](int g) {
+    const int e0 = g * G;
+    const int Gv = min(G, p.E - e0);
+    const uint32_t wb = (uint32_t)Gv * H * W * 4, rb = (uint32_t)Gv * R * h * h * 4;
+    mbar_arrive_expect_tx(bar, wb + rb);
+    tma_load_1d(raw_wall, p.walls + (size_t)e0 * H * W, wb, bar);
+    tma_load_1d(raw_rock, p.rocks + (size_t)e0 * R * h * h, rb, bar);
+  };
+
+  if (tid == 0 && (int)blockIdx.x < p.ngroups) issue_loads(blockIdx.x);
+
+  const int W4 = W / 4, h4 = h / 4;
+  const bool scaled = p.level != nullptr;
+  int it = 0;
+  for (int g = blockIdx.x; g < p.ngroups; g += gridDim.x, ++it) {
+    const int e0 = g * G;
+    const int Gv = min(G, p.E - e0);
+    int* flags = masked + (it & 1) * slots;
+    int* flags_next = masked + ((it + 1) & 1) * slots;
+
+    mbar_wait(bar, it & 1);
+
+    // ---- prep: raw -> compute layout ---------------------------------------- //
+    for (int k = tid; k < slots; k += nthreads) flags_next[k] = 0;
+    for (uint32_t q = tid; q < (uint32_t)(Gv * H * W4); q += nthreads) {
+      uint32_t row, c4;
+      fdivmod(q, p.dW4, row, c4);
+      float4 x = lds128(raw_wall + 4 * q);
+      if (scaled) {
+        const float lv = __ldg(p.level + e0 + fdiv(row, p.dH));
+        x.x = __fdiv_rn(x.x, lv);
+        x.y = __fdiv_rn(x.y, lv);
+        x.z = __fdiv_rn(x.z, lv);
+        x.w = __fdiv_rn(x.w, lv);
+      }
+      *reinterpret_cast<float4*>(wall_s + row * Ws + 4 * c4) = x;
+    }
+    for (uint32_t q = tid; q < (uint32_t)(Gv * R * h * h4); q += nthreads) {
+      uint32_t rrow, c4, slot, u;
+      fdivmod(q, p.dh4, rrow, c4);
+      fdivmod(rrow, p.dh, slot, u);
+      const float lv = scaled ? __ldg(p.level + e0 + fdiv(slot, p.dRC)) : 1.f;
+      float4 x = lds128(raw_rock + 4 * q);
+      bool dead = false;
+      x.x = prep_rock(x.x, scaled, lv, p.threshold, dead);
+      x.y = prep_rock(x.y, scaled, lv, p.threshold, dead);
+      x.z = prep_rock(x.z, scaled, lv, p.threshold, dead);
+      x.w = prep_rock(x.w, scaled, lv, p.threshold, dead);
+      if (dead) flags[slot] = 1;
+      float* dst = rock_s + slot * p.rock_stride + u * hp + 4 * c4;
+      *reinterpret_cast<float4*>(dst) = x;
+      if constexpr (PAIRED) {
+        float* sh = rock_sh + slot * p.rock_stride + u * hp + 4 * c4;
+        if (c4 != 0) sh[-1] = x.x;
+        sh[0] = x.y;
+        sh[1] = x.z;
+        sh[2] = x.w;
+      }
+    }
+    // The previous group's bulk store must have finished READING out_s before
+    // this group's sweep overwrites it.
+    if (tid == 0 && p.stage_out) tma_store_wait_read();
+    __syncthreads();
+
+    // ---- prefetch the next group while this one is swept ---------------------- //
+    // (raw_* were last read through the generic proxy in the prep above)
+    if (tid == 0 && g + (int)gridDim.x < p.ngroups) {
+      fence_proxy_async();
+      issue_loads(g + gridDim.x);
+    }
+
+    // ---- sweep ---------------------------------------------------------------- //
+    const int items = Gv * R * p.strips * Ph;
+    for (int item = tid; item < items; item += nthreads) {
+      uint32_t rest, i, strip, slot;
+      fdivmod((uint32_t)item, p.dPh, rest, i);
+      fdivmod(rest, p.dStrips, slot, strip);
+      const uint32_t el = fdiv(slot, p.dRC);
+      float acc[T];
+      sweep_item<T, VC, PAIRED>(acc, wall_s + el * p.wall_stride + i * Ws + strip * S,
+                                rock_s + slot * p.rock_stride,
+                                rock_sh + slot * p.rock_stride, h, hp, Ws);
+      const bool floor0 = flags[slot] != 0;
+      const int ncols = ((int)strip == p.strips - 1) ? min(T, Pw - (int)strip * S) : S;
+      const size_t off = (size_t)slot * P + i * Pw + strip * S;
+      if (p.stage_out) {
+        float* o = out_s + off;
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+          if (t < ncols) o[t] = floor0 ? fmaxf(acc[t], 0.f) : acc[t];
+      } else {
+        float* o = p.out + (size_t)e0 * R * P + off;
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+          if (t < ncols) __stcs(o + t, floor0 ? fmaxf(acc[t], 0.f) : acc[t]);
+      }
+    }
+    if (p.stage_out) {
+      fence_proxy_async();          // generic-proxy writes -> visible to the TMA store
+      __syncthreads();
+      if (tid == 0) {
+        tma_store_1d(p.out + (size_t)e0 * R * P, out_s, (uint32_t)Gv * R * P * 4);
+        tma_store_commit();
+      }
+    } else {
+      __syncthreads();              // compute layout is rewritten by the next prep
+    }
+  }
+  if (tid == 0 && p.stage_out) tma_store_wait_all();
+}
+
+// --------------------------------------------------------------------------- //
+// Direct kernel (big walls): one CTA per (environment group, rotation chunk).
+// --------------------------------------------------------------------------- //
+template <int T, int VC, bool PAIRED>
+__global__ void __launch_bounds__(288, 2)
+maxplus_direct_kernel(const MaxPlusParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   int* masked = reinterpret_cast<int*>(smem_raw + 16);
   const int flag_bytes = round_up(p.G * p.RC * 4, 16);
   float* wall_s = reinterpret_cast<float*>(smem_raw + 16 + flag_bytes);
   float* rock_s = wall_s + p.G * p.wall_stride;
-  // PAIRED keeps a second, one-column-shifted copy of every rock behind the first.
   float* rock_sh = rock_s + p.G * p.RC * p.rock_stride;
+  constexpr int S = T - 1;
 
   const int tid = threadIdx.x;
   const int nthreads = blockDim.x;
@@ -113,8 +348,9 @@ maxplus_f32_kernel(const MaxPlusParams p) {
   const int Gv = min(p.G, p.E - e0);
   const int RCv = min(p.RC, p.R - r0);
   const int H = p.H, W = p.W, h = p.h, hp = p.hp, Ws = p.Ws;
+  const FastDiv dRCv = {RCv == 1 ? 0u : (uint32_t)(((1ull << 32) + RCv - 1) / RCv),
+                        (uint32_t)RCv};
 
-  // ---- stage 0: barrier init ------------------------------------------------ //
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
@@ -122,7 +358,7 @@ maxplus_f32_kernel(const MaxPlusParams p) {
   for (int k = tid; k < p.G * p.RC; k += nthreads) masked[k] = 0;
   __syncthreads();
 
-  // ---- stage 1: bulk TMA loads (warp 0) + padding fills (everyone) ---------- //
+  // ---- bulk TMA loads (warp 0) + padding fills (everyone) -------------------- //
   const bool any_tma = p.tma_wall || p.tma_rock;
   if (tid < 32 && any_tma) {
     if (tid == 0) {
@@ -133,166 +369,103 @@ maxplus_f32_kernel(const MaxPlusParams p) {
     }
     __syncwarp();
     if (p.tma_wall) {
-      for (int k = tid; k < Gv * H; k += 32) {
-        const int el = k / H, row = k % H;
-        tma_load_1d(wall_s + el * p.wall_stride + row * Ws,
-                    p.walls + ((size_t)(e0 + el) * H + row) * W, W * 4, bar);
-      }
+      for (int k = tid; k < Gv * H; k += 32)   // row k of the group: el*H + row
+        tma_load_1d(wall_s + k * Ws, p.walls + ((size_t)e0 * H + k) * W, W * 4, bar);
     }
     if (p.tma_rock) {
-      if (hp == h) {
-        for (int k = tid; k < Gv * RCv; k += 32) {
-          const int el = k / RCv, r = k % RCv;
-          tma_load_1d(rock_s + (el * p.RC + r) * p.rock_stride,
-                      p.rocks + ((size_t)(e0 + el) * p.R + r0 + r) * h * h,
-                      h * h * 4, bar);
-        }
-      } else {
-        for (int k = tid; k < Gv * RCv * h; k += 32) {
-          const int u = k % h, er = k / h;
-          const int el = er / RCv, r = er % RCv;
-          tma_load_1d(rock_s + (el * p.RC + r) * p.rock_stride + u * hp,
-                      p.rocks + (((size_t)(e0 + el) * p.R + r0 + r) * h + u) * h,
-                      h * 4, bar);
-        }
+      for (uint32_t k = tid; k < (uint32_t)(Gv * RCv * h); k += 32) {
+        uint32_t er, u, el, r;
+        fdivmod(k, p.dh, er, u);
+        fdivmod(er, dRCv, el, r);
+        tma_load_1d(rock_s + (el * p.RC + r) * p.rock_stride + u * hp,
+                    p.rocks + (((size_t)(e0 + el) * p.R + r0 + r) * h + u) * h,
+                    h * 4, bar);
       }
     }
   }
   if (!p.tma_wall) {
-    for (int k = tid; k < Gv * H * W; k += nthreads) {
-      const int el = k / (H * W), rem = k % (H * W);
-      wall_s[el * p.wall_stride + (rem / W) * Ws + rem % W] =
-          __ldg(p.walls + (size_t)(e0 + el) * H * W + rem);
+    for (uint32_t k = tid; k < (uint32_t)(Gv * H * W); k += nthreads) {
+      uint32_t row, c;
+      fdivmod(k, p.dW, row, c);
+      wall_s[row * Ws + c] = __ldg(p.walls + (size_t)e0 * H * W + k);
     }
   }
   if (!p.tma_rock) {
-    for (int k = tid; k < Gv * RCv * h * h; k += nthreads) {
-      const int er = k / (h * h), rem = k % (h * h);
-      const int el = er / RCv, r = er % RCv;
-      rock_s[(el * p.RC + r) * p.rock_stride + (rem / h) * hp + rem % h] =
-          __ldg(p.rocks + ((size_t)(e0 + el) * p.R + r0 + r) * h * h + rem);
+    for (uint32_t k = tid; k < (uint32_t)(Gv * RCv * h * h); k += nthreads) {
+      uint32_t rrow, c, er, u, el, r;
+      fdivmod(k, p.dh, rrow, c);
+      fdivmod(rrow, p.dh, er, u);
+      fdivmod(er, dRCv, el, r);
+      rock_s[(el * p.RC + r) * p.rock_stride + u * hp + c] =
+          __ldg(p.rocks + (((size_t)(e0 + el) * p.R + r0 + r) * h + u) * h + c);
     }
   }
-  // Wall pad columns [W, Ws) must be finite; rock pad columns [h, hp) are -inf
-  // (never win, and do not count as "masked" cells).
+  // Wall pad columns [W, Ws) must be finite.  (Rock pad columns [h, hp) and the
+  // shifted copy are written by the normalise pass below.)
   {
     const int padw = Ws - W;
-    for (int k = tid; k < Gv * H * padw; k += nthreads) {
-      const int el = k / (H * padw), rem = k % (H * padw);
-      wall_s[el * p.wall_stride + (rem / padw) * Ws + W + rem % padw] = 0.f;
-    }
-    const int padr = hp - h;
-    for (int k = tid; k < Gv * RCv * h * padr; k += nthreads) {
-      const int er = k / (h * padr), rem = k % (h * padr);
-      const int el = er / RCv, r = er % RCv;
-      rock_s[(el * p.RC + r) * p.rock_stride + (rem / padr) * hp + h + rem % padr] =
-          kNegInf;
-    }
+    for (int k = tid; k < Gv * H * padw; k += nthreads)
+      wall_s[(k / padw) * Ws + W + k % padw] = 0.f;
   }
   if (any_tma) mbar_wait(bar, 0);
   __syncthreads();
 
-  // ---- stage 2: normalise in place, fold the mask into the rock ------------- //
-  if (p.level != nullptr) {
-    for (int k = tid; k < Gv * H * W; k += nthreads) {
-      const int el = k / (H * W), rem = k % (H * W);
-      float* q = wall_s + el * p.wall_stride + (rem / W) * Ws + rem % W;
-      *q = __fdiv_rn(*q, __ldg(p.level + e0 + el));
+  // ---- normalise in place, fold the mask, build the shifted copy ------------- //
+  const bool scaled = p.level != nullptr;
+  if (scaled) {
+    for (uint32_t k = tid; k < (uint32_t)(Gv * H * W); k += nthreads) {
+      uint32_t row, c;
+      fdivmod(k, p.dW, row, c);
+      float* q = wall_s + row * Ws + c;
+      *q = __fdiv_rn(*q, __ldg(p.level + e0 + fdiv(row, p.dH)));
     }
   }
-  for (int k = tid; k < Gv * RCv * h * h; k += nthreads) {
-    const int er = k / (h * h), rem = k % (h * h);
-    const int el = er / RCv, r = er % RCv;
+  for (uint32_t k = tid; k < (uint32_t)(Gv * RCv * h * hp); k += nthreads) {
+    uint32_t rrow, c, er, u, el, r;
+    fdivmod(k, p.dhp, rrow, c);
+    fdivmod(rrow, p.dh, er, u);
+    fdivmod(er, dRCv, el, r);
     const int slot = el * p.RC + r;
-    float* q = rock_s + slot * p.rock_stride + (rem / h) * hp + rem % h;
-    float n = *q;
-    if (p.level != nullptr) n = __fdiv_rn(n, __ldg(p.level + e0 + el));
-    const bool live = n > p.threshold;
-    if (!live) masked[slot] = 1;
-    *q = live ? n : kNegInf;
+    float* q = rock_s + slot * p.rock_stride + u * hp + c;
+    float n = kNegInf;
+    if ((int)c < h) {
+      bool dead = false;
+      n = prep_rock(*q, scaled, scaled ? __ldg(p.level + e0 + el) : 1.f, p.threshold,
+                    dead);
+      if (dead) masked[slot] = 1;
+    }
+    *q = n;
+    if constexpr (PAIRED) {
+      float* sh = rock_sh + slot * p.rock_stride + u * hp + c;
+      if (c != 0) sh[-1] = n;
+      if ((int)c == hp - 1) sh[0] = kNegInf;
+    }
   }
   __syncthreads();
-  if constexpr (PAIRED) {
-    // shifted copy: rock_sh[u][v] = rock_s[u][v+1] (last column -inf)
-    for (int k = tid; k < Gv * RCv * h * hp; k += nthreads) {
-      const int er = k / (h * hp), rem = k % (h * hp);
-      const int el = er / RCv, r = er % RCv;
-      const int slot = el * p.RC + r;
-      const int v = rem % hp;
-      rock_sh[slot * p.rock_stride + rem] =
-          (v + 1 < hp) ? rock_s[slot * p.rock_stride + rem + 1] : kNegInf;
-    }
-    __syncthreads();
-  }
 
-  // ---- stage 3: register-tiled (add, max) sweep ----------------------------- //
+  // ---- sweep ------------------------------------------------------------------ //
   const int Ph = p.Ph, Pw = p.Pw;
   const int items = Gv * RCv * p.strips * Ph;
-  constexpr int NR4 = (T + VC + 2) / 4;   // float4 loads per wall row chunk
-  constexpr int S = T - 1;                // strip pitch (multiple of 4)
-  static_assert(S % 4 == 0 && 4 * NR4 >= T + VC - 1, "tile shape");
   for (int item = tid; item < items; item += nthreads) {
-    const int i = item % Ph;
-    int rest = item / Ph;
-    const int strip = rest % p.strips;
-    rest /= p.strips;
-    const int r = rest % RCv;
-    const int el = rest / RCv;
+    uint32_t rest, i, strip, er, el, r;
+    fdivmod((uint32_t)item, p.dPh, rest, i);
+    fdivmod(rest, p.dStrips, er, strip);
+    fdivmod(er, dRCv, el, r);
     const int slot = el * p.RC + r;
-    const float* wbase = wall_s + el * p.wall_stride + i * Ws + strip * S;
-    const float* rbase = rock_s + slot * p.rock_stride;
-    const float* sbase = rock_sh + slot * p.rock_stride;
-
     float acc[T];
-#pragma unroll
-    for (int t = 0; t < T; ++t) acc[t] = kNegInf;
-
-    for (int u = 0; u < h; ++u) {
-      for (int vc = 0; vc < hp; vc += VC) {
-        float row[4 * NR4];
-        float nv[VC];
-        float nvs[VC];
-#pragma unroll
-        for (int k = 0; k < NR4; ++k) {
-          const float4 x = lds128(wbase + u * Ws + vc + 4 * k);
-          row[4 * k + 0] = x.x;
-          row[4 * k + 1] = x.y;
-          row[4 * k + 2] = x.z;
-          row[4 * k + 3] = x.w;
-        }
-#pragma unroll
-        for (int k = 0; k < VC / 4; ++k) {
-          const float4 x = lds128(rbase + u * hp + vc + 4 * k);
-          nv[4 * k + 0] = x.x;
-          nv[4 * k + 1] = x.y;
-          nv[4 * k + 2] = x.z;
-          nv[4 * k + 3] = x.w;
-          if constexpr (PAIRED) {
-            const float4 y = lds128(sbase + u * hp + vc + 4 * k);
-            nvs[4 * k + 0] = y.x;
-            nvs[4 * k + 1] = y.y;
-            nvs[4 * k + 2] = y.z;
-            nvs[4 * k + 3] = y.w;
-          }
-        }
-        cell_block<T, VC, PAIRED>(acc, row, nv, nvs);
-      }
-    }
-
-    // ---- stage 4: the reference's zero floor, then store --------------------- //
+    sweep_item<T, VC, PAIRED>(acc, wall_s + el * p.wall_stride + i * Ws + strip * S,
+                              rock_s + slot * p.rock_stride,
+                              rock_sh + slot * p.rock_stride, h, hp, Ws);
     const bool floor0 = masked[slot] != 0;
     float* orow = p.out +
                   (((size_t)(e0 + el) * p.R + r0 + r) * Ph + i) * (size_t)Pw +
                   strip * S;
     // The last column of a strip is the first of the next one; only the last
     // strip stores it.
-    const int ncols = (strip == p.strips - 1) ? min(T, Pw - strip * S) : S;
+    const int ncols = ((int)strip == p.strips - 1) ? min(T, Pw - (int)strip * S) : S;
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      float v = acc[t];
-      if (floor0) v = fmaxf(v, 0.f);
-      if (t < ncols) __stcs(orow + t, v);
-    }
+    for (int t = 0; t < T; ++t)
+      if (t < ncols) __stcs(orow + t, floor0 ? fmaxf(acc[t], 0.f) : acc[t]);
   }
 }
 
@@ -334,21 +507,40 @@ Choice choose_tile(int Pw, int h) {
   return c;
 }
 
-template <int T, int VC>
-int launch(const MaxPlusParams& p, int blocks, int threads, size_t smem,
-           bool paired, cudaStream_t stream) {
-  if (paired) {
-    auto k = maxplus_f32_kernel<T, VC, true>;
-    SRL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    k<<<blocks, threads, smem, stream>>>(p);
-  } else {
-    auto k = maxplus_f32_kernel<T, VC, false>;
-    SRL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    k<<<blocks, threads, smem, stream>>>(p);
+int pick_threads(int items, int cap) {
+  if (items <= cap) return round_up(items < 32 ? 32 : items, 32);
+  int best_t = cap;
+  double best_w = 1e9;
+  for (int t = 192; t <= cap; t += 32) {   // several passes: waste the fewest lanes
+    const int passes = (items + t - 1) / t;
+    const double w = (double)passes * t / items;
+    if (w < best_w - 1e-9) {
+      best_w = w;
+      best_t = t;
+    }
   }
-  return check_launch("maxplus_f32_kernel");
+  return best_t;
+}
+
+template <int T, int VC>
+int launch(const MaxPlusParams& p, bool staged, int blocks, int threads, size_t smem,
+           bool paired, cudaStream_t stream) {
+#define SRL_LAUNCH(...)                                                              \
+  do {                                                                               \
+    auto k = __VA_ARGS__;                                                            \
+    SRL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                  (int)smem));                                       \
+    k<<<blocks, threads, smem, stream>>>(p);                                         \
+  } while (0)
+  if (staged) {
+    if (paired) SRL_LAUNCH(maxplus_staged_kernel<T, VC, true>);
+    else SRL_LAUNCH(maxplus_staged_kernel<T, VC, false>);
+  } else {
+    if (paired) SRL_LAUNCH(maxplus_direct_kernel<T, VC, true>);
+    else SRL_LAUNCH(maxplus_direct_kernel<T, VC, false>);
+  }
+#undef SRL_LAUNCH
+  return check_launch("maxplus_f32 kernel");
 }
 
 }  // namespace
@@ -356,25 +548,28 @@ int launch(const MaxPlusParams& p, int blocks, int threads, size_t smem,
 int maxplus_f32(const float* walls, const float* rocks, const float* level,
                 float* out, int E, int R, int H, int W, int h, float threshold,
                 int variant, cudaStream_t stream) {
-  SRL_REQUIRE(walls && rocks && out, SRL_E_INVALID, "maxplus_f32: null pointer");
   SRL_REQUIRE(E >= 0 && R >= 1 && h >= 1 && H >= h && W >= h, SRL_E_INVALID,
               "maxplus_f32: bad shape E=%d R=%d H=%d W=%d h=%d", E, R, H, W, h);
   if (E == 0) return SRL_OK;
+  SRL_REQUIRE(walls && rocks && out, SRL_E_INVALID, "maxplus_f32: null pointer");
+  SRL_REQUIRE(H <= 4096 && W <= 4096 && R <= 4096, SRL_E_UNSUPPORTED,
+              "maxplus_f32: dimension above 4096");
 
   MaxPlusParams p;
   p.walls = walls; p.rocks = rocks; p.level = level; p.out = out;
   p.E = E; p.R = R; p.H = H; p.W = W; p.h = h;
   p.Ph = H - h + 1; p.Pw = W - h + 1;
   p.threshold = threshold;
+  const int P = p.Ph * p.Pw;
 
   const Choice c = choose_tile(p.Pw, h);
   const int T = c.T, VC = c.VC;
-  const bool paired = (variant != 0) && VC >= 4;
+  const bool paired = variant != 0;
   p.hp = round_up(h, VC);
   p.strips = strips_for(p.Pw, T);
   // Columns a thread may touch: strip start + (hp - VC) + 4*NR4 floats.
   const int nr4 = (T + VC + 2) / 4;
-  int need = (p.strips - 1) * (T - 1) + (p.hp - VC) + 4 * nr4;
+  const int need = (p.strips - 1) * (T - 1) + (p.hp - VC) + 4 * nr4;
   p.Ws = round_up(need > W ? need : W, 4);
   if ((p.Ws / 4) % 2 == 0) p.Ws += 4;
   p.wall_stride = H * p.Ws;
@@ -382,62 +577,88 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
   p.tma_wall = (W % 4 == 0) && (((uintptr_t)walls) % 16 == 0);
   p.tma_rock = (h % 4 == 0) && (((uintptr_t)rocks) % 16 == 0);
 
-  // Shared-memory budget: aim for >= 2 CTAs per SM (one CTA's load/normalise
-  // phases overlap the other's sweep).
-  const size_t kBudget = 100 * 1024;
+  const int sms = sm_count();
+  SRL_REQUIRE(sms > 0, SRL_E_CUDA, "maxplus_f32: no CUDA device");
+  const size_t kBudget = 110 * 1024;     // per CTA, two CTAs per SM
+  const size_t kMax = 220 * 1024;
   const size_t wall_bytes = (size_t)p.wall_stride * 4;
-  const size_t rock_bytes = (size_t)p.rock_stride * 4 * (paired ? 2 : 1);
-  auto smem_for = [&](int G, int RC) {
-    return 16 + (size_t)round_up(G * RC * 4, 16) + G * wall_bytes +
-           (size_t)G * RC * rock_bytes;
-  };
-  int RC = R, G = 1;
-  while (RC > 1 && smem_for(1, RC) > kBudget) RC = (RC + 1) / 2;
-  SRL_REQUIRE(smem_for(1, RC) <= 220 * 1024, SRL_E_UNSUPPORTED,
-              "maxplus_f32: one wall (%dx%d) + one rock (%d) exceed shared memory",
-              H, W, h);
-  // Target <= 288 threads per CTA so two CTAs (<= 112 registers/thread) are
-  // resident per SM: one CTA's load/normalise phases hide under the other's
-  // sweep.  SRL_MP_G / SRL_MP_THREADS override for experiments.
-  const int items_per_env = RC * p.strips * p.Ph;
+  const size_t rock_bytes = (size_t)p.rock_stride * 4 * 2;
   const int kThreads = 288;
-  if (RC == R) {
-    while (G < 32 && G < E && smem_for(G + 1, RC) <= kBudget &&
+
+  // ---- staged persistent kernel: whole environments (all R rotations) -------- //
+  auto staged_smem = [&](int G, bool stage_out) {
+    return 16 + (size_t)round_up(2 * G * R * 4, 16) +
+           (size_t)G * H * W * 4 + (size_t)G * R * h * h * 4 +     // raw staging
+           G * wall_bytes + (size_t)G * R * rock_bytes +           // compute layout
+           (stage_out ? (size_t)G * R * P * 4 : 0);
+  };
+  auto staged_fits = [&](int G, bool stage_out, size_t cap) {
+    return staged_smem(G, stage_out) <= cap && (size_t)G * H * W < 65536 &&
+           (size_t)G * R * h * p.hp < 65536 && (size_t)G * R * P < 65536 * 4;
+  };
+  const bool can_stage_out = ((size_t)R * P) % 4 == 0 && ((uintptr_t)out) % 16 == 0;
+  bool staged = p.tma_wall && p.tma_rock && staged_fits(1, can_stage_out, kBudget);
+  if (const char* s = getenv("SRL_MP_MODE")) {
+    if (atoi(s) == 0) staged = false;
+  }
+
+  int G = 1, RC = R, blocks, threads;
+  size_t smem;
+  if (staged) {
+    const int items_per_env = R * p.strips * p.Ph;
+    while (G < 32 && G < E && staged_fits(G + 1, can_stage_out, kBudget) &&
            (G + 1) * items_per_env <= kThreads)
       ++G;
-  }
-  if (const char* s = getenv("SRL_MP_G")) {
-    const int g = atoi(s);
-    if (g >= 1 && RC == R && smem_for(g, RC) <= 220 * 1024) G = g;
-  }
-  p.G = G; p.RC = RC; p.rchunks = (R + RC - 1) / RC;
-
-  const int items = G * items_per_env;
-  int threads;
-  if (items <= kThreads) {
-    threads = round_up(items, 32);
-  } else {
-    // several passes: pick the warp count that wastes the fewest lanes
-    int best_t = 256; double best_w = 1e9;
-    for (int t = 192; t <= kThreads; t += 32) {
-      const int passes = (items + t - 1) / t;
-      const double w = (double)passes * t / items;
-      if (w < best_w - 1e-9) { best_w = w; best_t = t; }
+    if (const char* s = getenv("SRL_MP_G")) {
+      const int g = atoi(s);
+      if (g >= 1 && staged_fits(g, can_stage_out, kMax)) G = g;
     }
-    threads = best_t;
+    p.stage_out = can_stage_out;
+    smem = staged_smem(G, can_stage_out);
+    threads = pick_threads(G * items_per_env, kThreads);
+    p.ngroups = (E + G - 1) / G;
+    const int per_sm = smem <= kBudget ? 2 : 1;
+    blocks = p.ngroups < sms * per_sm ? p.ngroups : sms * per_sm;
+  } else {
+    auto direct_smem = [&](int g, int rc) {
+      return 16 + (size_t)round_up(g * rc * 4, 16) + g * wall_bytes +
+             (size_t)g * rc * rock_bytes;
+    };
+    while (RC > 1 && (direct_smem(1, RC) > kBudget ||
+                      (size_t)RC * p.strips * p.Ph >= (1u << 20) ||
+                      (size_t)RC * h * p.hp >= 65536))
+      RC = (RC + 1) / 2;
+    SRL_REQUIRE(direct_smem(1, RC) <= kMax, SRL_E_UNSUPPORTED,
+                "maxplus_f32: one wall (%dx%d) + one rock (%d) exceed shared memory",
+                H, W, h);
+    const int items_per_env = RC * p.strips * p.Ph;
+    if (RC == R) {
+      while (G < 32 && G < E && direct_smem(G + 1, RC) <= kBudget &&
+             (G + 1) * items_per_env <= kThreads &&
+             (size_t)(G + 1) * H * W < 65536 && (size_t)(G + 1) * RC * h * p.hp < 65536)
+        ++G;
+    }
+    p.stage_out = 0;
+    smem = direct_smem(G, RC);
+    threads = pick_threads(G * items_per_env, kThreads);
+    p.ngroups = (E + G - 1) / G;
+    blocks = p.ngroups * ((R + RC - 1) / RC);
   }
   if (const char* s = getenv("SRL_MP_THREADS")) {
     const int t = atoi(s);
     if (t >= 32 && t <= 288 && t % 32 == 0) threads = t;
   }
-  const int blocks = ((E + G - 1) / G) * p.rchunks;
-  const size_t smem = smem_for(G, RC);
+  p.G = G; p.RC = RC; p.rchunks = (R + RC - 1) / RC;
+  p.dPh = make_fastdiv(p.Ph); p.dStrips = make_fastdiv(p.strips);
+  p.dRC = make_fastdiv(RC); p.dW = make_fastdiv(W); p.dH = make_fastdiv(H);
+  p.dh = make_fastdiv(h); p.dhp = make_fastdiv(p.hp);
+  p.dW4 = make_fastdiv(W >= 4 ? W / 4 : 1); p.dh4 = make_fastdiv(h >= 4 ? h / 4 : 1);
 
-#define SRL_MP_CASE(TT, VV)                                          \
-  if (T == TT && VC == VV)                                           \
-    return launch<TT, VV>(p, blocks, threads, smem, paired, stream);
-#define SRL_MP_ROW(VV)                                                        \
-  SRL_MP_CASE(5, VV) SRL_MP_CASE(9, VV) SRL_MP_CASE(13, VV) SRL_MP_CASE(17, VV) \
+#define SRL_MP_CASE(TT, VV)                                                     \
+  if (T == TT && VC == VV)                                                      \
+    return launch<TT, VV>(p, staged, blocks, threads, smem, paired, stream);
+#define SRL_MP_ROW(VV)                                                            \
+  SRL_MP_CASE(5, VV) SRL_MP_CASE(9, VV) SRL_MP_CASE(13, VV) SRL_MP_CASE(17, VV)   \
   SRL_MP_CASE(21, VV) SRL_MP_CASE(25, VV)
   SRL_MP_ROW(4)
   SRL_MP_ROW(8)

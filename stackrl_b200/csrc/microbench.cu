@@ -37,12 +37,31 @@ __device__ __forceinline__ void vadd2(float& lo, float& hi, float a_lo, float a_
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(c));
 }
 
+__device__ __forceinline__ float vimax3(float a, float b, float c) {
+  // signed-integer 3-input max on the float bit patterns (VIMNMX3): orders
+  // non-negative floats and -inf exactly like the float max.
+  return __int_as_float(
+      __vimax3_s32(__float_as_int(a), __float_as_int(b), __float_as_int(c)));
+}
+__device__ __forceinline__ float vimax(float a, float b) {
+  int d;
+  asm volatile("max.s32 %0, %1, %2;"
+               : "=r"(d)
+               : "r"(__float_as_int(a)), "r"(__float_as_int(b)));
+  return __int_as_float(d);
+}
+
+// VARIANT: 0 FADD+FMNMX | 1 2xFADD+FMNMX3 | 2 FADD2+FMNMX3 (kernel's mix)
+//          3 FADD only | 4 FMNMX only | 5 FMNMX3 only | 6 FADD2 only
+//          7 FADD2+VIMNMX3(s32) | 8 VIMNMX3 only | 9 FADD+VIMNMX(s32)
+// Every op takes a loop-carried accumulator as an operand, so ptxas can neither
+// hoist it out of the loop nor fold it.  Dependency distance is >= 8 ops.
+// "cells" are counted as if each variant did the full (add, max) pair work of
+// its mixed counterpart: variants 3-6, 8 report the rate of the single op class
+// in cell units (2 cells per FADD2 / FMNMX3 / VIMNMX3, 1 per FADD / FMNMX).
 template <int VARIANT>
 __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out,
                                                       int iters) {
-  // Every add takes a loop-carried accumulator as an operand, so ptxas can
-  // neither hoist it out of the loop nor fold the max.  The dependency distance
-  // is kT cells, far beyond the 4-cycle pipe latency.
   float nv[kV];
   float acc[kT];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -52,32 +71,47 @@ __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out
   for (int t = 0; t < kT; ++t) acc[t] = in[(tid + t) & 1023];
 
   for (int it = 0; it < iters; ++it) {
-    if constexpr (VARIANT == 0) {
 #pragma unroll
-      for (int v = 0; v < kV; ++v)
+    for (int v = 0; v < kV; v += 2) {
 #pragma unroll
-        for (int t = 0; t < kT; ++t)
-          acc[t] = vmax(acc[t], vadd(acc[(t + 8) % kT], nv[v]));
-    } else if constexpr (VARIANT == 1) {
-#pragma unroll
-      for (int v = 0; v < kV; v += 2)
-#pragma unroll
-        for (int t = 0; t < kT; ++t)
-          acc[t] = vmax3(acc[t], vadd(acc[(t + 8) % kT], nv[v]),
-                         vadd(acc[(t + 9) % kT], nv[v + 1]));
-    } else {
-#pragma unroll
-      for (int v = 0; v < kV; v += 2)
-#pragma unroll
-        for (int t = 0; t < kT; ++t) {
+      for (int t = 0; t < kT; ++t) {
+        const int k = ((t + 8) % kT) & ~1;     // even-aligned register pair
+        const int k1 = (t + 8) % kT, k2 = (t + 9) % kT;
+        if constexpr (VARIANT == 0) {
+          acc[t] = vmax(acc[t], vadd(acc[k1], nv[v]));
+          acc[t] = vmax(acc[t], vadd(acc[k2], nv[v + 1]));
+        } else if constexpr (VARIANT == 1) {
+          acc[t] = vmax3(acc[t], vadd(acc[k1], nv[v]), vadd(acc[k2], nv[v + 1]));
+        } else if constexpr (VARIANT == 2 || VARIANT == 7) {
           float s0, s1;
-          const int k = ((t + 8) % kT) & ~1;     // even-aligned register pair
           // (odd t swaps the rock pair so the two adds are not common
           // subexpressions of the even neighbour's)
           if (t & 1) vadd2(s0, s1, acc[k], acc[k + 1], nv[v + 1], nv[v]);
           else vadd2(s0, s1, acc[k], acc[k + 1], nv[v], nv[v + 1]);
-          acc[t] = vmax3(acc[t], s0, s1);
+          if constexpr (VARIANT == 2) acc[t] = vmax3(acc[t], s0, s1);
+          else acc[t] = vimax3(acc[t], s0, s1);
+        } else if constexpr (VARIANT == 3) {
+          acc[t] = vadd(acc[k1], nv[v]);
+          acc[t] = vadd(acc[k2], nv[v + 1]);
+        } else if constexpr (VARIANT == 4) {
+          acc[t] = vmax(acc[k1], nv[v]);
+          acc[t] = vmax(acc[k2], nv[v + 1]);
+        } else if constexpr (VARIANT == 5) {
+          acc[t] = vmax3(acc[k1], acc[k2], nv[v]);
+        } else if constexpr (VARIANT == 6) {
+          if ((t & 1) == 0) {
+            float s0, s1;
+            vadd2(s0, s1, acc[k], acc[k + 1], nv[v], nv[v + 1]);
+            acc[(t + 4) % kT] = s0;
+            acc[(t + 5) % kT] = s1;
+          }
+        } else if constexpr (VARIANT == 8) {
+          acc[t] = vimax3(acc[k1], acc[k2], nv[v]);
+        } else if constexpr (VARIANT == 9) {
+          acc[t] = vimax(acc[t], vadd(acc[k1], nv[v]));
+          acc[t] = vimax(acc[t], vadd(acc[k2], nv[v + 1]));
         }
+      }
     }
   }
   float r = acc[0];
@@ -89,7 +123,7 @@ __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out
 }  // namespace
 
 int microbench_addmax(int variant, int iters, double* host_cells_per_s) {
-  SRL_REQUIRE(host_cells_per_s != nullptr && iters > 0 && variant >= 0 && variant <= 2,
+  SRL_REQUIRE(host_cells_per_s != nullptr && iters > 0 && variant >= 0 && variant <= 9,
               SRL_E_INVALID, "microbench_addmax: bad arguments");
   const int sms = sm_count();
   SRL_REQUIRE(sms > 0, SRL_E_CUDA, "microbench_addmax: no device");
@@ -106,9 +140,12 @@ int microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   float best_ms = 1e30f;
   for (int rep = 0; rep < 4; ++rep) {   // rep 0 is the warm-up
     SRL_CUDA(cudaEventRecord(t0));
-    if (variant == 0) addmax_kernel<0><<<blocks, threads>>>(in, out, iters);
-    else if (variant == 1) addmax_kernel<1><<<blocks, threads>>>(in, out, iters);
-    else addmax_kernel<2><<<blocks, threads>>>(in, out, iters);
+    switch (variant) {
+#define SRL_MB(V) case V: addmax_kernel<V><<<blocks, threads>>>(in, out, iters); break;
+      SRL_MB(0) SRL_MB(1) SRL_MB(2) SRL_MB(3) SRL_MB(4) SRL_MB(5) SRL_MB(6) SRL_MB(7)
+      SRL_MB(8) SRL_MB(9)
+#undef SRL_MB
+    }
     SRL_CUDA(cudaEventRecord(t1));
     SRL_CUDA(cudaEventSynchronize(t1));
     float ms = 0;
@@ -121,7 +158,8 @@ int microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   cudaFree(in);
   cudaFree(out);
   if (rc != SRL_OK) return rc;
-  const double cells = (double)blocks * threads * (double)iters * kT * kV;
+  double cells = (double)blocks * threads * (double)iters * kT * kV;
+  if (variant == 6) cells *= 0.5;   // one FADD2 per two (v, t) steps
   *host_cells_per_s = cells / (best_ms * 1e-3);
   return SRL_OK;
 }

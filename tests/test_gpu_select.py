@@ -1,0 +1,146 @@
+"""goal_overlap / Baseline.call / PyGreedy conventions on the GPU against the
+reference's golden outputs and the oracle.  Indices and masks are exact; the
+float64 value maps are bit-exact (they are negations / one float64 add of
+bit-exact float32 scores)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import scoring_np as S
+from stackrl_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+F32_CASES = ['c2like_f32', 'nonsquare_wall_f32', 'dense_rock_f32', 'empty_rock_f32',
+             'ties_f32', 'flat_wall_f32', 'c4like_f32', 'c5like_f32',
+             'full_rock_window_f32']
+ALL_CASES = F32_CASES + ['stackv0_u8', 'c5like_u8']
+
+
+@pytest.fixture(scope='module')
+def B():
+  from stackrl_b200 import baselines
+  return baselines
+
+
+@pytest.mark.parametrize('case', ALL_CASES)
+def test_goal_overlap_matches_reference(B, scoring_golden, case):
+  obs = scoring_golden.obs(case)
+  assert np.array_equal(B.goal_overlap(obs), scoring_golden[case + '/goal_overlap'])
+  assert np.array_equal(B.goal_overlap(obs, threshold=0.5),
+                        scoring_golden[case + '/goal_overlap_t50'])
+
+
+@pytest.mark.parametrize('case', F32_CASES)
+def test_baseline_height_matches_reference(B, scoring_golden, case):
+  obs = scoring_golden.obs(case)
+  keys = sorted({k.rsplit('/', 1)[0] for k in scoring_golden.keys(case + '/select_height')})
+  assert keys
+  for key in keys:
+    _, _, g, m = key.split('/')[1].split('_')
+    pol = B.Baseline(method='height', goal=g == 'g1', minorder=int(m[1:]), value=True)
+    a, v = pol(obs)
+    assert a == int(scoring_golden[key + '/action']), key
+    want = scoring_golden[key + '/values']
+    assert v.dtype == want.dtype and np.array_equal(v, want), key
+
+
+@pytest.mark.parametrize('case', ['c2like_f32', 'ties_f32', 'c4like_f32'])
+def test_baseline_with_user_callable(B, scoring_golden, case):
+  """method=<callable> (seam b3): the map comes from the callable (here the
+  oracle's `difference`), the selection runs on the GPU."""
+  obs = scoring_golden.obs(case)
+  for minorder in (0, 1, 2):
+    key = '{}/select_difference_g1_m{}'.format(case, minorder)
+    pol = B.Baseline(method=S.difference, minorder=minorder, value=True)
+    a, v = pol(obs)
+    assert a == int(scoring_golden[key + '/action'])
+    assert np.array_equal(v, scoring_golden[key + '/values'])
+
+
+def test_batched_batchwise_matches_reference(B, scoring_golden):
+  obs = scoring_golden.obs('batched_f32')
+  pol = B.Baseline(method='height', value=True, batched=True, batchwise=True)
+  (k, idx), v = pol(obs)
+  assert k == int(scoring_golden['batched_f32/height/k'])
+  assert idx == int(scoring_golden['batched_f32/height/index'])
+  assert np.array_equal(v, scoring_golden['batched_f32/height/values'])
+  pol = B.Baseline(method='height', value=True, batched=True, unravel=True)
+  a, v = pol(obs)
+  assert np.array_equal(a, scoring_golden['batched_f32/height_unravel/actions'])
+  assert np.array_equal(v, scoring_golden['batched_f32/height_unravel/values'])
+
+
+def test_unbatched_return_conventions(B, scoring_golden):
+  obs = scoring_golden.obs('c2like_f32')
+  want = int(scoring_golden['c2like_f32/select_height_g1_m1/action'])
+  assert B.Baseline(method='height')(obs) == want
+  ij = B.Baseline(method='height', unravel=True)(obs)
+  assert tuple(ij) == tuple(np.unravel_index(want, (17, 17)))
+  with pytest.raises(ValueError):
+    B.Baseline(method='nope')
+  with pytest.raises(TypeError):
+    B.Baseline(method=3)
+
+
+@pytest.mark.parametrize('shape', [(6, 8, 32, 32, 16), (3, 4, 64, 64, 16), (2, 3, 40, 56, 8)])
+@pytest.mark.parametrize('goal,minorder', [(True, 1), (True, 0), (True, 2), (False, 1)])
+def test_placement_scorer_batched(B, shape, goal, minorder):
+  """Device-resident batch: actions / batch-wise picks equal to looping the
+  oracle's Baseline.call + PyGreedy over every environment and view."""
+  E, R, H, W, h = shape
+  walls, rocks, _ = synth.placement_batch(31, E, R, H, W, h)
+  goals = synth.goals(32, E, H, W)
+  dev = torch.device('cuda')
+  scorer = B.PlacementScorer(goal=goal, minorder=minorder)
+  out = scorer(torch.from_numpy(walls).to(dev), torch.from_numpy(goals).to(dev),
+               torch.from_numpy(rocks).to(dev), want_shown=True)
+  actions = out['actions'].cpu().numpy()
+  best = out['best'].cpu().numpy()
+  shown = out['shown'].cpu().numpy()
+  for e in range(E):
+    wg = np.stack([walls[e], goals[e]], -1)
+    obs = (np.stack([wg] * R), rocks[e][..., None])
+    (k, idx), v = S.greedy(
+      obs, lambda o: S.baseline_call(o, method='height', goal=goal, minorder=minorder),
+      value=True, batched=True, batchwise=True)
+    per_view = [S.baseline_call((wg, rocks[e, r][..., None]), goal=goal,
+                                minorder=minorder)[0] for r in range(R)]
+    assert list(actions[e]) == per_view
+    assert (best[e, 0], best[e, 1]) == (k, idx)
+    assert np.array_equal(shown[e].reshape(R, -1), v)
+
+
+def test_select_first_index_ties():
+  """All-equal scores: np.argmin's first index, on a goal mask whose first
+  member is not position 0."""
+  from stackrl_b200 import capi
+  dev = torch.device('cuda')
+  values = torch.full((2, 1, 5, 7), 0.5, dtype=torch.float32, device=dev)
+  counts = torch.zeros((2, 1, 5, 7), dtype=torch.int32, device=dev)
+  counts[0, 0, 2, 3:] = 4
+  counts[0, 0, 3, :] = 4
+  counts[1] = 1
+  actions, shown, best = capi.select(values, counts, minorder=1)
+  assert actions.cpu().tolist() == [[2 * 7 + 3], [0]]
+  v = values[0, 0].cpu().numpy().astype('float64')
+  m = (counts[0, 0].cpu().numpy() >= 0.75 * 4)
+  a, s = S.select(v, m, 1)
+  assert a == 2 * 7 + 3 and np.array_equal(shown[0, 0].cpu().numpy(), s)
+
+
+def test_drop_height_matches_pose_formula():
+  """Observer.pose's z (observer.py:401-409) at picked positions."""
+  from stackrl_b200 import capi
+  E, R, H, W, h = 9, 4, 32, 32, 16
+  walls, rocks, _ = synth.placement_batch(41, E, R, H, W, h)
+  rng = np.random.default_rng(0)
+  picks = np.stack([rng.integers(0, R, E), rng.integers(0, H - h + 1, E),
+                    rng.integers(0, W - h + 1, E)], -1).astype('int32')
+  dev = torch.device('cuda')
+  got = capi.drop_height_f32(torch.from_numpy(walls).to(dev),
+                             torch.from_numpy(rocks).to(dev),
+                             torch.from_numpy(picks).to(dev)).cpu().numpy()
+  for e in range(E):
+    r, i, j = picks[e]
+    assert got[e] == S.drop_height(walls[e], rocks[e, r], (i, j))
