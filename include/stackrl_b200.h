@@ -61,15 +61,12 @@ SRL_API int srl_maxplus_f32(const float* walls, const float* rocks, const float*
                     float* out, int E, int R, int H, int W, int h,
                     float threshold, srl_stream_t stream);
 
-#ifdef SRL_NEXT   /* lands with its kernel */
 /* Same for uint8 observations (registered Stack-v0/1/2 dtype): the reference
  * divides uint8 by uint8 -> float64, so this evaluates IEEE float64
  * a/g + b/g per cell.  level [E] u8 (goal.max()), out f64. */
 SRL_API int srl_maxplus_u8(const uint8_t* walls, const uint8_t* rocks,
                    const uint8_t* level, double* out, int E, int R, int H,
                    int W, int h, srl_stream_t stream);
-
-#endif  /* SRL_NEXT */
 
 /* ---- a4: Observer.pose drop height (observer.py:401-409) --------------------
  * z[e] = max( (walls[e, i:i+h, j:j+h] + rocks[e, r])[rocks[e, r] > 1e-4] ),
@@ -108,7 +105,6 @@ SRL_API int srl_select_f64(const double* values, const int32_t* counts, int64_t*
                    double* shown, int64_t* best, int E, int R, int Ph, int Pw,
                    int minorder, double overlap_threshold, srl_stream_t stream);
 
-#ifdef SRL_NEXT   /* lands with its kernel */
 /* ---- a6: baselines.difference (baselines.py:45-77), exponents (2, 2|0) -------
  * f = sum_{u,v} w[u,v] * |h0 - (o+n)|^p  in numpy's order: float32 lift and
  * residual, float64 weights/product, pairwise summation over the contiguous
@@ -122,6 +118,7 @@ SRL_API int srl_difference_f32(const float* walls, const float* rocks,
                        float* top, int E, int R, int H, int W, int h,
                        int difference_exponent, srl_stream_t stream);
 
+#ifdef SRL_NEXT   /* lands with its kernel */
 /* ---- a2/a3: Observer.__call__ rasterisation + depth->elevation
  *      (observer.py:252-260, 267-277; pybullet.getCameraImage) ----------------
  * One job = one image: a camera (column-major GL view and projection matrices,

@@ -60,8 +60,12 @@ def _height_device(walls, goals, rocks):
   if walls.dtype == torch.float32:
     level = goals.amax(dim=(1, 2))          # get_inputs: goal.max() (baselines.py:23)
     return capi.maxplus_f32(walls, rocks, level)
-  raise NotImplementedError(
-    'observation dtype {} is not wired to a kernel yet'.format(walls.dtype))
+  if walls.dtype == torch.uint8:
+    # uint8/uint8 is float64 in numpy: IEEE float64 a/g + b/g per cell.
+    return capi.maxplus_u8(walls, rocks, goals.amax(dim=(1, 2)))
+  raise TypeError(
+    'observations must be float32 or uint8 (the dtypes the reference registers), '
+    'got {}'.format(walls.dtype))
 
 
 # ---- baselines.py:28-43 ------------------------------------------------------ #
@@ -75,6 +79,45 @@ def height(inputs, mask=None, **kwargs):
   f = _height_device(walls, goals, rocks)[0, 0].cpu().numpy().astype('float64')
   if mask is not None:
     f = np.where(mask, f, 0.)
+  return f
+
+
+# ---- baselines.py:45-77 ------------------------------------------------------ #
+def difference(inputs, mask=None, difference_exponent=2, weights_exponent=2,
+               return_height=False, **kwargs):
+  """Difference based heuristic: weighted residual between the rock's underside
+  and the wall at the drop height.  float64, bit-exact with the reference for
+  ``difference_exponent`` in {1, 2} (numpy's float32 pow for other exponents is
+  libm-defined and is refused rather than approximated)."""
+  if difference_exponent not in (1, 2):
+    raise ValueError('difference_exponent must be 1 or 2 for a bit-reproducible '
+                     'result, got {}'.format(difference_exponent))
+  walls, goals, rocks = _planes(inputs)
+  if walls.dtype != torch.float32:
+    raise TypeError('difference is wired for float32 observations')
+  level = goals.amax(dim=(1, 2))
+  if weights_exponent in (0, 2):
+    weights = capi.difference_weights(rocks, level, weights_exponent)
+  else:
+    # Any other exponent goes through numpy's own float64 pow on the host so the
+    # weights keep the reference's bits (baselines.py:54-62).
+    n = (rocks[0, 0] / level[0]).cpu().numpy()
+    live = n > 0
+    di = (np.arange(n.shape[0], dtype='float') - n.shape[0] / 2) ** 2
+    dj = (np.arange(n.shape[1], dtype='float') - n.shape[1] / 2) ** 2
+    w = np.where(live, (di[:, None] + dj[None, :]) ** (weights_exponent / 2), 0)
+    w /= w.sum()
+    weights = _upload(w[None, None])
+  f, top = capi.difference_f32(walls, rocks, level, weights, difference_exponent,
+                               want_top=return_height)
+  f = f[0, 0].cpu().numpy()
+  if mask is not None:
+    f = np.where(mask, f, 0.)
+  if return_height:
+    h0 = top[0, 0].cpu().numpy().astype('float64')
+    if mask is not None:
+      h0 = np.where(mask, h0, 0.)
+    return f, h0
   return f
 
 
@@ -98,6 +141,7 @@ def goal_overlap(inputs, threshold=0.75, **kwargs):
 methods = {
   'random': random,
   'height': height,
+  'difference': difference,
 }
 
 
@@ -170,6 +214,14 @@ class Baseline(object):
     walls, goals, rocks = _upload(wall), _upload(goal), _upload(rock[:, None])
     if self.model is height:
       values = _height_device(walls, goals, rocks)
+    elif self.model is difference and walls.dtype == torch.float32 and \
+        self.kwargs.get('difference_exponent', 2) in (1, 2) and \
+        self.kwargs.get('weights_exponent', 2) in (0, 2):
+      level = goals.amax(dim=(1, 2))
+      weights = capi.difference_weights(rocks, level,
+                                        self.kwargs.get('weights_exponent', 2))
+      values, _ = capi.difference_f32(walls, rocks, level, weights,
+                                      self.kwargs.get('difference_exponent', 2))
     else:
       maps = [np.asarray(self.model((np.stack([wall[k], goal[k]], -1), rock[k][..., None]),
                                     **self.kwargs), dtype='float64') for k in range(N)]

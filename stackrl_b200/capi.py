@@ -111,6 +111,20 @@ def maxplus_f32(walls, rocks, level=None, threshold=0., out=None):
   return out
 
 
+def maxplus_u8(walls, rocks, level, out=None):
+  """uint8 walls [E,H,W], rocks [E,R,h,h], level [E] -> float64 [E,R,Ph,Pw]."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  args = (_dev(walls, torch.uint8, 'walls'), _dev(rocks, torch.uint8, 'rocks'),
+          _dev(level, torch.uint8, 'level'))
+  if out is None:
+    out = torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.float64,
+                      device=walls.device)
+  with torch.cuda.device(walls.device):
+    _check(lib.srl_maxplus_u8(*args, _dev(out, torch.float64, 'out'),
+                              E, R, H, W, h, _stream()))
+  return out
+
+
 def _batch_dims(walls, rocks):
   E, H, W = walls.shape
   E2, R, h, h2 = rocks.shape
@@ -173,6 +187,32 @@ def select(values, counts=None, minorder=1, overlap_threshold=0.75,
               _opt(shown, torch.float64, 'shown'), _opt(best, torch.int64, 'best'),
               E, R, Ph, Pw, int(minorder), float(overlap_threshold), _stream()))
   return actions, shown, best
+
+
+def difference_weights(rocks, level=None, weights_exponent=2):
+  """rocks [E,R,h,h] float32 -> normalised radial weights [E,R,h,h] float64."""
+  E, R, h, h2 = rocks.shape
+  out = torch.empty((E, R, h, h), dtype=torch.float64, device=rocks.device)
+  args = (_dev(rocks, torch.float32, 'rocks'), _opt(level, torch.float32, 'level'))
+  with torch.cuda.device(rocks.device):
+    _check(lib.srl_difference_weights(*args, _dev(out, torch.float64, 'weights'),
+                                      E, R, h, int(weights_exponent), _stream()))
+  return out
+
+
+def difference_f32(walls, rocks, level, weights, difference_exponent=2, want_top=False):
+  """-> (f [E,R,Ph,Pw] float64, h0 [E,R,Ph,Pw] float32 | None)."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  args = (_dev(walls, torch.float32, 'walls'), _dev(rocks, torch.float32, 'rocks'),
+          _opt(level, torch.float32, 'level'), _dev(weights, torch.float64, 'weights'))
+  shape = (E, R, H - h + 1, W - h + 1)
+  out = torch.empty(shape, dtype=torch.float64, device=walls.device)
+  top = torch.empty(shape, dtype=torch.float32, device=walls.device) if want_top else None
+  with torch.cuda.device(walls.device):
+    _check(lib.srl_difference_f32(*args, _dev(out, torch.float64, 'out'),
+                                  _opt(top, torch.float32, 'top'), E, R, H, W, h,
+                                  int(difference_exponent), _stream()))
+  return out, top
 
 
 def microbench_addmax(variant, iters=2000):

@@ -63,6 +63,11 @@ int srl_maxplus_f32(const float* walls, const float* rocks, const float* level,
                           variant, (cudaStream_t)stream);
 }
 
+int srl_maxplus_u8(const uint8_t* walls, const uint8_t* rocks, const uint8_t* level,
+                   double* out, int E, int R, int H, int W, int h, srl_stream_t stream) {
+  return srl::maxplus_u8(walls, rocks, level, out, E, R, H, W, h, (cudaStream_t)stream);
+}
+
 int srl_drop_height_f32(const float* walls, const float* rocks, const int32_t* picks,
                         float* out, int E, int R, int H, int W, int h, float threshold,
                         srl_stream_t stream) {
@@ -96,6 +101,21 @@ int srl_select_f64(const double* values, const int32_t* counts, int64_t* actions
                    int minorder, double overlap_threshold, srl_stream_t stream) {
   return srl::select_f64(values, counts, actions, shown, best, E, R, Ph, Pw, minorder,
                          overlap_threshold, (cudaStream_t)stream);
+}
+
+int srl_difference_weights(const float* rocks, const float* level, double* weights,
+                           int E, int R, int h, int weights_exponent,
+                           srl_stream_t stream) {
+  return srl::difference_weights(rocks, level, weights, E, R, h, weights_exponent,
+                                 (cudaStream_t)stream);
+}
+
+int srl_difference_f32(const float* walls, const float* rocks, const float* level,
+                       const double* weights, double* out, float* top, int E, int R,
+                       int H, int W, int h, int difference_exponent,
+                       srl_stream_t stream) {
+  return srl::difference_f32(walls, rocks, level, weights, out, top, E, R, H, W, h,
+                             difference_exponent, (cudaStream_t)stream);
 }
 
 int srl_microbench_addmax(int variant, int iters, double* host_cells_per_s) {

@@ -27,6 +27,15 @@ int drop_height_f32(const float* walls, const float* rocks, const int32_t* picks
                     float* out, int E, int R, int H, int W, int h, float threshold,
                     cudaStream_t stream);
 
+int maxplus_u8(const uint8_t* walls, const uint8_t* rocks, const uint8_t* level,
+               double* out, int E, int R, int H, int W, int h, cudaStream_t stream);
+
+int difference_weights(const float* rocks, const float* level, double* weights, int E,
+                       int R, int h, int weights_exponent, cudaStream_t stream);
+int difference_f32(const float* walls, const float* rocks, const float* level,
+                   const double* weights, double* out, float* top, int E, int R, int H,
+                   int W, int h, int difference_exponent, cudaStream_t stream);
+
 int microbench_addmax(int variant, int iters, double* host_cells_per_s);
 
 }  // namespace srl

@@ -167,10 +167,17 @@ __device__ __forceinline__ void sweep_item(float (&acc)[T], const float* wbase,
   }
 }
 
+// IEEE x / level.  Zero numerators (rock background, empty wall) are common and
+// would take __fdiv_rn's slow path; +-0 / level = +-0 * level bit for bit (the
+// level is a finite, non-zero goal height).
+__device__ __forceinline__ float div_level(float x, float level) {
+  return x == 0.f ? __fmul_rn(x, level) : __fdiv_rn(x, level);
+}
+
 // Normalise + mask one rock value (baselines.py:24-25, :32).
 __device__ __forceinline__ float prep_rock(float n, bool scaled, float level,
                                            float thr, bool& dead) {
-  if (scaled) n = __fdiv_rn(n, level);
+  if (scaled) n = div_level(n, level);
   const bool live = n > thr;
   dead = dead || !live;
   return live ? n : kNegInf;
@@ -243,10 +250,10 @@ maxplus_staged_kernel(const MaxPlusParams p) {
       float4 x = lds128(raw_wall + 4 * q);
       if (scaled) {
         const float lv = __ldg(p.level + e0 + fdiv(row, p.dH));
-        x.x = __fdiv_rn(x.x, lv);
-        x.y = __fdiv_rn(x.y, lv);
-        x.z = __fdiv_rn(x.z, lv);
-        x.w = __fdiv_rn(x.w, lv);
+        x.x = div_level(x.x, lv);
+        x.y = div_level(x.y, lv);
+        x.z = div_level(x.z, lv);
+        x.w = div_level(x.w, lv);
       }
       *reinterpret_cast<float4*>(wall_s + row * Ws + 4 * c4) = x;
     }
@@ -417,7 +424,7 @@ maxplus_direct_kernel(const MaxPlusParams p) {
       uint32_t row, c;
       fdivmod(k, p.dW, row, c);
       float* q = wall_s + row * Ws + c;
-      *q = __fdiv_rn(*q, __ldg(p.level + e0 + fdiv(row, p.dH)));
+      *q = div_level(*q, __ldg(p.level + e0 + fdiv(row, p.dH)));
     }
   }
   for (uint32_t k = tid; k < (uint32_t)(Gv * RCv * h * hp); k += nthreads) {

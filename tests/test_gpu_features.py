@@ -1,0 +1,116 @@
+"""uint8 (float64) max-plus, `difference`, and the remaining drop-in functions
+of the baselines mirror against the reference's golden outputs.  Bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import scoring_np as S
+from stackrl_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+F32_CASES = ['c2like_f32', 'nonsquare_wall_f32', 'dense_rock_f32', 'ties_f32',
+             'flat_wall_f32', 'c4like_f32', 'c5like_f32', 'full_rock_window_f32']
+
+
+@pytest.fixture(scope='module')
+def B():
+  from stackrl_b200 import baselines
+  return baselines
+
+
+@pytest.mark.parametrize('case', ['stackv0_u8', 'c5like_u8'])
+def test_height_uint8_is_float64_exact(B, scoring_golden, case):
+  got = B.height(scoring_golden.obs(case))
+  want = scoring_golden[case + '/height']
+  assert got.dtype == np.float64 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize('case', ['stackv0_u8', 'c5like_u8'])
+def test_baseline_uint8_actions(B, scoring_golden, case):
+  obs = scoring_golden.obs(case)
+  keys = sorted({k.rsplit('/', 1)[0] for k in scoring_golden.keys(case + '/select_height')})
+  for key in keys:
+    _, _, g, m = key.split('/')[1].split('_')
+    pol = B.Baseline(method='height', goal=g == 'g1', minorder=int(m[1:]), value=True)
+    a, v = pol(obs)
+    assert a == int(scoring_golden[key + '/action']), key
+    assert np.array_equal(v, scoring_golden[key + '/values']), key
+
+
+def test_batched_uint8_batchwise(B, scoring_golden):
+  obs = scoring_golden.obs('batched_u8')
+  pol = B.Baseline(method='height', value=True, batched=True, batchwise=True)
+  (k, idx), v = pol(obs)
+  assert k == int(scoring_golden['batched_u8/height/k'])
+  assert idx == int(scoring_golden['batched_u8/height/index'])
+  assert np.array_equal(v, scoring_golden['batched_u8/height/values'])
+
+
+def test_uint8_batch_matches_oracle():
+  from stackrl_b200 import capi
+  E, R, H, W, h = 5, 3, 32, 32, 8
+  rng = np.random.default_rng(3)
+  walls = rng.integers(0, 200, (E, H, W), dtype=np.uint8)
+  rocks = rng.integers(0, 86, (E, R, h, h), dtype=np.uint8)
+  rocks[rng.random(rocks.shape) < 0.3] = 0
+  level = rng.integers(100, 255, (E,), dtype=np.uint8)
+  dev = torch.device('cuda')
+  got = capi.maxplus_u8(torch.from_numpy(walls).to(dev), torch.from_numpy(rocks).to(dev),
+                        torch.from_numpy(level).to(dev)).cpu().numpy()
+  for e in range(E):
+    goal = np.full((H, W), level[e], dtype=np.uint8)
+    for r in range(R):
+      want = S.height((np.stack([walls[e], goal], -1), rocks[e, r][..., None]))
+      assert np.array_equal(got[e, r], want)
+
+
+@pytest.mark.parametrize('case', F32_CASES)
+def test_difference_bit_exact(B, scoring_golden, case):
+  obs = scoring_golden.obs(case)
+  d, h0 = B.difference(obs, return_height=True)
+  assert d.dtype == np.float64
+  assert np.array_equal(h0, scoring_golden[case + '/difference_height'])
+  assert np.array_equal(d, scoring_golden[case + '/difference'])
+  if case + '/difference_w0' in scoring_golden:
+    assert np.array_equal(B.difference(obs, weights_exponent=0),
+                          scoring_golden[case + '/difference_w0'])
+    assert np.array_equal(B.difference(obs, difference_exponent=1),
+                          scoring_golden[case + '/difference_d1'])
+
+
+@pytest.mark.parametrize('side', [3, 5, 6, 10, 12, 20])
+def test_difference_pairwise_order_odd_sizes(B, side):
+  """Rock sizes whose h*h is not a power of two exercise every branch of
+  numpy's pairwise summation (n < 8, remainder loop, uneven tree split)."""
+  obs = synth.observation(50 + side, 3 * side + 1, 2 * side + 3, side)
+  assert np.array_equal(B.difference(obs), S.difference(obs))
+  assert np.array_equal(B.difference(obs, weights_exponent=3),
+                        S.difference(obs, weights_exponent=3))
+
+
+def test_difference_rejects_unreproducible_exponent(B):
+  obs = synth.observation(1, 16, 16, 4)
+  with pytest.raises(ValueError):
+    B.difference(obs, difference_exponent=3)
+
+
+def test_baseline_difference_actions(B, scoring_golden):
+  for case in ('c2like_f32', 'ties_f32', 'c4like_f32'):
+    obs = scoring_golden.obs(case)
+    for minorder in (0, 1, 2):
+      key = '{}/select_difference_g1_m{}'.format(case, minorder)
+      a, v = B.Baseline(method='difference', minorder=minorder, value=True)(obs)
+      assert a == int(scoring_golden[key + '/action'])
+      assert np.array_equal(v, scoring_golden[key + '/values'])
+  obs = scoring_golden.obs('batched_f32')
+  (k, idx), v = B.Baseline(method='difference', value=True, batched=True,
+                           batchwise=True)(obs)
+  assert k == int(scoring_golden['batched_f32/difference/k'])
+  assert idx == int(scoring_golden['batched_f32/difference/index'])
+  assert np.array_equal(v, scoring_golden['batched_f32/difference/values'])
+
+
+def test_random_method_is_numpy_stream(B):
+  obs = synth.observation(2, 16, 16, 4)
+  assert np.array_equal(B.random(obs, seed=5), S.random(obs, seed=5))
