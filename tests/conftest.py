@@ -44,3 +44,23 @@ class Golden(object):
 @pytest.fixture(scope='session')
 def scoring_golden():
   return Golden('scoring.npz')
+
+
+@pytest.fixture(scope='session')
+def observe_golden():
+  return Golden('observe.npz')
+
+
+# Reference default geometry, used by the episode fixtures.
+GEOM = dict(H=128, W=128, h=32, pixel=0.125 / 32, max_z=0.375,
+            object_max_dimension=0.125, object_z=0.125, goal_z=0.25)
+
+
+def split_depths(golden, key):
+  """The depth images recorded since the previous step, in call order."""
+  flat = golden[key + '/depths']
+  out, at = [], 0
+  for rows, cols in golden[key + '/depth_shapes']:
+    out.append(flat[at:at + rows * cols].reshape(rows, cols))
+    at += rows * cols
+  return out

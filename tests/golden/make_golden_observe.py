@@ -1,0 +1,116 @@
+"""Golden episodes of the UNMODIFIED reference env on the fake pybullet backend.
+
+Called from make_golden.py (build container only).  Runs the reference's own
+StackEnv / TestStackEnv (env.py), Observer, Rewarder and Baseline('height')
+with oracle.fake_pybullet as the ``pybullet`` module ("reference code, fake
+physics": bodies stay where they are placed) and records, per step, the depth
+images the fake renderer produced, the Observer's maps, the poses, the rewards,
+the packed observations and the actions.  The meshes used are stored too, so the
+fixture is self-contained on the GPU box.
+"""
+import os
+
+import numpy as np
+
+from oracle import fake_pybullet, refload
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _episode(ns, fb, env_cls, urdfs, dtype, steps, policy_kwargs, out, prefix, **env_kwargs):
+  depth_log = []
+  real = fb.getCameraImage
+
+  def recording(*a, **k):
+    res = real(*a, **k)
+    depth_log.append(res[3].copy())
+    return res
+  fb.getCameraImage = recording
+
+  env = env_cls(urdfs=urdfs, dtype=dtype, rewarder='all', seed=7, episode_length=steps,
+                **env_kwargs)
+  pol = ns.baselines.Baseline(method='height', value=True, **policy_kwargs)
+  obs = env.reset()
+  order = [env._sim._last_urdf] if hasattr(env._sim, '_last_urdf') else []
+  out[prefix + '/goal'] = env._rew.goal.copy()
+  out[prefix + '/goal_lims'] = np.array(env._rew._goal_lims)
+  out[prefix + '/n_steps'] = np.int64(steps)
+  k = 0
+  done = False
+  while not done:
+    m, n = env._obs.state
+    out['{}/s{}/overhead_map'.format(prefix, k)] = np.array(m)
+    out['{}/s{}/object_map'.format(prefix, k)] = np.array(n)
+    out['{}/s{}/obs0'.format(prefix, k)] = obs[0]
+    out['{}/s{}/obs1'.format(prefix, k)] = obs[1]
+    out['{}/s{}/depths'.format(prefix, k)] = np.concatenate(
+      [d.ravel() for d in depth_log]) if depth_log else np.zeros(0, 'float32')
+    out['{}/s{}/depth_shapes'.format(prefix, k)] = np.array([d.shape for d in depth_log])
+    del depth_log[:]
+    a, v = pol(obs)
+    if isinstance(a, tuple):
+      action = (int(a[0]), int(a[1]))
+      out['{}/s{}/action'.format(prefix, k)] = np.array(action, dtype='int64')
+      pose = env._obs.pose([action[1] // env._action_width, action[1] % env._action_width],
+                           index=action[0])
+      out['{}/s{}/pose_orientation'.format(prefix, k)] = np.array(pose['orientation'])
+    else:
+      action = int(a)
+      out['{}/s{}/action'.format(prefix, k)] = np.int64(action)
+      pose = env._obs.pose([action // env._action_width, action % env._action_width])
+    out['{}/s{}/pose_position'.format(prefix, k)] = np.array(pose['position'], dtype='float64')
+    obs, reward, done, info = env.step(action)
+    out['{}/s{}/rewards'.format(prefix, k)] = np.array(
+      [info[name] for name in ('IoU', 'OR', 'DIoU', 'DOR')], dtype='float64')
+    k += 1
+  # terminal observation
+  m, n = env._obs.state
+  out['{}/s{}/overhead_map'.format(prefix, k)] = np.array(m)
+  out['{}/s{}/obs0'.format(prefix, k)] = obs[0]
+  out['{}/s{}/depths'.format(prefix, k)] = np.concatenate([d.ravel() for d in depth_log])
+  out['{}/s{}/depth_shapes'.format(prefix, k)] = np.array([d.shape for d in depth_log])
+  out[prefix + '/n_recorded'] = np.int64(k)
+  fb.getCameraImage = real
+  env.close()
+
+
+def main(ns=None):
+  fb = fake_pybullet.FakeBullet()
+  ns = refload.load(pybullet=fb)
+  # Log the order in which the simulator loads URDFs (the env's RNG decides it).
+  loaded = []
+  real_load = fb.loadURDF
+
+  def logging_load(fileName, *a, **k):
+    loaded.append(os.path.basename(fileName))
+    return real_load(fileName, *a, **k)
+  fb.loadURDF = logging_load
+
+  names = ['0_0', '0_3', '50_000', '55_017', '60_250', '75_003', '80_499', '95_042']
+  urdfs = [os.path.join(ns.root, 'stackrl/envs/data/generated', n + '.urdf') for n in names]
+  out = {}
+  for n, u in zip(names, urdfs):
+    mesh, com = fake_pybullet.parse_urdf(u)
+    v, t = fake_pybullet.load_obj(mesh)
+    out['mesh/{}/verts'.format(n)] = v
+    out['mesh/{}/tris'.format(n)] = t
+    out['mesh/{}/com'.format(n)] = com
+  out['mesh_names'] = np.array(names)
+
+  episodes = [
+    ('stack_f32', ns.env.StackEnv, 'float32', 6, {}, {}),
+    ('stack_u8', ns.env.StackEnv, 'uint8', 6, {}, {}),
+    ('test_f32_rot8', ns.env.TestStackEnv, 'float32', 5,
+     dict(batched=True, batchwise=True), dict(orientation_freedom=3)),
+  ]
+  for prefix, cls, dtype, steps, pk, ek in episodes:
+    del loaded[:]
+    _episode(ns, fb, cls, urdfs, dtype, steps, pk, out, prefix, **ek)
+    out[prefix + '/urdf_order'] = np.array([n[:-5] for n in loaded])
+  path = os.path.join(HERE, 'observe.npz')
+  np.savez_compressed(path, **out)
+  print('observe.npz: {} arrays, {:.0f} KB'.format(len(out), os.path.getsize(path) / 1024))
+
+
+if __name__ == '__main__':
+  main()

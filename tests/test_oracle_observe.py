@@ -1,0 +1,76 @@
+"""oracle/observe_np.py (depth->elevation, packing, IoU/OR) and the oracle's
+pose restatement against episodes of the UNMODIFIED reference env recorded on
+the fake pybullet backend (tests/golden/observe.npz).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import observe_np as O
+from oracle import scoring_np as S
+from tests.conftest import GEOM, split_depths
+
+EPISODES = [('stack_f32', 'float32', 1), ('stack_u8', 'uint8', 1), ('test_f32_rot8', 'float32', 8)]
+
+
+@pytest.mark.parametrize('name,dtype,views', EPISODES)
+def test_conversion_and_packing(observe_golden, name, dtype, views):
+  g = observe_golden
+  goal = g[name + '/goal']
+  n_steps = int(g[name + '/n_recorded'])
+  rock = None
+  for k in range(n_steps + 1):
+    key = '{}/s{}'.format(name, k)
+    depths = split_depths(g, key)
+    wall = O.wall_elevation(depths[0], GEOM['max_z'])
+    assert np.array_equal(wall, g[key + '/overhead_map'])
+    if len(depths) > 1:
+      rock = [O.rock_elevation(d, GEOM['object_z']) for d in depths[1:]]
+      assert len(rock) == views
+    if k == n_steps:
+      break
+    want_rock = g[key + '/object_map']
+    if views == 1:
+      assert np.array_equal(rock[0], want_rock)
+      obs = O.pack_obs(wall, goal, rock[0], dtype, GEOM['max_z'], GEOM['object_max_dimension'])
+    else:
+      assert np.array_equal(np.array(rock), want_rock)
+      obs = O.pack_obs_batched(wall, goal, rock, dtype, GEOM['max_z'],
+                               GEOM['object_max_dimension'])
+    assert obs[0].dtype == g[key + '/obs0'].dtype
+    assert np.array_equal(obs[0], g[key + '/obs0'])
+    assert np.array_equal(obs[1], g[key + '/obs1'])
+
+
+@pytest.mark.parametrize('name,dtype,views', EPISODES)
+def test_pose_and_actions(observe_golden, name, dtype, views):
+  g = observe_golden
+  px = GEOM['pixel']
+  size = (GEOM['h'] * px, GEOM['h'] * px, GEOM['object_z'])
+  Pw = GEOM['W'] - GEOM['h'] + 1
+  for k in range(int(g[name + '/n_recorded'])):
+    key = '{}/s{}'.format(name, k)
+    obs = (g[key + '/obs0'], g[key + '/obs1'])
+    if views == 1:
+      a, _ = S.baseline_call(obs, method='height')
+      assert a == int(g[key + '/action'])
+      view, flat = None, a
+      rock = g[key + '/object_map']
+    else:
+      (view, flat), _ = S.greedy(obs, lambda o: S.baseline_call(o, method='height'),
+                                 value=True, batched=True, batchwise=True)
+      assert (view, flat) == tuple(g[key + '/action'])
+      rock = g[key + '/object_map'][view]
+    pos = S.pose(g[key + '/overhead_map'], rock, (flat // Pw, flat % Pw), (px, px), size)
+    assert np.array_equal(np.array(pos, dtype='float64'), g[key + '/pose_position'])
+
+
+@pytest.mark.parametrize('name', ['stack_f32', 'test_f32_rot8'])
+def test_iou_and_or_rewards(observe_golden, name):
+  g = observe_golden
+  goal = g[name + '/goal']
+  memory = {'iou': 0., 'or': 0.}
+  for k in range(int(g[name + '/n_recorded'])):
+    wall = g['{}/s{}/overhead_map'.format(name, k + 1)]
+    want = g['{}/s{}/rewards'.format(name, k)]
+    for col, metric in ((0, 'iou'), (1, 'or')):
+      r, memory[metric] = O.reward(wall, goal, GEOM['goal_z'], metric, memory[metric])
+      assert r == want[col], (k, metric)
