@@ -118,39 +118,47 @@ SRL_API int srl_difference_f32(const float* walls, const float* rocks,
                        float* top, int E, int R, int H, int W, int h,
                        int difference_exponent, srl_stream_t stream);
 
-#ifdef SRL_NEXT   /* lands with its kernel */
 /* ---- a2/a3: Observer.__call__ rasterisation + depth->elevation
  *      (observer.py:252-260, 267-277; pybullet.getCameraImage) ----------------
  * One job = one image: a camera (column-major GL view and projection matrices,
- * as computeViewMatrix / computeProjectionMatrix return them), an image size,
- * and a contiguous range of world-space triangles.  Depth follows the GL
- * convention the reference inverts (observer.py:259-260); `mode` selects the
- * fused conversion:
+ * as computeViewMatrix / computeProjectionMatrix define them, in float64) and a
+ * contiguous range of instances; one instance = a mesh of the bank (vertex and
+ * triangle ranges, triangle indices local to the mesh) placed by a rotation
+ * matrix (row-major) and a translation.  The reference delegates this step to
+ * Bullet's TinyRenderer, which is outside its tree: the exact sampling rules
+ * are the ones of oracle/csrc/oracle.c (DESIGN.md "raster").  Depth follows the
+ * GL convention the reference inverts (observer.py:259-260); `mode` selects the
+ * fused conversion, evaluated in float32 in numpy's operation order:
  *   SRL_RASTER_DEPTH  out = depth in [0,1] (background 1)
  *   SRL_RASTER_WALL   out = far - far*(far-zr)/(far - zr*d)            (:259-260)
- *   SRL_RASTER_ROCK   out = (far + zr/2 - (far^2-(zr/2)^2)/(far+zr*(1/2-d)))
- *                           with columns mirrored                       (:274-277)
- *   verts [nverts,3] f32 world space; tris [ntris,3] i32 vertex indices;
- *   jobs [njobs] srl_raster_job; out [njobs, rows, cols] f32. */
+ *   SRL_RASTER_ROCK   out = far + zr/2 - (far^2-(zr/2)^2)/(far + zr*(1/2-d)),
+ *                           columns mirrored                            (:274-277)
+ *   verts [nverts,3] f32; tris [ntris,3] i32; insts, jobs: device arrays of the
+ *   structs below; out [njobs, rows, cols] f32. */
 #define SRL_RASTER_DEPTH 0
 #define SRL_RASTER_WALL  1
 #define SRL_RASTER_ROCK  2
+typedef struct srl_raster_instance {
+  double rot[9];         /* row-major rotation, mesh frame -> world */
+  double pos[3];
+  int32_t vert_begin, vert_count, tri_begin, tri_count;
+} srl_raster_instance;
 typedef struct srl_raster_job {
-  float view[16];        /* column-major */
-  float proj[16];        /* column-major */
-  int32_t tri_begin;     /* first triangle of this image */
-  int32_t tri_count;
-  int32_t ground;        /* 1: an infinite z=0 ground plane is part of the scene */
-  float zrange;          /* zr above: max_z (wall) or object_z (rock) */
+  double view[16];       /* column-major */
+  double proj[16];       /* column-major */
+  int32_t inst_begin, inst_count;
+  double zrange;         /* zr above: max_z (wall) or object_z (rock) */
 } srl_raster_job;
 SRL_API int srl_raster(const float* verts, const int32_t* tris,
-               const srl_raster_job* jobs, float* out, int njobs, int rows,
-               int cols, int mode, double far_plane, srl_stream_t stream);
+                       const srl_raster_instance* insts, const srl_raster_job* jobs,
+                       float* out, int njobs, int rows, int cols, int mode,
+                       double far_plane, srl_stream_t stream);
 
 /* ---- a11: Rewarder._intersection/_union (rewarder.py:297-307) ---------------
  * inter[e] = sum(min(walls[e][goal != 0], goal_z[e])), uni[e] = sum(max(walls[e],
- * goals[e])), vol[e] = sum(goals[e]); float32 accumulation in numpy's pairwise
- * order is NOT reproduced (tolerance 1e-6 relative). */
+ * goals[e])), vol[e] = sum(goals[e]).  Accumulated in float64 and rounded once;
+ * numpy's float32 pairwise order is not reproduced (tolerance 1e-6 relative,
+ * see DESIGN.md). */
 SRL_API int srl_reward_sums_f32(const float* walls, const float* goals,
                         const float* goal_z, float* inter, float* uni,
                         float* vol, int E, int H, int W, srl_stream_t stream);
@@ -164,8 +172,6 @@ SRL_API int srl_pack_obs(const float* walls, const float* goals, const float* ro
                  void* wall_goal, void* rock, int E, int R, int H, int W, int h,
                  int dtype_code, float scale, int repeat_wall,
                  srl_stream_t stream);
-
-#endif  /* SRL_NEXT */
 
 /* ---- measurement helpers (not part of the reference's surface) --------------
  * Issue-rate micro-benchmark used to fix the FP32 roofline of the max-plus

@@ -148,8 +148,9 @@ void oracle_raster_depth(const float* verts, const int32_t* tris,
           float acc = w0 * d0;
           acc = acc + w1 * d1;
           acc = acc + w2 * d2;
-          const float d = acc / area;
+          float d = acc / area;
           if (!(d >= 0.f) || d > 1.f) continue;
+          if (d == 0.f) d = 0.f; /* +0: the device keeps depths as ordered uint bits */
           if (d < depth[i * cols + j]) depth[i * cols + j] = d;
         }
     }

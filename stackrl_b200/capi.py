@@ -46,7 +46,7 @@ _SIGNATURES = {
   'srl_select_f64': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_difference_weights': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
   'srl_difference_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
-  'srl_raster': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _P]),
+  'srl_raster': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_reward_sums_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
   'srl_pack_obs': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_float, _I, _P]),
   'srl_microbench_addmax': (_I, [_I, _I, _c.POINTER(_c.c_double)]),
@@ -213,6 +213,82 @@ def difference_f32(walls, rocks, level, weights, difference_exponent=2, want_top
                                   _opt(top, torch.float32, 'top'), E, R, H, W, h,
                                   int(difference_exponent), _stream()))
   return out, top
+
+
+# numpy mirrors of srl_raster_instance / srl_raster_job (include/stackrl_b200.h)
+import numpy as _np
+INSTANCE_DTYPE = _np.dtype([('rot', '<f8', (9,)), ('pos', '<f8', (3,)),
+                            ('vert_begin', '<i4'), ('vert_count', '<i4'),
+                            ('tri_begin', '<i4'), ('tri_count', '<i4')], align=True)
+JOB_DTYPE = _np.dtype([('view', '<f8', (16,)), ('proj', '<f8', (16,)),
+                       ('inst_begin', '<i4'), ('inst_count', '<i4'),
+                       ('zrange', '<f8')], align=True)
+assert INSTANCE_DTYPE.itemsize == 112 and JOB_DTYPE.itemsize == 272
+RASTER_DEPTH, RASTER_WALL, RASTER_ROCK = 0, 1, 2
+
+
+def raster(verts, tris, instances, jobs, rows, cols, mode, far_plane=1000., out=None):
+  """verts [NV,3] f32 / tris [NT,3] i32 CUDA tensors (the mesh bank),
+  instances / jobs numpy structured arrays (INSTANCE_DTYPE / JOB_DTYPE) or
+  CUDA uint8 tensors holding them -> [njobs, rows, cols] float32."""
+  dev = verts.device
+  def as_bytes(a, dtype):
+    if isinstance(a, torch.Tensor):
+      return a
+    a = _np.ascontiguousarray(a, dtype=dtype)
+    return torch.from_numpy(a.view(_np.uint8).reshape(-1)).to(dev, non_blocking=True)
+  njobs = len(jobs) if not isinstance(jobs, torch.Tensor) else jobs.numel() // JOB_DTYPE.itemsize
+  inst_t = as_bytes(instances, INSTANCE_DTYPE)
+  jobs_t = as_bytes(jobs, JOB_DTYPE)
+  if inst_t.numel() == 0:                      # a scene may be empty (ground only)
+    inst_t = torch.zeros(INSTANCE_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+  if verts.numel() == 0:
+    verts = torch.zeros((1, 3), dtype=torch.float32, device=dev)
+  if tris.numel() == 0:
+    tris = torch.zeros((1, 3), dtype=torch.int32, device=dev)
+  if out is None:
+    out = torch.empty((njobs, rows, cols), dtype=torch.float32, device=dev)
+  args = (_dev(verts, torch.float32, 'verts'), _dev(tris, torch.int32, 'tris'),
+          _dev(inst_t, torch.uint8, 'instances'), _dev(jobs_t, torch.uint8, 'jobs'),
+          _dev(out, torch.float32, 'out'))
+  with torch.cuda.device(dev):
+    _check(lib.srl_raster(*args, int(njobs), int(rows), int(cols), int(mode),
+                          float(far_plane), _stream()))
+  return out
+
+
+def reward_sums(walls, goals, goal_z):
+  """-> (intersection [E], union [E], goal volume [E]) float32."""
+  E, H, W = walls.shape
+  dev = walls.device
+  args = (_dev(walls, torch.float32, 'walls'), _dev(goals, torch.float32, 'goals'),
+          _dev(goal_z, torch.float32, 'goal_z'))
+  inter = torch.empty((E,), dtype=torch.float32, device=dev)
+  uni = torch.empty_like(inter)
+  vol = torch.empty_like(inter)
+  with torch.cuda.device(dev):
+    _check(lib.srl_reward_sums_f32(*args, _P(inter.data_ptr()), _P(uni.data_ptr()),
+                                   _P(vol.data_ptr()), E, H, W, _stream()))
+  return inter, uni, vol
+
+
+def pack_obs(walls, goals, rocks, dtype='float32', scale=1., repeat_wall=False):
+  """Planar maps -> reference-layout observation tensors
+  ([E,(R,)H,W,2], [E,R,h,h,1]) in float32 or uint8."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  dev = walls.device
+  tdt = {'float32': torch.float32, 'uint8': torch.uint8}[str(dtype)]
+  code = 0 if tdt == torch.float32 else 1
+  wg_shape = (E, R, H, W, 2) if repeat_wall else (E, H, W, 2)
+  args = (_dev(walls, torch.float32, 'walls'), _dev(goals, torch.float32, 'goals'),
+          _dev(rocks, torch.float32, 'rocks'))
+  wall_goal = torch.empty(wg_shape, dtype=tdt, device=dev)
+  rock = torch.empty((E, R, h, h, 1), dtype=tdt, device=dev)
+  with torch.cuda.device(dev):
+    _check(lib.srl_pack_obs(*args, _P(wall_goal.data_ptr()), _P(rock.data_ptr()),
+                            E, R, H, W, h, code, float(scale), int(bool(repeat_wall)),
+                            _stream()))
+  return wall_goal, rock
 
 
 def microbench_addmax(variant, iters=2000):

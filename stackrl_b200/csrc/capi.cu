@@ -118,6 +118,27 @@ int srl_difference_f32(const float* walls, const float* rocks, const float* leve
                              difference_exponent, (cudaStream_t)stream);
 }
 
+int srl_raster(const float* verts, const int32_t* tris, const srl_raster_instance* insts,
+               const srl_raster_job* jobs, float* out, int njobs, int rows, int cols,
+               int mode, double far_plane, srl_stream_t stream) {
+  return srl::raster(verts, tris, insts, jobs, out, njobs, rows, cols, mode, far_plane,
+                     (cudaStream_t)stream);
+}
+
+int srl_reward_sums_f32(const float* walls, const float* goals, const float* goal_z,
+                        float* inter, float* uni, float* vol, int E, int H, int W,
+                        srl_stream_t stream) {
+  return srl::reward_sums_f32(walls, goals, goal_z, inter, uni, vol, E, H, W,
+                              (cudaStream_t)stream);
+}
+
+int srl_pack_obs(const float* walls, const float* goals, const float* rocks,
+                 void* wall_goal, void* rock, int E, int R, int H, int W, int h,
+                 int dtype_code, float scale, int repeat_wall, srl_stream_t stream) {
+  return srl::pack_obs(walls, goals, rocks, wall_goal, rock, E, R, H, W, h, dtype_code,
+                       scale, repeat_wall, (cudaStream_t)stream);
+}
+
 int srl_microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   return srl::microbench_addmax(variant, iters, host_cells_per_s);
 }

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "stackrl_b200.h"
+
 namespace srl {
 
 int maxplus_f32(const float* walls, const float* rocks, const float* level,
@@ -35,6 +37,16 @@ int difference_weights(const float* rocks, const float* level, double* weights, 
 int difference_f32(const float* walls, const float* rocks, const float* level,
                    const double* weights, double* out, float* top, int E, int R, int H,
                    int W, int h, int difference_exponent, cudaStream_t stream);
+
+int raster(const float* verts, const int32_t* tris, const srl_raster_instance* insts,
+           const srl_raster_job* jobs, float* out, int njobs, int rows, int cols, int mode,
+           double far_plane, cudaStream_t stream);
+
+int pack_obs(const float* walls, const float* goals, const float* rocks, void* wall_goal,
+             void* rock, int E, int R, int H, int W, int h, int dtype_code, float scale,
+             int repeat_wall, cudaStream_t stream);
+int reward_sums_f32(const float* walls, const float* goals, const float* goal_z, float* inter,
+                    float* uni, float* vol, int E, int H, int W, cudaStream_t stream);
 
 int microbench_addmax(int variant, int iters, double* host_cells_per_s);
 

@@ -1,0 +1,252 @@
+"""Rasterisation + observation path on the GPU.
+
+Parity target: the oracle's software z-buffer (oracle/csrc/oracle.c through
+oracle.raster_np) -- NOT pybullet's TinyRenderer, which the reference uses but
+does not contain (PARITY UNPINNED for the depth image itself; the arithmetic the
+reference applies to it IS pinned by tests/golden/observe.npz).  CUDA and oracle
+run the same IEEE op sequence, so depth images and elevations are compared
+bit-for-bit, which is stricter than the 1e-5 relative bound of the task."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import observe_np as O
+from oracle import raster_np as R
+from stackrl_b200 import synth
+from tests.conftest import GEOM, split_depths
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def mods():
+  from stackrl_b200 import camera, capi, envs, meshes, observer
+  return dict(camera=camera, capi=capi, envs=envs, meshes=meshes, observer=observer)
+
+
+def _random_scene(meshes, seed, n_rocks, subdivisions=2):
+  rng = np.random.default_rng(seed)
+  verts, tris = meshes.synthetic_rocks(seed, n_rocks, subdivisions, max_dimension=0.12)
+  bodies = []
+  for k in range(n_rocks):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    pos = np.array([rng.uniform(0.08, 0.42), rng.uniform(0.08, 0.42), rng.uniform(0.03, 0.3)])
+    bodies.append((verts[k], tris, R.quat_matrix(q), pos))
+  return bodies
+
+
+def _gpu_render(mods, bodies, view, proj, rows, cols, mode, zrange):
+  obs, capi = mods['observer'], mods['capi']
+  verts, tris, inst = obs._instances(bodies)
+  job = obs._job(view, proj, 0, len(inst), zrange)
+  dev = torch.device('cuda')
+  return capi.raster(torch.from_numpy(verts).to(dev), torch.from_numpy(tris).to(dev),
+                     inst, job, rows, cols, mode)[0].cpu().numpy()
+
+
+@pytest.mark.parametrize('seed,n_rocks,sub', [(0, 1, 2), (1, 6, 2), (2, 12, 1), (3, 3, 3)])
+def test_wall_image_matches_oracle_bitwise(mods, seed, n_rocks, sub):
+  geo = mods['camera'].ObserverGeometry(128, 32, 0.125 / 32, 0.375)
+  bodies = _random_scene(mods['meshes'], seed, n_rocks, sub)
+  want_d = R.render_depth(geo.overhead_view, geo.overhead_projection, 128, 128, bodies)
+  got_d = _gpu_render(mods, bodies, geo.overhead_view, geo.overhead_projection, 128, 128,
+                      mods['capi'].RASTER_DEPTH, 0.375)
+  assert np.array_equal(got_d, want_d)
+  assert (want_d < 1).sum() > 50                      # something was drawn
+  got = _gpu_render(mods, bodies, geo.overhead_view, geo.overhead_projection, 128, 128,
+                    mods['capi'].RASTER_WALL, 0.375)
+  want = O.wall_elevation(want_d, 0.375)
+  assert np.array_equal(got, want)
+  np.testing.assert_allclose(got, want, rtol=1e-5, atol=0)   # the bound the task states
+
+
+@pytest.mark.parametrize('seed', [0, 5])
+def test_rock_images_all_orientations(mods, seed):
+  geo = mods['camera'].ObserverGeometry(128, 32, 0.16 / 32, 0.375, orientation_freedom=3)
+  verts, tris = mods['meshes'].synthetic_rocks(seed, 1, 3, max_dimension=0.16)
+  spawn = ((0., 0., 0.375 + 0.16), (0., 0., 0., 1.))
+  bodies = [(verts[0], tris, np.identity(3), np.array(spawn[0]))]
+  for k in range(8):
+    view = geo.object_view(spawn, k)
+    want_d = R.render_depth(view, geo.object_projection, 32, 32, bodies)
+    got = _gpu_render(mods, bodies, view, geo.object_projection, 32, 32,
+                      mods['capi'].RASTER_ROCK, geo.object_z)
+    want = O.rock_elevation(want_d, geo.object_z)
+    assert np.array_equal(got, want)
+    assert (got == 0).sum() > 20 and got.max() > geo.object_z / 2   # exact-zero background
+
+
+def test_box_known_answer(mods, observe_golden):
+  """The reference's perfect box 0_0.obj (half extents 0.0536 x 0.0268 x
+  0.0179 m) resting on the ground: flat top at 2*hz, footprint 2hx x 2hy."""
+  v, t = observe_golden['mesh/0_0/verts'], observe_golden['mesh/0_0/tris']
+  hx, hy, hz = np.abs(v).max(axis=0)
+  geo = mods['camera'].ObserverGeometry(128, 32, 0.125 / 32, 0.375)
+  bodies = [(v, t, np.identity(3), np.array([0.25, 0.25, hz]))]
+  m = _gpu_render(mods, bodies, geo.overhead_view, geo.overhead_projection, 128, 128,
+                  mods['capi'].RASTER_WALL, 0.375)
+  top = m[m > 0]
+  assert np.all(np.abs(top - 2 * hz) <= 2 ** -14 + 1e-7)     # float32 quantum at 1000 m
+  px = 0.125 / 32
+  assert abs(len(top) - (2 * hx / px) * (2 * hy / px)) <= 2 * (2 * hx + 2 * hy) / px
+  rows, cols = np.nonzero(m)
+  assert abs((rows.min() + rows.max() + 1) / 2 * px - 0.25) <= px    # rows run along x
+  assert rows.max() - rows.min() > cols.max() - cols.min()          # long side along x
+  assert np.all(m[m <= 0] == 0)                                     # ground exactly 0.0
+
+
+def test_sphere_underside_analytic(mods):
+  geo = mods['camera'].ObserverGeometry(128, 32, 0.125 / 32, 0.375)
+  v, t = mods['meshes'].icosphere(4)
+  radius = 0.05
+  spawn = ((0., 0., 0.5), (0., 0., 0., 1.))
+  bodies = [((v * radius).astype('float32'), t, np.identity(3), np.array(spawn[0]))]
+  m = _gpu_render(mods, bodies, geo.object_view(spawn, 0), geo.object_projection, 32, 32,
+                  mods['capi'].RASTER_ROCK, geo.object_z)
+  c = (np.arange(32) + 0.5 - 16) * (0.125 / 32)
+  rho2 = c[:, None] ** 2 + c[None, :] ** 2
+  inside = rho2 < (radius - 0.125 / 32) ** 2
+  want = geo.object_z / 2 + np.sqrt(np.clip(radius ** 2 - rho2, 0, None))
+  assert np.abs(m - want)[inside].max() < 4e-4         # faceting + 2^-14 quantisation
+  assert np.all(m[rho2 > (radius + 0.125 / 32) ** 2] == 0)
+
+
+def test_drop_lands_lowest_point_on_floor(mods):
+  """A rock rendered from below and max-plus-dropped on an empty floor rests
+  with its lowest vertex at z = 0 (known-answer 2)."""
+  from stackrl_b200 import capi
+  geo = mods['camera'].ObserverGeometry(128, 32, 0.125 / 32, 0.375)
+  verts, tris = mods['meshes'].synthetic_rocks(9, 1, 3, max_dimension=0.12)
+  spawn = ((0., 0., 0.5), (0., 0., 0., 1.))
+  bodies = [(verts[0], tris, np.identity(3), np.array(spawn[0]))]
+  rock = _gpu_render(mods, bodies, geo.object_view(spawn, 0), geo.object_projection, 32, 32,
+                     capi.RASTER_ROCK, geo.object_z)
+  dev = torch.device('cuda')
+  z = capi.drop_height_f32(torch.zeros((1, 128, 128), device=dev),
+                           torch.from_numpy(rock)[None, None].to(dev),
+                           torch.tensor([[0, 40, 40]], dtype=torch.int32, device=dev))
+  centre_z = z.item() - geo.object_z / 2
+  lowest = centre_z + float(verts[0][:, 2].min())
+  assert abs(lowest) < 1.5e-3                                # within pixel sampling of the tip
+
+
+def _fixture_bank(mods, g):
+  bank = mods['meshes'].MeshBank()
+  for name in g['mesh_names']:
+    bank.add(g['mesh/{}/verts'.format(name)], g['mesh/{}/tris'.format(name)],
+             g['mesh/{}/com'.format(name)], name=str(name))
+  return bank
+
+
+@pytest.mark.parametrize('name,dtype,freedom', [('stack_f32', 'float32', 0),
+                                                ('stack_u8', 'uint8', 0),
+                                                ('test_f32_rot8', 'float32', 3)])
+def test_batched_env_replays_reference_episode(mods, observe_golden, name, dtype, freedom):
+  """BatchedStackEnv + the GPU height policy reproduce, step for step, the
+  episode the UNMODIFIED reference StackEnv / TestStackEnv produced with
+  Baseline('height') on the static fake backend: same observations (bitwise),
+  same actions, same rewards (IoU within 1e-6)."""
+  g = observe_golden
+  envs = mods['envs']
+  bank = _fixture_bank(mods, g)
+  steps = int(g[name + '/n_steps'])
+  order = [bank.names[str(n)] for n in g[name + '/urdf_order']][::-1]
+  lims = g[name + '/goal_lims']
+  E = 3                                                # three identical replicas
+  env = envs.BatchedStackEnv(bank, E, episode_length=steps, dtype=dtype, rewarder='iou',
+                             orientation_freedom=freedom, seed=0)
+  policy = envs.HeightPolicy()
+  obs, _, _ = env.reset(rock_orders=[order] * E, goal_lims=[lims] * E)
+  assert np.array_equal(env.goals[0].cpu().numpy(), g[name + '/goal'])
+  for k in range(steps):
+    key = '{}/s{}'.format(name, k)
+    assert np.array_equal(env.obs.walls[1].cpu().numpy(), g[key + '/overhead_map'])
+    rock = env.obs.rocks[1].cpu().numpy()
+    assert np.array_equal(rock if freedom else rock[0], g[key + '/object_map'])
+    for e in range(E):
+      assert np.array_equal(obs[0][e].cpu().numpy(), g[key + '/obs0'])
+      assert np.array_equal(obs[1][e].cpu().numpy(), g[key + '/obs1'])
+    action = policy(env)
+    if freedom:
+      got = (int(action[0][0]), int(action[1][0]))
+      assert got == tuple(int(x) for x in g[key + '/action'])
+    else:
+      assert int(action[0]) == int(g[key + '/action'])
+    obs, reward, terminal = env.step(action)
+    placed = env._placed[0][-1]
+    assert np.array_equal(placed[0], g[key + '/pose_position'])
+    if freedom:
+      assert np.allclose(placed[2], g[key + '/pose_orientation'], atol=1e-15)
+    np.testing.assert_allclose(reward.cpu().numpy(), g[key + '/rewards'][0], rtol=1e-6,
+                               atol=1e-9)
+    assert bool(terminal[0]) == (k == steps - 1)
+  assert np.array_equal(obs[0][0].cpu().numpy(), g['{}/s{}/obs0'.format(name, steps)])
+
+
+def test_drop_in_observer_against_recorded_maps(mods, observe_golden):
+  """gpu_observer_class: the single-environment Observer API driven by a
+  scene()-exposing simulator reproduces the reference Observer's maps."""
+  g = observe_golden
+  name = 'test_f32_rot8'
+  order = [str(n) for n in g[name + '/urdf_order']]
+
+  class Sim(object):
+    new_pose = ((0., 0., 0.375 + 0.125), (0., 0., 0., 1.))
+    def __init__(self):
+      self.bodies, self._new = [], True
+    @property
+    def has_new_object(self):
+      new, self._new = self._new, False
+      return new
+    def add(self, mesh, pos, quat):
+      v, t, com = (g['mesh/{}/{}'.format(mesh, k)] for k in ('verts', 'tris', 'com'))
+      rot = R.quat_matrix(quat)
+      self.bodies.append((v, t, rot, np.asarray(pos) - rot.dot(com)))
+      self._new = True
+    def scene(self):
+      return list(self.bodies)
+
+  sim = Sim()
+  Obs = mods['observer'].gpu_observer_class(object)
+  obs = Obs(sim, overhead_resolution=128, object_resolution=32, pixel_size=0.125 / 32,
+            max_z=0.375, orientation_freedom=3)
+  placed = []
+  for k in range(3):
+    sim.bodies = list(placed)
+    sim.add(order[k], *Sim.new_pose)                     # the spawned, unplaced rock
+    obs()
+    wall, rocks = obs.state
+    key = '{}/s{}'.format(name, k)
+    assert np.array_equal(wall, g[key + '/overhead_map'])
+    assert np.array_equal(np.array(rocks), g[key + '/object_map'])
+    assert obs.num_objects == 8 and obs.shape == ((128, 128), (32, 32))
+    view, flat = (int(x) for x in g[key + '/action'])
+    pose = obs.pose([flat // 97, flat % 97], index=view)
+    assert np.array_equal(np.array(pose['position'], dtype='float64'), g[key + '/pose_position'])
+    assert np.allclose(pose['orientation'], g[key + '/pose_orientation'], atol=1e-15)
+    v, t, com = (g['mesh/{}/{}'.format(order[k], n)] for n in ('verts', 'tris', 'com'))
+    rot = R.quat_matrix(pose['orientation'])
+    placed.append((v, t, rot, np.asarray(pose['position'], dtype='float64') - rot.dot(com)))
+
+
+def test_pack_and_reward_kernels(mods):
+  capi = mods['capi']
+  E, R_, H, W, h = 5, 3, 32, 40, 8
+  walls, rocks, _ = synth.placement_batch(3, E, R_, H, W, h)
+  goals = synth.goals(4, E, H, W)
+  dev = torch.device('cuda')
+  wd, gd, rd = (torch.from_numpy(x).to(dev) for x in (walls, goals, rocks))
+  for dtype in ('float32', 'uint8'):
+    wg, rk = capi.pack_obs(wd, gd, rd, dtype=dtype, scale=0.375)
+    wg2, rk2 = capi.pack_obs(wd, gd, rd, dtype=dtype, scale=0.375, repeat_wall=True)
+    for e in range(E):
+      want = O.pack_obs_batched(walls[e], goals[e], list(rocks[e]), dtype, 0.375, 0.125)
+      assert np.array_equal(wg[e].cpu().numpy(), want[0][0])
+      assert np.array_equal(wg2[e].cpu().numpy(), want[0])
+      assert np.array_equal(rk[e].cpu().numpy(), want[1])
+  inter, uni, vol = capi.reward_sums(wd, gd, torch.full((E,), 0.25, device=dev))
+  for e in range(E):
+    np.testing.assert_allclose(inter[e].item(), O.intersection(walls[e], goals[e], 0.25), rtol=1e-6)
+    np.testing.assert_allclose(uni[e].item(), O.union(walls[e], goals[e]), rtol=1e-6)
+    np.testing.assert_allclose(vol[e].item(), goals[e].sum(), rtol=1e-6)
