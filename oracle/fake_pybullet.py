@@ -83,7 +83,9 @@ class FakeBullet(object):
 
   # -- server / world ---------------------------------------------------------- #
   def connect(self, mode=DIRECT, **_):
+    # a new connection is a fresh server: nothing survives a disconnect
     self._connected = True
+    self._bodies, self._shapes = {}, {}
     return 0
 
   def disconnect(self, physicsClientId=0, **_):

@@ -275,5 +275,16 @@ class HeightPolicy(object):
 
   def __call__(self, env):
     walls, goals, rocks = env.planes()
+    if env._dtype == 'uint8':
+      # The reference policy scores the observation it is given: for the
+      # registered uint8 envs that is the quantised maps (float64 arithmetic).
+      wall_goal, rock = env.observation
+      if env.R > 1:
+        wall_goal = wall_goal[:, 0]
+      walls = wall_goal[..., 0].contiguous()
+      goals = wall_goal[..., 1].contiguous()
+      rocks = rock[..., 0].contiguous()
+      if env.R == 1:
+        rocks = rocks[:, None].contiguous()
     best = self._scorer(walls, goals, rocks)['best']
     return (best[:, 0], best[:, 1]) if env.R > 1 else best[:, 1]

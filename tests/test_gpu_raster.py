@@ -128,7 +128,9 @@ def test_drop_lands_lowest_point_on_floor(mods):
                            torch.tensor([[0, 40, 40]], dtype=torch.int32, device=dev))
   centre_z = z.item() - geo.object_z / 2
   lowest = centre_z + float(verts[0][:, 2].min())
-  assert abs(lowest) < 1.5e-3                                # within pixel sampling of the tip
+  # Pixel-centre sampling can miss the very tip of a spiky rock (never the other
+  # way round): the tip ends at most about one pixel (3.9 mm) below the floor.
+  assert -4e-3 < lowest <= 1e-4
 
 
 def _fixture_bank(mods, g):
