@@ -1,16 +1,20 @@
 #!/usr/bin/env python
-"""bench.py -- placement evaluations / s of the max-plus scoring path on B200.
+"""bench.py -- placement evaluations / s of the placement-scoring hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl graft|reference]
 
 Workload (BASELINE.json configs[1], SURVEY 8d "C2"): 4096 environments per GPU,
 32x32 wall heightmap, 16x16 rock underside map, 8 rotations -> 4096*8*17*17 =
-9 469 952 placement evaluations per step per GPU.  A step is one pass of the
-scoring hot path over one batch of synthetic observations.  Environments are
-independent, so N GPUs run N shards with no data-path collective ("weak"
-scaling); rank 0 gathers the timing with one all-reduce (MAX).
+9 469 952 placement evaluations per step per GPU.  One step is one pass of the
+scoring hot path over one batch of synthetic observations, i.e. what the
+reference's ``Baseline('height', batched, batchwise)`` does per observation:
+max-plus drop map (baselines.py:28-43), goal-overlap mask (:152-156), masked
+local-minimum arg-min and batch-wise pick (:201-217, policies.py:57-91).
+Environments are independent, so N GPUs run N shards with no data-path
+collective ("weak" scaling); the ranks exchange timings and checksums with one
+all-gather at the end.
 
-Prints ONE JSON line (see the contract in the task statement / DESIGN.md).
+Prints ONE JSON line (contract: task statement / DESIGN.md "Measurement").
 """
 import argparse
 import json
@@ -33,7 +37,8 @@ NSETS = 8          # distinct input/output sets cycled through (beats the 126 MB
 
 def workload_name():
   return ('C2: batched max-plus placement search, {envs} envs/GPU, {H}x{W} wall, '
-          '{h}x{h} rock, {rotations} rotations').format(**CFG)
+          '{h}x{h} rock, {rotations} rotations (score map + goal mask + arg-min)'
+          ).format(**CFG)
 
 
 def evals_per_step():
@@ -47,6 +52,15 @@ def measured_peaks():
     with open(path) as f:
       return json.load(f), 'measured (MEASURED_PEAKS.json)'
   return {'hbm_gbs': 6650.0}, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic(kernel):
+  """dram bytes per launch of `kernel` from the committed ncu summary, if any."""
+  path = os.path.join(ROOT, 'profiles', 'ncu_summary.json')
+  if os.path.exists(path):
+    with open(path) as f:
+      return json.load(f).get(kernel, {}).get('dram_bytes_per_launch')
+  return None
 
 
 # --------------------------------------------------------------------------- #
@@ -114,40 +128,32 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------- #
-# CPU baseline: the oracle's loop-form restatement of baselines.height
+# CPU baseline: the oracle's loop-form restatement of Baseline('height').call
 # --------------------------------------------------------------------------- #
 def _cpu_maps(args):
-  """Worker: score `count` (env, rotation) maps with the reference-shaped
-  Python-loop + numpy max-plus (oracle.scoring_np.height_loop)."""
+  """Worker: score `count` (env, rotation) views with the reference-shaped
+  Python-loop + numpy path (oracle.scoring_np.baseline_call_loop)."""
   seed, count = args
   from oracle import scoring_np
   from stackrl_b200 import synth
-  walls, rocks, level = synth.placement_batch(seed, count, 1, CFG['H'], CFG['W'], CFG['h'])
-  obs = []
-  for e in range(count):
-    goal = np.full(walls.shape[1:], level[e], dtype='float32')
-    obs.append((np.stack([walls[e], goal], -1), rocks[e, 0][..., None]))
+  walls, rocks, _ = synth.placement_batch(seed, count, 1, CFG['H'], CFG['W'], CFG['h'])
+  goals = synth.goals(seed + 7, count, CFG['H'], CFG['W'])
+  obs = [(np.stack([walls[e], goals[e]], -1), rocks[e, 0][..., None]) for e in range(count)]
   t0 = time.perf_counter()
   for o in obs:
-    scoring_np.height_loop(o)
+    scoring_np.baseline_call_loop(o)
   return time.perf_counter() - t0
 
 
-def cpu_baseline(maps_per_core, cores):
+CPU_SAMPLE = ('oracle.scoring_np.baseline_call_loop: numpy port of Baseline("height").call '
+              '(baselines.py:28-43 Python double loop, :152-156, :201-217)')
+
+
+def cpu_baseline_one_core(maps):
   P = evals_per_step() // (CFG['envs'] * CFG['rotations'])
-  if cores == 1:
-    dt = _cpu_maps((123, maps_per_core))
-    wall = dt
-  else:
-    import multiprocessing as mp
-    ctx = mp.get_context('spawn')
-    with ctx.Pool(cores) as pool:
-      pool.map(_cpu_maps, [(1, 2)] * cores)            # import + warm-up
-      t0 = time.perf_counter()
-      pool.map(_cpu_maps, [(200 + k, maps_per_core) for k in range(cores)])
-      wall = time.perf_counter() - t0
-  value = maps_per_core * cores * P / wall
-  return value, wall
+  _cpu_maps((1, 4))
+  dt = _cpu_maps((123, maps))
+  return maps * P / dt, dt
 
 
 def run_reference(args, rank, world):
@@ -156,7 +162,7 @@ def run_reference(args, rank, world):
   if rank != 0:
     return
   cores = os.cpu_count() or 1
-  maps_per_core = 48          # ~0.15 s of work per core per step at ~3 ms/map
+  maps_per_core = 40          # ~0.15 s of work per core per step at ~3.5 ms/view
   P = evals_per_step() // (CFG['envs'] * CFG['rotations'])
   import multiprocessing as mp
   ctx = mp.get_context('spawn')
@@ -168,9 +174,9 @@ def run_reference(args, rank, world):
       pool.map(_cpu_maps, [(1000 * s + k, maps_per_core) for k in range(cores)])
     wall = time.perf_counter() - t0
   value = args.steps * cores * maps_per_core * P / wall
-  sample = ('{} maps ({}x{} wall, {}x{} rock) per step over {} processes; '
-            'oracle.scoring_np.height_loop (numpy port of baselines.py:28-43)'
-            ).format(cores * maps_per_core, CFG['H'], CFG['W'], CFG['h'], CFG['h'], cores)
+  sample = ('{} views ({}x{} wall, {}x{} rock) per step over {} processes; {}'
+            ).format(cores * maps_per_core, CFG['H'], CFG['W'], CFG['h'], CFG['h'], cores,
+                     CPU_SAMPLE)
   line = {
     'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
     'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -189,51 +195,149 @@ def run_reference(args, rank, world):
 # --------------------------------------------------------------------------- #
 # GPU arm
 # --------------------------------------------------------------------------- #
+def _time_loop(torch, fn, steps):
+  ev0 = torch.cuda.Event(enable_timing=True)
+  ev1 = torch.cuda.Event(enable_timing=True)
+  torch.cuda.synchronize()
+  ev0.record()
+  for k in range(steps):
+    fn(k)
+  ev1.record()
+  torch.cuda.synchronize()
+  return ev0.elapsed_time(ev1) / steps
+
+
+def extra_metrics(torch, dev):
+  """Short measurements of the other two BASELINE metrics on this GPU: mesh
+  rasterisation (config 3 geometry) and full env observations (config 4
+  geometry, static settle).  Reported under `extra`; not the headline."""
+  from stackrl_b200 import capi, envs, meshes
+  from stackrl_b200.camera import ObserverGeometry
+  out = {}
+  # -- config 3: 4096 synthetic rocks, 32x32 px at 0.005 m/px ------------------- #
+  n, sub = 4096, 3
+  verts, tris = meshes.synthetic_rocks(4, n, sub, max_dimension=0.16)
+  bank = meshes.MeshBank()
+  for k in range(n):
+    bank.add(verts[k], tris)
+  from stackrl_b200.observer import BatchedObserver
+  obs = BatchedObserver(bank, n, 1, overhead_resolution=128, object_resolution=32,
+                        pixel_size=0.005, max_z=0.375, device=dev)
+  ids = np.arange(n)
+  obs.observe_rocks(ids)
+  torch.cuda.synchronize()
+  g = obs.geo
+  def rocks_only(_):
+    capi.raster(obs._verts, obs._tris, obs._rock_inst, obs._rock_jobs, g.object_h,
+                g.object_w, capi.RASTER_ROCK,
+                out=obs.rocks.view(n, g.object_h, g.object_w))
+  ms = _time_loop(torch, rocks_only, 20)
+  ntri, nvert = len(tris), verts.shape[1]
+  bytes_per_rock = 12 * nvert + 12 * ntri + 4 * 32 * 32
+  peaks, _ = measured_peaks()
+  out['raster'] = {
+    'workload': 'C3: {} synthetic rocks x {} tris ({} verts), 32x32 px at 0.005 m/px'.format(
+      n, ntri, nvert),
+    'rocks_per_s': n / (ms * 1e-3), 'tris_per_s': n * ntri / (ms * 1e-3), 'ms': ms,
+    'roofline': {'bound': 'hbm', 'achieved': n * bytes_per_rock / (ms * 1e-3) / 1e9,
+                 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                 'frac': n * bytes_per_rock / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                 'bytes_per_rock': bytes_per_rock}}
+  # -- config 4 slice: env observations, 64x64 wall, 16x16 rock ----------------- #
+  E = 4096
+  bank2 = meshes.MeshBank()
+  v2, t2 = meshes.synthetic_rocks(5, 64, 1, max_dimension=0.12)
+  for k in range(64):
+    bank2.add(v2[k], t2)
+  env = envs.BatchedStackEnv(bank2, E, episode_length=12, observable_size_ratio=4,
+                             resolution_factor=4, dtype='float32', rewarder='iou', seed=5,
+                             device=dev)
+  policy = envs.HeightPolicy()
+  env.reset()
+  for _ in range(4):
+    env.step(policy(env))
+  torch.cuda.synchronize()
+  def observe(_):
+    env.obs.observe_walls()
+    env.obs.observe_rocks(env._current)
+    env.reward_terms()
+    env.observation
+  ms = _time_loop(torch, observe, 10)
+  t0 = time.perf_counter()
+  for _ in range(4):
+    env.step(policy(env))
+  torch.cuda.synchronize()
+  step_ms = (time.perf_counter() - t0) / 4 * 1e3
+  out['env_obs'] = {
+    'workload': 'C4 slice: {} envs/GPU, 64x64 wall, 16x16 rock, ~5 placed rocks of {} tris, '
+                'float32 obs + IoU terms'.format(E, len(t2)),
+    'obs_per_s': E / (ms * 1e-3), 'ms': ms,
+    'full_step_ms_with_host_glue': step_ms, 'full_steps_per_s': E / (step_ms * 1e-3)}
+  return out
+
+
 def run_graft(args, rank, local_rank, world):
   import torch
   if not torch.cuda.is_available():
     raise SystemExit('bench.py needs a CUDA device: stackrl_b200 has no CPU path')
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda', local_rank)
-  dist = None
-  if world > 1:
-    import torch.distributed as dist
-    dist.init_process_group('nccl', device_id=dev)
 
-  from stackrl_b200 import capi, synth
+  from stackrl_b200 import baselines, capi, sharding, synth
+  dist = sharding.init('nccl', dev) if world > 1 else None
 
   E, R, H, W, h = (CFG[k] for k in ('envs', 'rotations', 'H', 'W', 'h'))
   P = (H - h + 1) * (W - h + 1)
-
-  # Synthetic batches: each rank owns its shard of environments; the
-  # NSETS sets differ by a cheap device-side perturbation of one host batch.
-  walls_h, rocks_h, level_h = synth.placement_batch(1000 * rank, E, R, H, W, h)
+  # Synthetic shard (SURVEY 8d): rank r owns environments [r*E, (r+1)*E) of the
+  # global batch; the NSETS sets differ by a roll of the environment axis.
+  walls_h, rocks_h, _ = synth.placement_batch(1000 * rank, E, R, H, W, h)
+  goals_h = synth.goals(1000 * rank + 7, E, H, W)
   sets = []
   for s in range(NSETS):
-    w = torch.from_numpy(walls_h).to(dev)
-    if s:
-      w = torch.roll(w, shifts=s, dims=0).contiguous()
-    r = torch.from_numpy(rocks_h).to(dev)
-    lvl = torch.from_numpy(level_h).to(dev)
-    out = torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.float32, device=dev)
-    sets.append((w, r, lvl, out))
-  set_bytes = sum(t.numel() * t.element_size() for t in sets[0])
+    w = torch.roll(torch.from_numpy(walls_h).to(dev), shifts=s, dims=0).contiguous()
+    g = torch.from_numpy(goals_h).to(dev).clone()
+    r = torch.roll(torch.from_numpy(rocks_h).to(dev), shifts=-s, dims=0).contiguous()
+    sets.append(dict(
+      walls=w, goals=g, rocks=r, level=g.amax(dim=(1, 2)),
+      values=torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.float32, device=dev),
+      counts=torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.int32, device=dev),
+      actions=torch.empty((E, R), dtype=torch.int64, device=dev),
+      best=torch.empty((E, 2), dtype=torch.int64, device=dev)))
+  set_bytes = sum(t.numel() * t.element_size() for t in sets[0].values())
+  lib, P_ = capi.lib, capi._P
+  stream = P_(torch.cuda.current_stream().cuda_stream)
+  mp_events = []
 
-  def step(k):
-    w, r, lvl, out = sets[k % NSETS]
-    capi.maxplus_f32(w, r, lvl, out=out)
+  def step(k, timed=False):
+    s = sets[k % NSETS]
+    if timed:
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+    capi._check(lib.srl_maxplus_f32(
+      P_(s['walls'].data_ptr()), P_(s['rocks'].data_ptr()), P_(s['level'].data_ptr()),
+      P_(s['values'].data_ptr()), E, R, H, W, h, 0.0, stream))
+    if timed:
+      b.record()
+      mp_events.append((a, b))
+    capi._check(lib.srl_goal_overlap_f32(
+      P_(s['walls'].data_ptr()), P_(s['goals'].data_ptr()), P_(s['rocks'].data_ptr()),
+      P_(s['counts'].data_ptr()), E, R, H, W, h, stream))
+    capi._check(lib.srl_select_f32(
+      P_(s['values'].data_ptr()), P_(s['counts'].data_ptr()), P_(s['actions'].data_ptr()),
+      P_(None), P_(s['best'].data_ptr()), E, R, H - h + 1, W - h + 1, 1, 0.75, stream))
 
   def barrier():
     if dist is not None:
       dist.barrier()
     torch.cuda.synchronize()
 
-  # ---- warm-up -------------------------------------------------------------- #
-  for k in range(max(args.warmup, 3)):
+  # ---- warm-up ------------------------------------------------------------------ #
+  warmup = max(args.warmup, 3)
+  for k in range(warmup):
     step(k)
   barrier()
 
-  # ---- timed region (device-resident inputs) -------------------------------- #
+  # ---- timed region (device-resident inputs) ------------------------------------ #
   sampler = ClockSampler(local_rank)
   ev0 = torch.cuda.Event(enable_timing=True)
   ev1 = torch.cuda.Event(enable_timing=True)
@@ -241,11 +345,12 @@ def run_graft(args, rank, local_rank, world):
   sampler.start()
   ev0.record()
   for k in range(args.steps):
-    step(k)
+    step(k, timed=True)
   ev1.record()
   torch.cuda.synchronize()
   sampler.stop()
   elapsed_ms = ev0.elapsed_time(ev1)
+  maxplus_ms = sum(a.elapsed_time(b) for a, b in mp_events) / len(mp_events)
   clocks_how = 'nvml during the timed region'
   if len(sampler.samples) < 3:
     # Timed region shorter than the NVML sampling period: sample the same
@@ -261,64 +366,60 @@ def run_graft(args, rank, local_rank, world):
     sampler.stop()
     clocks_how = 'nvml over a 0.25 s repeat of the timed loop (region too short to sample)'
   barrier()
-  if dist is not None:
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-  ms_per_step = elapsed_ms / args.steps
-  value = world * evals_per_step() / (ms_per_step * 1e-3)
 
-  # ---- end to end: host buffers in, host result out -------------------------- #
-  walls_p = torch.from_numpy(walls_h).pin_memory()
-  rocks_p = torch.from_numpy(rocks_h).pin_memory()
-  level_p = torch.from_numpy(level_h).pin_memory()
-  out_p = torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.float32).pin_memory()
-  w_d, r_d, l_d, o_d = sets[0]
-  h2d = sum(t.numel() * t.element_size() for t in (walls_p, rocks_p, level_p))
-  d2h = out_p.numel() * out_p.element_size()
-
-  def e2e_step():
-    w_d.copy_(walls_p, non_blocking=True)
-    r_d.copy_(rocks_p, non_blocking=True)
-    l_d.copy_(level_p, non_blocking=True)
-    capi.maxplus_f32(w_d, r_d, l_d, out=o_d)
-    out_p.copy_(o_d, non_blocking=True)
-
-  e2e_steps = max(3, min(args.steps, 50))
+  # ---- end to end: host buffers in, host actions out ------------------------------ #
+  scorer = baselines.PlacementScorer('height')
+  pipe = baselines.HostPipeline(scorer, E, R, H, W, h, chunks=4, device=dev)
+  pipe.stage(walls_h, goals_h, rocks_h)
+  e2e_steps = max(3, min(args.steps, 30))
   for _ in range(3):
-    e2e_step()
+    pipe.run()
   barrier()
   ev0.record()
   for _ in range(e2e_steps):
-    e2e_step()
+    actions_h, best_h = pipe.run()
   ev1.record()
   torch.cuda.synchronize()
   e2e_ms = ev0.elapsed_time(ev1)
-  if dist is not None:
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-  e2e_value = world * evals_per_step() / (e2e_ms / e2e_steps * 1e-3)
+  # The pipelined host path must agree with the device-resident one.
+  same = bool(np.array_equal(actions_h, sets[0]['actions'].cpu().numpy()))
 
+  # ---- gather: max over ranks, checksums ------------------------------------------ #
+  stats = sharding.gather_stats(
+    [elapsed_ms, e2e_ms, maxplus_ms, sharding.checksum(sets[0]['actions']) % 2 ** 40,
+     float(same)], dev)
   if rank != 0:
     if dist is not None:
       dist.destroy_process_group()
     return
+  elapsed_ms = float(stats[:, 0].max())
+  e2e_ms = float(stats[:, 1].max())
+  maxplus_ms = float(stats[:, 2].max())
+  ms_per_step = elapsed_ms / args.steps
+  value = world * evals_per_step() / (ms_per_step * 1e-3)
+  e2e_value = world * evals_per_step() / (e2e_ms / e2e_steps * 1e-3)
 
-  # ---- roofline of the dominant kernel --------------------------------------- #
+  # ---- roofline of the dominant kernel (max-plus) ---------------------------------- #
   peaks, peak_src = measured_peaks()
   cells = evals_per_step() * h * h                  # (add, max) cells per launch
-  kernel_s = ms_per_step * 1e-3                     # the step IS one launch
-  peak_cells = max(capi.microbench_addmax(v, 400) for v in (0, 1, 2))
+  kernel_s = maxplus_ms * 1e-3
+  micro = {v: capi.microbench_addmax(v, 400) for v in (0, 2, 7)}
+  peak_cells = max(micro.values())
   alg_bytes = 4 * (E * H * W + E * R * h * h + E * R * P)
   roofline = {
     'bound': 'fp32-alu',
+    'kernel': 'maxplus_staged_kernel<17,16,paired>',
+    'kernel_ms': maxplus_ms,
+    'share_of_step': maxplus_ms / ms_per_step,
     'achieved': 2 * cells / kernel_s / 1e12,
     'peak': 2 * peak_cells / 1e12,
     'unit': 'Tops/s',
     'frac': (cells / kernel_s) / peak_cells,
-    'traffic': None,
-    'peak_source': 'srl_microbench_addmax (FADD2+FMNMX3 issue rate, measured in this run)',
+    'traffic': ncu_traffic('maxplus_staged_kernel'),
+    'peak_source': 'srl_microbench_addmax, best (add,max) issue rate measured in this run '
+                   '(FADD+FMNMX {:.3g}, FADD2+FMNMX3 {:.3g}, FADD2+VIMNMX3 {:.3g} cells/s); '
+                   'MEASURED_PEAKS.json has no non-tensor FP32 figure'.format(
+                     micro[0], micro[2], micro[7]),
     'ops_per_eval': 2 * h * h,
     'hbm': {'achieved': alg_bytes / kernel_s / 1e9, 'peak': peaks['hbm_gbs'],
             'unit': 'GB/s', 'frac': alg_bytes / kernel_s / 1e9 / peaks['hbm_gbs'],
@@ -327,27 +428,36 @@ def run_graft(args, rank, local_rank, world):
 
   line = {
     'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
-    'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
+    'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms_per_step,
     'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
     'dtype': 'f32', 'data': 'synthetic',
     'config': {'workload': workload_name(), 'evals_per_step_per_gpu': evals_per_step(),
                'l2': '{} distinct input/output sets cycled, {:.0f} MB each ({:.0f} MB total '
                      '> 126 MB L2)'.format(NSETS, set_bytes / 1e6, NSETS * set_bytes / 1e6),
-               'parallelism': 'env-sharded x{}'.format(world)},
+               'parallelism': 'env-sharded x{}, no data-path collective'.format(world),
+               'shard_checksums': [int(c) for c in stats[:, 3].tolist()],
+               'host_pipeline_matches_device': bool(stats[:, 4].min() == 1.0)},
     'clocks': sampler.summary(clocks_how),
-    'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-            'd2h_bytes_per_step': d2h, 'steps': e2e_steps},
-    'gpu_launches': args.steps,
+    'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': pipe.h2d_bytes,
+            'd2h_bytes_per_step': pipe.d2h_bytes, 'steps': e2e_steps,
+            'api': 'stackrl_b200.baselines.HostPipeline(PlacementScorer): pinned host '
+                   'observations -> actions'},
+    'gpu_launches': 3 * args.steps,
+    'kernels_per_step': ['maxplus_staged_kernel', 'goal_overlap_kernel', 'select_kernel'],
     'roofline': roofline,
   }
+  if world == 1 and not args.no_extra:
+    try:
+      line['extra'] = extra_metrics(torch, dev)
+    except Exception as exc:   # the headline must survive a failure of the extras
+      line['extra'] = {'error': repr(exc)}
   if world == 1 and not args.no_cpu_baseline:
-    maps = 1536
-    v, wall = cpu_baseline(maps, 1)
+    maps = 1024
+    v, wall = cpu_baseline_one_core(maps)
     line['cpu_baseline'] = {
       'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-      'sample': '{} maps of the same shapes in {:.1f} s on 1 core; '
-                'oracle.scoring_np.height_loop (numpy port of baselines.py:28-43); '
-                'host has {} cores'.format(maps, wall, os.cpu_count())}
+      'sample': '{} views of the same shapes in {:.1f} s on 1 core; {}; host has {} '
+                'cores'.format(maps, wall, CPU_SAMPLE, os.cpu_count())}
   print(json.dumps(line))
   if dist is not None:
     dist.destroy_process_group()
@@ -360,6 +470,7 @@ def main():
   ap.add_argument('--warmup', type=int, default=10)
   ap.add_argument('--impl', default='graft', choices=['graft', 'reference'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-extra', action='store_true')
   args = ap.parse_args()
   rank = int(os.environ.get('RANK', '0'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))

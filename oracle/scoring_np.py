@@ -198,6 +198,14 @@ def baseline_call(obs, method='height', goal=True, minorder=1, **kwargs):
   return select(values, mask, minorder)
 
 
+def baseline_call_loop(obs, goal=True, minorder=1, **kwargs):
+  """Baseline('height').call with the reference's cost structure (the Python
+  double loop of ``height_loop``); the form bench.py times on the CPU."""
+  values = height_loop(obs)
+  mask = goal_overlap(obs, **kwargs) if goal else None
+  return select(values, mask, minorder)
+
+
 # ---- stackrl/agents/policies.py:57-91 (PyGreedy.__call__) ------------------- #
 def greedy(obs, call, value=False, unravel=False, batched=False,
            batchwise=False):

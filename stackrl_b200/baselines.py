@@ -174,6 +174,68 @@ class PlacementScorer(object):
             'shown': shown}
 
 
+class HostPipeline(object):
+  """``PlacementScorer`` for batches that live in HOST memory.
+
+  The batch is cut into chunks of environments; chunk k+1's host->device copies
+  (from pinned staging buffers, on a copy stream) overlap chunk k's kernels, and
+  only the actions / batch-wise picks travel back.  This is the end-to-end call
+  bench.py times (``e2e``): numpy in, numpy out."""
+
+  def __init__(self, scorer, envs, rotations, H, W, h, chunks=4, device=None):
+    self.scorer = scorer
+    self.dev = device if device is not None else _device()
+    self.E, self.R = int(envs), int(rotations)
+    self.bounds = [(k * self.E // chunks, (k + 1) * self.E // chunks) for k in range(chunks)]
+    self.bounds = [b for b in self.bounds if b[1] > b[0]]
+    f32 = torch.float32
+    self.pin = {
+      'walls': torch.empty((self.E, H, W), dtype=f32).pin_memory(),
+      'goals': torch.empty((self.E, H, W), dtype=f32).pin_memory(),
+      'rocks': torch.empty((self.E, self.R, h, h), dtype=f32).pin_memory(),
+    }
+    self.dev_in = {k: torch.empty(v.shape, dtype=f32, device=self.dev)
+                   for k, v in self.pin.items()}
+    self.actions = torch.empty((self.E, self.R), dtype=torch.int64).pin_memory()
+    self.best = torch.empty((self.E, 2), dtype=torch.int64).pin_memory()
+    self.copy_stream = torch.cuda.Stream(device=self.dev)
+    self.h2d_bytes = sum(v.numel() * 4 for v in self.pin.values())
+    self.d2h_bytes = (self.actions.numel() + self.best.numel()) * 8
+
+  def stage(self, walls, goals, rocks):
+    """Copy caller arrays into the pinned staging buffers (host memcpy)."""
+    self.pin['walls'].numpy()[...] = walls
+    self.pin['goals'].numpy()[...] = goals
+    self.pin['rocks'].numpy()[...] = rocks
+
+  def run(self):
+    """Score the staged batch: H2D per chunk -> max-plus, goal overlap, select
+    -> D2H of actions.  Returns (actions [E,R], best [E,2]) numpy views after a
+    full synchronise."""
+    main = torch.cuda.current_stream(self.dev)
+    self.copy_stream.wait_stream(main)
+    ready = []
+    with torch.cuda.stream(self.copy_stream):
+      for lo, hi in self.bounds:
+        for k in self.pin:
+          self.dev_in[k][lo:hi].copy_(self.pin[k][lo:hi], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(self.copy_stream)
+        ready.append(ev)
+    for (lo, hi), ev in zip(self.bounds, ready):
+      main.wait_event(ev)
+      out = self.scorer(self.dev_in['walls'][lo:hi], self.dev_in['goals'][lo:hi],
+                        self.dev_in['rocks'][lo:hi])
+      self.actions[lo:hi].copy_(out['actions'], non_blocking=True)
+      self.best[lo:hi].copy_(out['best'], non_blocking=True)
+    main.synchronize()
+    return self.actions.numpy(), self.best.numpy()
+
+  def __call__(self, walls, goals, rocks):
+    self.stage(walls, goals, rocks)
+    return self.run()
+
+
 class Baseline(object):
   """Greedy policy over a heuristic value map: the reference's
   ``stackrl.baselines.Baseline`` (baselines.py:167-217) with ``PyGreedy``'s
