@@ -58,8 +58,10 @@ void oracle_maxplus_f32(const float* wall, const float* rocks, float level,
  *    then each rounded to float32;
  *  - per triangle, in float32: signed area; clockwise/counter-clockwise both
  *    drawn (vertices 1,2 swapped when the area is negative);
- *  - a pixel (i, j) is sampled at its centre (j + 0.5, i + 0.5); it is covered
- *    when the three edge functions are >= 0 with a top-left style tie rule;
+ *  - a pixel (i, j) is sampled at its centre (j + 0.5, i + 0.5); candidates are
+ *    the pixels whose centre lies in the triangle's float32 bounding box
+ *    (ceil(min - 0.5) .. floor(max - 0.5)); a candidate is covered when the
+ *    three edge functions are >= 0 with a top-left style tie rule;
  *  - its depth is (w0*d0 + w1*d1 + w2*d2) / area, evaluated left to right with
  *    separate float32 multiplies and adds; fragments outside [0, 1] are clipped;
  *  - the image keeps the minimum depth per pixel; background 1.0. */
@@ -126,8 +128,9 @@ void oracle_raster_depth(const float* verts, const int32_t* tris,
       if (!(maxx >= 0.f) || !(maxy >= 0.f) || !(minx <= (float)cols) ||
           !(miny <= (float)rows))
         continue;
-      int jlo = (int)floorf(fmaxf(minx, 0.f)) - 1, jhi = (int)ceilf(fminf(maxx, (float)cols)) + 1;
-      int ilo = (int)floorf(fmaxf(miny, 0.f)) - 1, ihi = (int)ceilf(fminf(maxy, (float)rows)) + 1;
+      /* pixels whose centre (j + 0.5, i + 0.5) lies inside the bounding box */
+      int jlo = (int)ceilf(fmaxf(minx, 0.f) - 0.5f), jhi = (int)floorf(fminf(maxx, (float)cols) - 0.5f);
+      int ilo = (int)ceilf(fmaxf(miny, 0.f) - 0.5f), ihi = (int)floorf(fminf(maxy, (float)rows) - 0.5f);
       if (jlo < 0) jlo = 0;
       if (ilo < 0) ilo = 0;
       if (jhi > cols - 1) jhi = cols - 1;

@@ -29,21 +29,26 @@ goal_overlap_kernel(const In* __restrict__ walls, const In* __restrict__ goals,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarps = blockDim.x >> 5;
 
+  // Stage the two comparisons as bytes first: every global load of the block is
+  // independent and coalesced (several in flight per thread), the bit-packing
+  // below then only touches shared memory.
+  uint8_t* flag = reinterpret_cast<uint8_t*>(win + H * Pw);      // [H*W + R*h*h]
   const In* wall = walls + (size_t)e * H * W;
   const In* goal = goals + (size_t)e * H * W;
+  const In* rock = rocks + (size_t)e * R * h * h;
+#pragma unroll 4
+  for (int k = tid; k < H * W; k += blockDim.x) flag[k] = wall[k] < goal[k];
+  uint8_t* rflag = flag + H * W;
+#pragma unroll 4
+  for (int k = tid; k < R * h * h; k += blockDim.x) rflag[k] = rock[k] > In(0);
+  __syncthreads();
   for (int k = warp; k < H * nW; k += nwarps) {
-    const int row = k / nW, word = k % nW;
-    const int col = word * 32 + lane;
-    bool b = false;
-    if (col < W) b = wall[row * W + col] < goal[row * W + col];
-    const uint32_t bits = __ballot_sync(0xffffffffu, b);
+    const int row = k / nW, col = (k % nW) * 32 + lane;
+    const uint32_t bits = __ballot_sync(0xffffffffu, col < W && flag[row * W + col]);
     if (lane == 0) below[k] = bits;
   }
-  const In* rock = rocks + (size_t)e * R * h * h;
   for (int k = warp; k < R * h; k += nwarps) {
-    bool b = false;
-    if (lane < h) b = rock[k * h + lane] > In(0);
-    const uint32_t bits = __ballot_sync(0xffffffffu, b);
+    const uint32_t bits = __ballot_sync(0xffffffffu, lane < h && rflag[k * h + lane]);
     if (lane == 0) foot[k] = bits;
   }
   __syncthreads();
@@ -75,7 +80,8 @@ int launch(const In* walls, const In* goals, const In* rocks, int32_t* counts, i
   SRL_REQUIRE(h <= 32, SRL_E_UNSUPPORTED,
               "goal_overlap: rock side %d > 32 (bit-packed rows hold 32 pixels)", h);
   const int nW = (W + 31) / 32 + 1;
-  const size_t smem = 4 * ((size_t)H * nW + (size_t)R * h + (size_t)H * (W - h + 1));
+  const size_t smem = 4 * ((size_t)H * nW + (size_t)R * h + (size_t)H * (W - h + 1)) +
+                      (size_t)H * W + (size_t)R * h * h;
   SRL_REQUIRE(smem <= 220 * 1024, SRL_E_UNSUPPORTED,
               "goal_overlap: %dx%d wall with %d rotations exceeds shared memory", H, W, R);
   auto k = goal_overlap_kernel<In>;

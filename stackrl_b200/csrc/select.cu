@@ -48,60 +48,50 @@ __device__ __forceinline__ int warp_max(int x) {
   return x;
 }
 
+// One CTA per environment, one WARP per map: the R views of an environment are
+// dealt round-robin to the warps, every reduction inside a map is a shuffle
+// reduction (no block barrier), and the batch-wise pick over the views is one
+// small shared-memory reduction at the end.
 template <typename V>
 __global__ void __launch_bounds__(kSelThreads)
 select_kernel(const V* __restrict__ values, const int32_t* __restrict__ counts,
               int64_t* __restrict__ actions, double* __restrict__ shown,
               int64_t* __restrict__ best, int R, int Ph, int Pw, int minorder,
               double overlap_threshold) {
-  __shared__ double s_d[kSelThreads / 32];
-  __shared__ int s_i[kSelThreads / 32];
-  __shared__ Best s_b[2][kSelThreads / 32];
-  __shared__ double s_vmax, s_cut;
-  __shared__ Best s_pick;
-  __shared__ double s_best_v;
-  __shared__ int s_best_r;
-  __shared__ long long s_best_a;
+  constexpr int NW = kSelThreads / 32;
+  __shared__ double s_score[NW];
+  __shared__ int s_view[NW];
+  __shared__ int s_action[NW];
 
   const int e = blockIdx.x;
   const int P = Ph * Pw;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = kSelThreads / 32;
-  if (tid == 0) {
-    s_best_r = -1;
-    s_best_v = 0.;
-    s_best_a = 0;
-  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // Running batch-wise pick of this warp (views visited in increasing order, so
+  // a strict > keeps numpy.argmax's first-index rule).
+  double my_score = 0.;
+  int my_view = -1, my_action = 0;
 
-  for (int r = 0; r < R; ++r) {
+  for (int r = warp; r < R; r += NW) {
     const V* v = values + ((size_t)e * R + r) * P;
     const int32_t* c = counts ? counts + ((size_t)e * R + r) * P : nullptr;
     double* sh = shown ? shown + ((size_t)e * R + r) * P : nullptr;
 
     // ---- pass 1: overlap-count maximum -> mask cut (baselines.py:155-156) ---- //
+    double cut = 0.;
     if (c) {
       int cm = 0;
-      for (int k = tid; k < P; k += kSelThreads) cm = max(cm, c[k]);
-      cm = warp_max(cm);
-      if (lane == 0) s_i[warp] = cm;
-      __syncthreads();
-      if (tid == 0) {
-        int m = s_i[0];
-        for (int w = 1; w < NW; ++w) m = max(m, s_i[w]);
-        s_cut = overlap_threshold * (double)m;     // float64, like numpy
-      }
-      __syncthreads();
+      for (int k = lane; k < P; k += 32) cm = max(cm, __ldg(c + k));
+      cut = overlap_threshold * (double)warp_max(cm);      // float64, like numpy
     }
-    const double cut = c ? s_cut : 0.;
 
     // ---- pass 2: masked maximum, local minima, both arg-min candidates ------- //
     double vm = -CUDART_INF;
     Best bmin = {0., -1};      // over mask & local minimum
     Best bmask = {0., -1};     // over mask (or everything when goal=False)
-    for (int k = tid; k < P; k += kSelThreads) {
-      const bool in = c ? ((double)c[k] >= cut) : true;
+    for (int k = lane; k < P; k += 32) {
+      const bool in = c ? ((double)__ldg(c + k) >= cut) : true;
       if (!in) continue;
-      const double x = (double)v[k];
+      const double x = (double)__ldg(v + k);
       vm = fmax(vm, x);
       Best cand = {x, k};
       bmask = better(bmask, cand);
@@ -109,7 +99,7 @@ select_kernel(const V* __restrict__ values, const int32_t* __restrict__ counts,
         // minimum_filter(size=1+2m, mode='constant', cval=0) == values
         // (baselines.py:209): x <= every in-bounds neighbour, and x <= 0 if the
         // window leaves the map (quirk Q6).
-        const int i = k / Pw, j = k % Pw;
+        const int i = k / Pw, j = k - i * Pw;
         bool low = true;
         if (i < minorder || j < minorder || i + minorder >= Ph || j + minorder >= Pw)
           low = x <= 0.;
@@ -119,7 +109,7 @@ select_kernel(const V* __restrict__ values, const int32_t* __restrict__ counts,
           for (int dj = -minorder; dj <= minorder; ++dj) {
             const int jj = j + dj;
             if (jj < 0 || jj >= Pw) continue;
-            if ((double)v[ii * Pw + jj] < x) {
+            if ((double)__ldg(v + ii * Pw + jj) < x) {
               low = false;
               break;
             }
@@ -131,47 +121,44 @@ select_kernel(const V* __restrict__ values, const int32_t* __restrict__ counts,
     vm = warp_max(vm);
     bmin = warp_best(bmin);
     bmask = warp_best(bmask);
-    if (lane == 0) {
-      s_d[warp] = vm;
-      s_b[0][warp] = bmin;
-      s_b[1][warp] = bmask;
+    const Best pick = bmin.idx >= 0 ? bmin : bmask;
+    if (lane == 0) actions[(size_t)e * R + r] = pick.idx;
+    // PyGreedy batchwise: first argmax over views of shown[action] = -value.
+    if (my_view < 0 || -pick.v > my_score) {
+      my_score = -pick.v;
+      my_view = r;
+      my_action = pick.idx;
     }
-    __syncthreads();
-    if (tid == 0) {
-      double m = s_d[0];
-      Best a = s_b[0][0], b = s_b[1][0];
-      for (int w = 1; w < NW; ++w) {
-        m = fmax(m, s_d[w]);
-        a = better(a, s_b[0][w]);
-        b = better(b, s_b[1][w]);
-      }
-      s_vmax = m;
-      const Best pick = a.idx >= 0 ? a : b;
-      s_pick = pick;
-      actions[(size_t)e * R + r] = pick.idx;
-      // PyGreedy batchwise: first argmax over views of shown[action] = -value.
-      const double score = -pick.v;
-      if (s_best_r < 0 || score > s_best_v) {
-        s_best_r = r;
-        s_best_v = score;
-        s_best_a = pick.idx;
-      }
-    }
-    __syncthreads();
 
     // ---- pass 3: negated value map (baselines.py:213, :215, :217) ------------- //
     if (sh) {
-      const double fill = s_vmax + 0.001;
-      for (int k = tid; k < P; k += kSelThreads) {
-        const bool in = c ? ((double)c[k] >= cut) : true;
-        sh[k] = -(in ? (double)v[k] : fill);
+      const double fill = vm + 0.001;
+      for (int k = lane; k < P; k += 32) {
+        const bool in = c ? ((double)__ldg(c + k) >= cut) : true;
+        sh[k] = -(in ? (double)__ldg(v + k) : fill);
       }
     }
-    __syncthreads();
   }
-  if (tid == 0 && best) {
-    best[2 * (size_t)e] = s_best_r;
-    best[2 * (size_t)e + 1] = s_best_a;
+  if (!best) return;
+  if (lane == 0) {
+    s_score[warp] = my_score;
+    s_view[warp] = my_view;
+    s_action[warp] = my_action;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int bv = -1, ba = 0;
+    double bs = 0.;
+    for (int w = 0; w < NW; ++w) {
+      if (s_view[w] < 0) continue;
+      if (bv < 0 || s_score[w] > bs || (s_score[w] == bs && s_view[w] < bv)) {
+        bs = s_score[w];
+        bv = s_view[w];
+        ba = s_action[w];
+      }
+    }
+    best[2 * (size_t)e] = bv;
+    best[2 * (size_t)e + 1] = ba;
   }
 }
 
