@@ -308,11 +308,23 @@ def run_graft(args, rank, local_rank, world):
   stream = P_(torch.cuda.current_stream().cuda_stream)
   mp_events = []
 
+  fused = not args.separate
+
   def step(k, timed=False):
     s = sets[k % NSETS]
     if timed:
       a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       a.record()
+    if fused:
+      # ONE launch: score maps (written in full), goal mask, arg-min, batch-wise pick.
+      capi._check(lib.srl_score_f32(
+        P_(s['walls'].data_ptr()), P_(s['goals'].data_ptr()), P_(s['rocks'].data_ptr()),
+        P_(None), P_(s['values'].data_ptr()), P_(s['actions'].data_ptr()),
+        P_(s['best'].data_ptr()), E, R, H, W, h, 2, 1, 0.75, stream))
+      if timed:
+        b.record()
+        mp_events.append((a, b))
+      return
     capi._check(lib.srl_maxplus_f32(
       P_(s['walls'].data_ptr()), P_(s['rocks'].data_ptr()), P_(s['level'].data_ptr()),
       P_(s['values'].data_ptr()), E, R, H, W, h, 0.0, stream))
@@ -408,14 +420,14 @@ def run_graft(args, rank, local_rank, world):
   alg_bytes = 4 * (E * H * W + E * R * h * h + E * R * P)
   roofline = {
     'bound': 'fp32-alu',
-    'kernel': 'maxplus_staged_kernel<17,16,paired>',
+    'kernel': 'score_fused_kernel<17,16>' if fused else 'maxplus_staged_kernel<17,16,paired>',
     'kernel_ms': maxplus_ms,
     'share_of_step': maxplus_ms / ms_per_step,
     'achieved': 2 * cells / kernel_s / 1e12,
     'peak': 2 * peak_cells / 1e12,
     'unit': 'Tops/s',
     'frac': (cells / kernel_s) / peak_cells,
-    'traffic': ncu_traffic('maxplus_staged_kernel'),
+    'traffic': ncu_traffic('score_fused_kernel' if fused else 'maxplus_staged_kernel'),
     'peak_source': 'srl_microbench_addmax, best (add,max) issue rate measured in this run '
                    '(FADD+FMNMX {:.3g}, FADD2+FMNMX3 {:.3g}, FADD2+VIMNMX3 {:.3g} cells/s); '
                    'MEASURED_PEAKS.json has no non-tensor FP32 figure'.format(
@@ -442,8 +454,9 @@ def run_graft(args, rank, local_rank, world):
             'd2h_bytes_per_step': pipe.d2h_bytes, 'steps': e2e_steps,
             'api': 'stackrl_b200.baselines.HostPipeline(PlacementScorer): pinned host '
                    'observations -> actions'},
-    'gpu_launches': 3 * args.steps,
-    'kernels_per_step': ['maxplus_staged_kernel', 'goal_overlap_kernel', 'select_kernel'],
+    'gpu_launches': (1 if fused else 3) * args.steps,
+    'kernels_per_step': ['score_fused_kernel'] if fused else
+    ['maxplus_staged_kernel', 'goal_overlap_kernel', 'select_kernel'],
     'roofline': roofline,
   }
   if world == 1 and not args.no_extra:
@@ -471,6 +484,8 @@ def main():
   ap.add_argument('--impl', default='graft', choices=['graft', 'reference'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-extra', action='store_true')
+  ap.add_argument('--separate', action='store_true',
+                  help='run the three separate kernels instead of the fused one')
   args = ap.parse_args()
   rank = int(os.environ.get('RANK', '0'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))

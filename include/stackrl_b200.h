@@ -105,6 +105,25 @@ SRL_API int srl_select_f64(const double* values, const int32_t* counts, int64_t*
                    double* shown, int64_t* best, int E, int R, int Ph, int Pw,
                    int minorder, double overlap_threshold, srl_stream_t stream);
 
+/* ---- a5+a7+a9+a10 fused: Baseline('height', batched, batchwise).__call__ -----
+ * (baselines.py:201-217 over :21-43 and :152-156; agents/policies.py:57-91).
+ * One launch computes the max-plus score maps, the goal-overlap mask, the masked
+ * local-minimum arg-min per view and the batch-wise pick; overlap counts stay in
+ * shared memory.  Results are identical to srl_maxplus_f32 + srl_goal_overlap_f32
+ * + srl_select_f32.
+ *   level_mode 0: no normalisation; 1: level[e]; 2: max(goals[e]) computed
+ *   in-kernel (get_inputs, baselines.py:23; goal heights must be >= 0).
+ *   goals == NULL is goal=False (plain arg-min).  values [E,R,P] f32 may be NULL
+ *   (score maps not written); actions [E,R] i64; best [E,2] i64 or NULL.
+ * Returns SRL_E_UNSUPPORTED for shapes outside the fused kernel (rows not
+ * multiples of 16 B, more than 288 (view,row,strip) items per environment, or
+ * maps that do not fit shared memory): use the separate entry points then. */
+SRL_API int srl_score_f32(const float* walls, const float* goals, const float* rocks,
+                          const float* level, float* values, int64_t* actions,
+                          int64_t* best, int E, int R, int H, int W, int h,
+                          int level_mode, int minorder, double overlap_threshold,
+                          srl_stream_t stream);
+
 /* ---- a6: baselines.difference (baselines.py:45-77), exponents (2, 2|0) -------
  * f = sum_{u,v} w[u,v] * |h0 - (o+n)|^p  in numpy's order: float32 lift and
  * residual, float64 weights/product, pairwise summation over the contiguous

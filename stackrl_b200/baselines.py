@@ -162,9 +162,22 @@ class PlacementScorer(object):
   def values(self, walls, goals, rocks):
     return _height_device(walls, goals, rocks)
 
-  def __call__(self, walls, goals, rocks, want_shown=False):
+  def __call__(self, walls, goals, rocks, want_shown=False, fused=True):
     """-> dict(values [E,R,Ph,Pw], actions [E,R], best [E,2] = (view, flat index),
-    shown [E,R,Ph,Pw] float64 if requested)."""
+    shown [E,R,Ph,Pw] float64 if requested).  float32 batches whose shape the
+    fused kernel covers take ONE launch (srl_score_f32); everything else, and
+    requests for the float64 value map, run the three separate kernels."""
+    if fused and not want_shown and walls.dtype == torch.float32:
+      try:
+        values, actions, best = capi.score_f32(
+          walls, goals if self.goal else None, rocks, goals.amax(dim=(1, 2)) if not self.goal
+          else None, level_mode=2 if self.goal else 1, minorder=self.minorder or 0,
+          overlap_threshold=self.threshold)
+        return {'values': values, 'counts': None, 'actions': actions, 'best': best,
+                'shown': None}
+      except capi.SrlError as err:
+        if err.code != capi.SRL_E_UNSUPPORTED:
+          raise
     values = self.values(walls, goals, rocks)
     counts = capi.goal_overlap(walls, goals, rocks) if self.goal else None
     actions, shown, best = capi.select(

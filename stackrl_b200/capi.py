@@ -44,6 +44,7 @@ _SIGNATURES = {
   'srl_goal_overlap_u8': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
   'srl_select_f32': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_select_f64': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_double, _P]),
+  'srl_score_f32': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_difference_weights': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
   'srl_difference_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
   'srl_raster': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _P]),
@@ -289,6 +290,31 @@ def pack_obs(walls, goals, rocks, dtype='float32', scale=1., repeat_wall=False):
                             E, R, H, W, h, code, float(scale), int(bool(repeat_wall)),
                             _stream()))
   return wall_goal, rock
+
+
+SRL_E_UNSUPPORTED = -2
+
+
+def score_f32(walls, goals, rocks, level=None, level_mode=2, minorder=1,
+              overlap_threshold=0.75, want_values=True, want_best=True):
+  """Fused scoring (one launch): -> (values [E,R,Ph,Pw] f32 | None, actions [E,R],
+  best [E,2] | None).  Raises SrlError with code SRL_E_UNSUPPORTED for shapes the
+  fused kernel does not cover."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  dev = walls.device
+  args = (_dev(walls, torch.float32, 'walls'), _opt(goals, torch.float32, 'goals'),
+          _dev(rocks, torch.float32, 'rocks'), _opt(level, torch.float32, 'level'))
+  values = torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.float32, device=dev) \
+    if want_values else None
+  actions = torch.empty((E, R), dtype=torch.int64, device=dev)
+  best = torch.empty((E, 2), dtype=torch.int64, device=dev) if want_best else None
+  with torch.cuda.device(dev):
+    _check(lib.srl_score_f32(*args, _opt(values, torch.float32, 'values'),
+                             _dev(actions, torch.int64, 'actions'),
+                             _opt(best, torch.int64, 'best'), E, R, H, W, h,
+                             int(level_mode), int(minorder), float(overlap_threshold),
+                             _stream()))
+  return values, actions, best
 
 
 def microbench_addmax(variant, iters=2000):

@@ -139,6 +139,14 @@ int srl_pack_obs(const float* walls, const float* goals, const float* rocks,
                        scale, repeat_wall, (cudaStream_t)stream);
 }
 
+int srl_score_f32(const float* walls, const float* goals, const float* rocks,
+                  const float* level, float* values, int64_t* actions, int64_t* best, int E,
+                  int R, int H, int W, int h, int level_mode, int minorder,
+                  double overlap_threshold, srl_stream_t stream) {
+  return srl::score_f32(walls, goals, rocks, level, values, actions, best, E, R, H, W, h,
+                        level_mode, minorder, overlap_threshold, (cudaStream_t)stream);
+}
+
 int srl_microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   return srl::microbench_addmax(variant, iters, host_cells_per_s);
 }

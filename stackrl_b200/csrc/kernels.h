@@ -48,6 +48,11 @@ int pack_obs(const float* walls, const float* goals, const float* rocks, void* w
 int reward_sums_f32(const float* walls, const float* goals, const float* goal_z, float* inter,
                     float* uni, float* vol, int E, int H, int W, cudaStream_t stream);
 
+int score_f32(const float* walls, const float* goals, const float* rocks, const float* level,
+              float* values, int64_t* actions, int64_t* best, int E, int R, int H, int W,
+              int h, int level_mode, int minorder, double overlap_threshold,
+              cudaStream_t stream);
+
 int microbench_addmax(int variant, int iters, double* host_cells_per_s);
 
 }  // namespace srl

@@ -1,0 +1,203 @@
+// Shared pieces of the max-plus kernels (maxplus.cu) and the fused scoring kernel
+// (score.cu): fast index division, kernel parameters, the register-tiled
+// (add, max) sweep, and the rock normalise/mask helper.  See maxplus.cu for the
+// design notes.
+#pragma once
+
+#include "common.cuh"
+
+namespace srl {
+
+// q = n / d for n * d < 2^32 (all index spaces here are < 2^16 x 2^16).
+struct FastDiv {
+  uint32_t mul, d;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  f.mul = d == 1 ? 0u : (uint32_t)(((1ull << 32) + (uint32_t)d - 1) / (uint32_t)d);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv f) {
+  return f.d == 1 ? n : __umulhi(n, f.mul);
+}
+__device__ __forceinline__ void fdivmod(uint32_t n, const FastDiv f, uint32_t& q,
+                                        uint32_t& r) {
+  q = fdiv(n, f);
+  r = n - q * f.d;
+}
+
+struct MaxPlusParams {
+  const float* walls;
+  const float* rocks;
+  const float* level;
+  float* out;
+  int E, R, H, W, h;
+  int Ph, Pw;
+  int hp;           // rock columns padded to a multiple of VC
+  int Ws;           // smem wall row stride (floats), Ws % 4 == 0, (Ws/4) odd
+  int wall_stride;  // smem floats per wall  (H * Ws)
+  int rock_stride;  // smem floats per rock copy (h * hp + 4)
+  int G;            // environments per CTA (group)
+  int RC;           // rotations per CTA
+  int rchunks;      // ceil(R / RC)
+  int strips;       // strips per output row; strip k starts at column k*(T-1)
+  int ngroups;      // ceil(E / G)
+  float threshold;
+  int tma_wall;     // wall rows can be bulk-copied (W % 4 == 0, 16-B aligned base)
+  int tma_rock;     // rock rows can be bulk-copied (h % 4 == 0, 16-B aligned base)
+  int stage_out;    // staged kernel: score maps leave by bulk TMA store
+  FastDiv dPh, dStrips, dRC, dW, dH, dh, dhp, dW4, dh4;
+};
+
+// Block of T x VC (add, max) cells: acc[t] = max(acc[t], row[t+v] + nv[v]).
+// PAIRED: nvs[v] = nv[v+1] is the one-column-shifted rock row, loaded from its
+// own smem copy so that (nvs[v], nvs[v+1]) for even v is an aligned register
+// pair holding (nv[v+1], nv[v+2]).
+template <int T, int VC, bool PAIRED>
+__device__ __forceinline__ void cell_block(float (&acc)[T],
+                                           const float (&row)[4 * ((T + VC + 2) / 4)],
+                                           const float (&nv)[VC],
+                                           const float (&nvs)[VC]) {
+  if constexpr (!PAIRED) {
+#pragma unroll
+    for (int v = 0; v < VC; ++v) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) acc[t] = fmaxf(acc[t], row[t + v] + nv[v]);
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      if ((t & 1) == 0) {
+        // even output column: wall index k = t+v is even for even v.
+#pragma unroll
+        for (int v = 0; v < VC; v += 2) {
+          float s0, s1;
+          fadd2(s0, s1, row[t + v], row[t + v + 1], nv[v], nv[v + 1]);
+          acc[t] = fmax3(acc[t], s0, s1);
+        }
+      } else {
+        // odd output column: pair odd v with v+1 (k = t+v even), using the
+        // shifted rock row; v = 0 and v = VC-1 stay single.
+        float e0 = row[t] + nv[0];
+        float e1 = row[t + VC - 1] + nv[VC - 1];
+        acc[t] = fmax3(acc[t], e0, e1);
+#pragma unroll
+        for (int v = 1; v + 1 < VC; v += 2) {
+          float s0, s1;
+          fadd2(s0, s1, row[t + v], row[t + v + 1], nvs[v - 1], nvs[v]);
+          acc[t] = fmax3(acc[t], s0, s1);
+        }
+      }
+    }
+  }
+}
+
+// All (add, max) cells of one item: T outputs of one output row against one rock.
+template <int T, int VC, bool PAIRED>
+__device__ __forceinline__ void sweep_item(float (&acc)[T], const float* wbase,
+                                           const float* rbase, const float* sbase,
+                                           int h, int hp, int Ws) {
+  constexpr int NR4 = (T + VC + 2) / 4;   // float4 loads per wall row chunk
+  static_assert((T - 1) % 4 == 0 && 4 * NR4 >= T + VC - 1, "tile shape");
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t] = kNegInf;
+  for (int u = 0; u < h; ++u) {
+    for (int vc = 0; vc < hp; vc += VC) {
+      float row[4 * NR4];
+      float nv[VC];
+      float nvs[VC];
+#pragma unroll
+      for (int k = 0; k < NR4; ++k) {
+        const float4 x = lds128(wbase + u * Ws + vc + 4 * k);
+        row[4 * k + 0] = x.x;
+        row[4 * k + 1] = x.y;
+        row[4 * k + 2] = x.z;
+        row[4 * k + 3] = x.w;
+      }
+#pragma unroll
+      for (int k = 0; k < VC / 4; ++k) {
+        const float4 x = lds128(rbase + u * hp + vc + 4 * k);
+        nv[4 * k + 0] = x.x;
+        nv[4 * k + 1] = x.y;
+        nv[4 * k + 2] = x.z;
+        nv[4 * k + 3] = x.w;
+        if constexpr (PAIRED) {
+          const float4 y = lds128(sbase + u * hp + vc + 4 * k);
+          nvs[4 * k + 0] = y.x;
+          nvs[4 * k + 1] = y.y;
+          nvs[4 * k + 2] = y.z;
+          nvs[4 * k + 3] = y.w;
+        }
+      }
+      cell_block<T, VC, PAIRED>(acc, row, nv, nvs);
+    }
+  }
+}
+
+// IEEE x / level.  Zero numerators (rock background, empty wall) are common and
+// would take __fdiv_rn's slow path; +-0 / level = +-0 * level bit for bit (the
+// level is a finite, non-zero goal height).
+__device__ __forceinline__ float div_level(float x, float level) {
+  return x == 0.f ? __fmul_rn(x, level) : __fdiv_rn(x, level);
+}
+
+// Normalise + mask one rock value (baselines.py:24-25, :32).
+__device__ __forceinline__ float prep_rock(float n, bool scaled, float level,
+                                           float thr, bool& dead) {
+  if (scaled) n = div_level(n, level);
+  const bool live = n > thr;
+  dead = dead || !live;
+  return live ? n : kNegInf;
+}
+
+// ---- host-side tile selection ------------------------------------------------ //
+struct Choice {
+  int T, VC;
+};
+
+// Per-thread tile widths with an instantiation: T = 4m+1 outputs, strips pitched
+// S = 4m apart (16-B aligned starts).  The reference geometries have
+// Pw = 2^a - 2^b + 1 == 1 (mod 4), which these cover with no wasted column.
+static const int kTs[] = {5, 9, 13, 17, 21, 25};
+
+inline int strips_for(int Pw, int T) {
+  return Pw <= T ? 1 : (Pw - T + (T - 1) - 1) / (T - 1) + 1;
+}
+
+inline Choice choose_tile(int Pw, int h) {
+  Choice c;
+  c.VC = h >= 13 ? 16 : (h >= 5 ? 8 : 4);
+  int best = kTs[0];
+  double best_cost = 1e30;
+  for (int T : kTs) {
+    if (c.VC == 16 && T > 21) continue;   // register budget (112/thread)
+    const int strips = strips_for(Pw, T);
+    const double waste = (double)strips * T / Pw;
+    const double loads = ((T + c.VC + 2) / 4 + c.VC / 2) / (double)(T * c.VC);
+    const double cost = waste * (1.03 + loads);
+    if (cost < best_cost - 1e-12) {
+      best_cost = cost;
+      best = T;
+    }
+  }
+  c.T = best;
+  return c;
+}
+
+inline int pick_threads(int items, int cap) {
+  if (items <= cap) return round_up(items < 32 ? 32 : items, 32);
+  int best_t = cap;
+  double best_w = 1e9;
+  for (int t = 192; t <= cap; t += 32) {   // several passes: waste the fewest lanes
+    const int passes = (items + t - 1) / t;
+    const double w = (double)passes * t / items;
+    if (w < best_w - 1e-9) {
+      best_w = w;
+      best_t = t;
+    }
+  }
+  return best_t;
+}
+
+}  // namespace srl

@@ -150,3 +150,62 @@ def test_drop_height_matches_pose_formula():
   for e in range(E):
     r, i, j = picks[e]
     assert got[e] == S.drop_height(walls[e], rocks[e, r], (i, j))
+
+
+@pytest.mark.parametrize('shape', [(7, 8, 32, 32, 16), (5, 1, 64, 64, 16), (4, 4, 32, 48, 8),
+                                   (3, 2, 40, 40, 12), (9, 3, 24, 24, 4)])
+@pytest.mark.parametrize('goal,minorder', [(True, 1), (True, 0), (True, 2), (False, 1)])
+def test_fused_scoring_equals_separate_kernels(B, shape, goal, minorder):
+  """srl_score_f32 (one launch) == srl_maxplus_f32 + srl_goal_overlap_f32 +
+  srl_select_f32, and both equal the oracle's Baseline.call per view."""
+  from stackrl_b200 import capi
+  E, R, H, W, h = shape
+  walls, rocks, _ = synth.placement_batch(51, E, R, H, W, h)
+  goals = synth.goals(52, E, H, W)
+  goals *= np.linspace(0.6, 1.4, E, dtype='float32')[:, None, None]   # per-env goal level
+  dev = torch.device('cuda')
+  wd, gd, rd = (torch.from_numpy(x).to(dev) for x in (walls, goals, rocks))
+  scorer = B.PlacementScorer(goal=goal, minorder=minorder)
+  sep = scorer(wd, gd, rd, fused=False)
+  values, actions, best = capi.score_f32(
+    wd, gd if goal else None, rd, None if goal else gd.amax(dim=(1, 2)),
+    level_mode=2 if goal else 1, minorder=minorder)
+  assert torch.equal(values, sep['values'])
+  assert torch.equal(actions, sep['actions'])
+  assert torch.equal(best, sep['best'])
+  fused = scorer(wd, gd, rd)                      # the default path takes the fused kernel
+  assert fused['counts'] is None and torch.equal(fused['actions'], actions)
+  for e in (0, E - 1):
+    wg = np.stack([walls[e], goals[e]], -1)
+    for r in range(R):
+      a, _ = S.baseline_call((wg, rocks[e, r][..., None]), goal=goal, minorder=minorder)
+      assert int(actions[e, r]) == a
+  # score maps are optional
+  none_values, actions2, _ = capi.score_f32(wd, gd if goal else None, rd,
+                                            None if goal else gd.amax(dim=(1, 2)),
+                                            level_mode=2 if goal else 1, minorder=minorder,
+                                            want_values=False)
+  assert none_values is None and torch.equal(actions2, actions)
+
+
+def test_fused_scoring_full_config2():
+  """BASELINE config 2 at full size: fused == separate on every environment."""
+  from stackrl_b200 import baselines, capi
+  E, R, H, W, h = 4096, 8, 32, 32, 16
+  walls, rocks, _ = synth.placement_batch(0, E, R, H, W, h)
+  goals = synth.goals(7, E, H, W)
+  dev = torch.device('cuda')
+  wd, gd, rd = (torch.from_numpy(x).to(dev) for x in (walls, goals, rocks))
+  sep = baselines.PlacementScorer()(wd, gd, rd, fused=False)
+  values, actions, best = capi.score_f32(wd, gd, rd)
+  assert torch.equal(values, sep['values'])
+  assert torch.equal(actions, sep['actions']) and torch.equal(best, sep['best'])
+
+
+def test_fused_scoring_rejects_unsupported_shapes():
+  from stackrl_b200 import capi
+  dev = torch.device('cuda')
+  with pytest.raises(capi.SrlError) as err:                 # 17-wide rows: no 16-B rows
+    capi.score_f32(torch.zeros((1, 17, 17), device=dev), torch.zeros((1, 17, 17), device=dev),
+                   torch.zeros((1, 1, 5, 5), device=dev))
+  assert err.value.code == capi.SRL_E_UNSUPPORTED
