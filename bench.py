@@ -308,7 +308,8 @@ def run_graft(args, rank, local_rank, world):
   stream = P_(torch.cuda.current_stream().cuda_stream)
   mp_events = []
 
-  fused = not args.separate
+  fused = args.fused
+  masked = not args.separate and not fused
 
   def step(k, timed=False):
     s = sets[k % NSETS]
@@ -331,6 +332,12 @@ def run_graft(args, rank, local_rank, world):
     if timed:
       b.record()
       mp_events.append((a, b))
+    if masked:
+      capi._check(lib.srl_mask_select_f32(
+        P_(s['values'].data_ptr()), P_(s['walls'].data_ptr()), P_(s['goals'].data_ptr()),
+        P_(s['rocks'].data_ptr()), P_(s['actions'].data_ptr()), P_(None),
+        P_(s['best'].data_ptr()), E, R, H, W, h, 1, 0.75, stream))
+      return
     capi._check(lib.srl_goal_overlap_f32(
       P_(s['walls'].data_ptr()), P_(s['goals'].data_ptr()), P_(s['rocks'].data_ptr()),
       P_(s['counts'].data_ptr()), E, R, H, W, h, stream))
@@ -454,8 +461,9 @@ def run_graft(args, rank, local_rank, world):
             'd2h_bytes_per_step': pipe.d2h_bytes, 'steps': e2e_steps,
             'api': 'stackrl_b200.baselines.HostPipeline(PlacementScorer): pinned host '
                    'observations -> actions'},
-    'gpu_launches': (1 if fused else 3) * args.steps,
+    'gpu_launches': (1 if fused else 2 if masked else 3) * args.steps,
     'kernels_per_step': ['score_fused_kernel'] if fused else
+    ['maxplus_staged_kernel', 'mask_select_kernel'] if masked else
     ['maxplus_staged_kernel', 'goal_overlap_kernel', 'select_kernel'],
     'roofline': roofline,
   }
@@ -484,6 +492,8 @@ def main():
   ap.add_argument('--impl', default='graft', choices=['graft', 'reference'])
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-extra', action='store_true')
+  ap.add_argument('--fused', action='store_true',
+                  help='run the single fully fused kernel (srl_score_f32)')
   ap.add_argument('--separate', action='store_true',
                   help='run the three separate kernels instead of the fused one')
   args = ap.parse_args()

@@ -105,6 +105,25 @@ SRL_API int srl_select_f64(const double* values, const int32_t* counts, int64_t*
                    double* shown, int64_t* best, int E, int R, int Ph, int Pw,
                    int minorder, double overlap_threshold, srl_stream_t stream);
 
+/* ---- a7+a9+a10 in one launch: goal_overlap feeding Baseline.call ---------------
+ * Same results as srl_goal_overlap_* followed by srl_select_*, but the overlap
+ * counts are produced and consumed in shared memory (they never reach HBM).
+ * values come from srl_maxplus_f32 (f32), srl_maxplus_u8 / srl_difference_f32
+ * (f64); walls/goals/rocks are the RAW observation planes (baselines.py:153-154). */
+SRL_API int srl_mask_select_f32(const float* values, const float* walls, const float* goals,
+                                const float* rocks, int64_t* actions, double* shown,
+                                int64_t* best, int E, int R, int H, int W, int h,
+                                int minorder, double overlap_threshold, srl_stream_t stream);
+SRL_API int srl_mask_select_f64(const double* values, const float* walls, const float* goals,
+                                const float* rocks, int64_t* actions, double* shown,
+                                int64_t* best, int E, int R, int H, int W, int h,
+                                int minorder, double overlap_threshold, srl_stream_t stream);
+SRL_API int srl_mask_select_f64_u8(const double* values, const uint8_t* walls,
+                                   const uint8_t* goals, const uint8_t* rocks,
+                                   int64_t* actions, double* shown, int64_t* best, int E,
+                                   int R, int H, int W, int h, int minorder,
+                                   double overlap_threshold, srl_stream_t stream);
+
 /* ---- a5+a7+a9+a10 fused: Baseline('height', batched, batchwise).__call__ -----
  * (baselines.py:201-217 over :21-43 and :152-156; agents/policies.py:57-91).
  * One launch computes the max-plus score maps, the goal-overlap mask, the masked

@@ -162,16 +162,21 @@ class PlacementScorer(object):
   def values(self, walls, goals, rocks):
     return _height_device(walls, goals, rocks)
 
-  def __call__(self, walls, goals, rocks, want_shown=False, fused=True):
+  def __call__(self, walls, goals, rocks, want_shown=False, fused='mask'):
     """-> dict(values [E,R,Ph,Pw], actions [E,R], best [E,2] = (view, flat index),
-    shown [E,R,Ph,Pw] float64 if requested).  float32 batches whose shape the
-    fused kernel covers take ONE launch (srl_score_f32); everything else, and
-    requests for the float64 value map, run the three separate kernels."""
-    if fused and not want_shown and walls.dtype == torch.float32:
+    shown [E,R,Ph,Pw] float64 if requested, counts [E,R,Ph,Pw] when computed).
+
+    fused='mask' (default): score map kernel + ONE kernel for goal mask, arg-min
+    and batch-wise pick (overlap counts stay in shared memory);
+    fused='full': everything in one launch (srl_score_f32; float32 batches of
+    supported shapes, falls back otherwise); fused=False: the three separate
+    kernels (also returns the counts)."""
+    if fused == 'full' and not want_shown and walls.dtype == torch.float32:
       try:
         values, actions, best = capi.score_f32(
-          walls, goals if self.goal else None, rocks, goals.amax(dim=(1, 2)) if not self.goal
-          else None, level_mode=2 if self.goal else 1, minorder=self.minorder or 0,
+          walls, goals if self.goal else None, rocks,
+          None if self.goal else goals.amax(dim=(1, 2)),
+          level_mode=2 if self.goal else 1, minorder=self.minorder or 0,
           overlap_threshold=self.threshold)
         return {'values': values, 'counts': None, 'actions': actions, 'best': best,
                 'shown': None}
@@ -179,9 +184,21 @@ class PlacementScorer(object):
         if err.code != capi.SRL_E_UNSUPPORTED:
           raise
     values = self.values(walls, goals, rocks)
-    counts = capi.goal_overlap(walls, goals, rocks) if self.goal else None
+    counts = None
+    if self.goal and fused:
+      try:
+        actions, shown, best = capi.mask_select(
+          values, walls, goals, rocks, minorder=self.minorder or 0,
+          overlap_threshold=self.threshold, want_shown=want_shown)
+        return {'values': values, 'counts': None, 'actions': actions, 'best': best,
+                'shown': shown}
+      except capi.SrlError as err:
+        if err.code != capi.SRL_E_UNSUPPORTED:
+          raise
+    if self.goal:
+      counts = capi.goal_overlap(walls, goals, rocks)
     actions, shown, best = capi.select(
-      values, counts, minorder=self.minorder, overlap_threshold=self.threshold,
+      values, counts, minorder=self.minorder or 0, overlap_threshold=self.threshold,
       want_shown=want_shown, want_best=True)
     return {'values': values, 'counts': counts, 'actions': actions, 'best': best,
             'shown': shown}
@@ -301,8 +318,17 @@ class Baseline(object):
       maps = [np.asarray(self.model((np.stack([wall[k], goal[k]], -1), rock[k][..., None]),
                                     **self.kwargs), dtype='float64') for k in range(N)]
       values = _upload(np.stack(maps)[:, None])
-    counts = capi.goal_overlap(walls, goals, rocks) if self.goal else None
     threshold = self.kwargs.get('threshold', 0.75)
+    if self.goal:
+      try:
+        actions, shown, _ = capi.mask_select(values, walls, goals, rocks,
+                                             minorder=self.minorder or 0,
+                                             overlap_threshold=threshold, want_best=False)
+        return actions[:, 0].cpu().numpy(), shown[:, 0].cpu().numpy()
+      except capi.SrlError as err:
+        if err.code != capi.SRL_E_UNSUPPORTED:
+          raise
+    counts = capi.goal_overlap(walls, goals, rocks) if self.goal else None
     actions, shown, _ = capi.select(values, counts, minorder=self.minorder or 0,
                                     overlap_threshold=threshold, want_best=False)
     return actions[:, 0].cpu().numpy(), shown[:, 0].cpu().numpy()

@@ -44,6 +44,9 @@ _SIGNATURES = {
   'srl_goal_overlap_u8': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
   'srl_select_f32': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_select_f64': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_double, _P]),
+  'srl_mask_select_f32': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_double, _P]),
+  'srl_mask_select_f64': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_double, _P]),
+  'srl_mask_select_f64_u8': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_score_f32': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_difference_weights': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
   'srl_difference_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
@@ -293,6 +296,30 @@ def pack_obs(walls, goals, rocks, dtype='float32', scale=1., repeat_wall=False):
 
 
 SRL_E_UNSUPPORTED = -2
+
+
+def mask_select(values, walls, goals, rocks, minorder=1, overlap_threshold=0.75,
+                want_shown=True, want_best=True):
+  """goal_overlap + select in one launch (counts stay in shared memory).
+  values [E,R,Ph,Pw] f32/f64; walls/goals [E,H,W], rocks [E,R,h,h] f32 or u8 (raw)."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  key = (values.dtype, walls.dtype)
+  fn = {(torch.float32, torch.float32): lib.srl_mask_select_f32,
+        (torch.float64, torch.float32): lib.srl_mask_select_f64,
+        (torch.float64, torch.uint8): lib.srl_mask_select_f64_u8}.get(key)
+  if fn is None:
+    raise TypeError('mask_select: unsupported dtypes {}'.format(key))
+  dev = values.device
+  args = (_dev(values, values.dtype, 'values'), _dev(walls, walls.dtype, 'walls'),
+          _dev(goals, walls.dtype, 'goals'), _dev(rocks, walls.dtype, 'rocks'))
+  actions = torch.empty((E, R), dtype=torch.int64, device=dev)
+  shown = torch.empty(tuple(values.shape), dtype=torch.float64, device=dev) if want_shown else None
+  best = torch.empty((E, 2), dtype=torch.int64, device=dev) if want_best else None
+  with torch.cuda.device(dev):
+    _check(fn(*args, _dev(actions, torch.int64, 'actions'),
+              _opt(shown, torch.float64, 'shown'), _opt(best, torch.int64, 'best'),
+              E, R, H, W, h, int(minorder), float(overlap_threshold), _stream()))
+  return actions, shown, best
 
 
 def score_f32(walls, goals, rocks, level=None, level_mode=2, minorder=1,

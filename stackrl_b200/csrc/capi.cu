@@ -147,6 +147,30 @@ int srl_score_f32(const float* walls, const float* goals, const float* rocks,
                         level_mode, minorder, overlap_threshold, (cudaStream_t)stream);
 }
 
+int srl_mask_select_f32(const float* values, const float* walls, const float* goals,
+                        const float* rocks, int64_t* actions, double* shown, int64_t* best,
+                        int E, int R, int H, int W, int h, int minorder,
+                        double overlap_threshold, srl_stream_t stream) {
+  return srl::mask_select_f32(values, walls, goals, rocks, actions, shown, best, E, R, H, W, h,
+                              minorder, overlap_threshold, (cudaStream_t)stream);
+}
+
+int srl_mask_select_f64(const double* values, const float* walls, const float* goals,
+                        const float* rocks, int64_t* actions, double* shown, int64_t* best,
+                        int E, int R, int H, int W, int h, int minorder,
+                        double overlap_threshold, srl_stream_t stream) {
+  return srl::mask_select_f64(values, walls, goals, rocks, actions, shown, best, E, R, H, W, h,
+                              minorder, overlap_threshold, (cudaStream_t)stream);
+}
+
+int srl_mask_select_f64_u8(const double* values, const uint8_t* walls, const uint8_t* goals,
+                           const uint8_t* rocks, int64_t* actions, double* shown,
+                           int64_t* best, int E, int R, int H, int W, int h, int minorder,
+                           double overlap_threshold, srl_stream_t stream) {
+  return srl::mask_select_f64_u8(values, walls, goals, rocks, actions, shown, best, E, R, H, W,
+                                 h, minorder, overlap_threshold, (cudaStream_t)stream);
+}
+
 int srl_microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   return srl::microbench_addmax(variant, iters, host_cells_per_s);
 }

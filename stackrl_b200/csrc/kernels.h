@@ -25,6 +25,19 @@ int select_f64(const double* values, const int32_t* counts, int64_t* actions,
                double* shown, int64_t* best, int E, int R, int Ph, int Pw, int minorder,
                double overlap_threshold, cudaStream_t stream);
 
+int mask_select_f32(const float* values, const float* walls, const float* goals,
+                    const float* rocks, int64_t* actions, double* shown, int64_t* best,
+                    int E, int R, int H, int W, int h, int minorder, double overlap_threshold,
+                    cudaStream_t stream);
+int mask_select_f64(const double* values, const float* walls, const float* goals,
+                    const float* rocks, int64_t* actions, double* shown, int64_t* best,
+                    int E, int R, int H, int W, int h, int minorder, double overlap_threshold,
+                    cudaStream_t stream);
+int mask_select_f64_u8(const double* values, const uint8_t* walls, const uint8_t* goals,
+                       const uint8_t* rocks, int64_t* actions, double* shown, int64_t* best,
+                       int E, int R, int H, int W, int h, int minorder,
+                       double overlap_threshold, cudaStream_t stream);
+
 int drop_height_f32(const float* walls, const float* rocks, const int32_t* picks,
                     float* out, int E, int R, int H, int W, int h, float threshold,
                     cudaStream_t stream);

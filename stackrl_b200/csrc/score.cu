@@ -42,6 +42,7 @@ struct ScoreParams {
   int nW;                   // 32-bit words per bit-packed wall row (+1 zero word)
   int pf, hb, ng;           // rows packed per word, bits per packed row, groups
   FastDiv dPw, dNW;
+  int region_bytes;         // compute layout, reused by the epilogue (win + counts)
 };
 
 __device__ __forceinline__ void keep_min(float& bv, int& bi, float v, int i) {
@@ -79,9 +80,10 @@ score_fused_kernel(const ScoreParams sp) {
   float* raw_goal = reinterpret_cast<float*>(at);                 at += with_goal ? G * H * W * 4 : 0;
   float* raw_wall = reinterpret_cast<float*>(at);                 at += G * H * W * 4;
   float* raw_rock = reinterpret_cast<float*>(at);                 at += slots * h * h * 4;
-  float* wall_s = reinterpret_cast<float*>(at);                   at += G * p.wall_stride * 4;
-  float* rock_s = reinterpret_cast<float*>(at);                   at += slots * p.rock_stride * 4;
-  float* rock_sh = reinterpret_cast<float*>(at);                  at += slots * p.rock_stride * 4;
+  float* wall_s = reinterpret_cast<float*>(at);
+  float* rock_s = wall_s + G * p.wall_stride;
+  float* rock_sh = rock_s + slots * p.rock_stride;
+  at += sp.region_bytes;          // >= compute layout and >= the epilogue's win + counts
   float* out_s = reinterpret_cast<float*>(at);
   // The epilogue reuses the compute layout (dead after the sweep) for the
   // row-packed windows and the 16-bit counts.
@@ -443,21 +445,25 @@ int score_f32(const float* walls, const float* goals, const float* rocks, const 
   const size_t kBudget = 112 * 1024;
   const bool stage_out = values != nullptr && ((size_t)R * P) % 4 == 0 &&
                          ((uintptr_t)values) % 16 == 0;
+  auto region_for = [&](int G) {
+    const int slots = G * R;
+    const size_t alias = (size_t)G * H * p.Pw * 4 + (size_t)slots * P * 2;
+    const size_t layout = (size_t)G * p.wall_stride * 4 + 2 * (size_t)slots * p.rock_stride * 4;
+    return (size_t)round_up((int)(alias > layout ? alias : layout), 16);
+  };
   auto smem_for = [&](int G, int threads) {
     const int slots = G * R;
     size_t s = 16 + round_up(2 * slots * 4, 16) + round_up(G * 4, 16) +
                3 * (size_t)round_up(slots * 4, 16) + 2 * (size_t)round_up(2 * threads * 4, 16) +
                round_up(G * H * sp.nW * 4, 16) + round_up(slots * sp.ng * 4, 16);
     s += (goals ? (size_t)G * H * W * 4 : 0) + (size_t)G * H * W * 4 + (size_t)slots * h * h * 4;
-    s += (size_t)G * p.wall_stride * 4 + 2 * (size_t)slots * p.rock_stride * 4;
+    s += region_for(G);
     s += (size_t)slots * P * 4;
     return s;
   };
   auto fits = [&](int G) {
     const int slots = G * R;
-    const size_t alias = (size_t)G * H * p.Pw * 4 + (size_t)slots * P * 2;
-    const size_t layout = (size_t)G * p.wall_stride * 4 + 2 * (size_t)slots * p.rock_stride * 4;
-    return smem_for(G, kThreads) <= kBudget && alias <= layout &&
+    return smem_for(G, kThreads) <= kBudget &&
            G * R * p.strips * p.Ph <= kThreads && (size_t)G * H * W < 65536 &&
            (size_t)slots * h * p.hp < 65536 && (size_t)slots * P < 65536 * 4;
   };
@@ -470,6 +476,7 @@ int score_f32(const float* walls, const float* goals, const float* rocks, const 
     if (g >= 1 && fits(g)) G = g;
   }
   p.G = G; p.RC = R; p.rchunks = 1;
+  sp.region_bytes = (int)region_for(G);
   p.stage_out = stage_out;
   p.ngroups = (E + G - 1) / G;
   const int threads = round_up(G * R * p.strips * p.Ph, 32);

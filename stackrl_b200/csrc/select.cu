@@ -177,6 +177,201 @@ int launch_select(const V* values, const int32_t* counts, int64_t* actions,
   return check_launch("select_kernel");
 }
 
+// --------------------------------------------------------------------------- //
+// goal_overlap + select in one launch ("mask_select"): the overlap counts of
+// baselines.py:152-155 are produced and consumed in shared memory (bit-packed
+// `wall < goal` windows, several rows per 32-bit word when the rock is small,
+// AND+POPC), so they never travel through HBM.  One CTA per environment; the
+// bit images are built by the whole block, then every warp owns whole views.
+// --------------------------------------------------------------------------- //
+struct MaskSelectParams {
+  int R, H, W, h, Ph, Pw, minorder;
+  int nW, pf, hb, ng;          // words per bit row (+1 zero word); row packing
+  double overlap_threshold;
+  uint32_t mulPw;              // ceil(2^32 / Pw) for k / Pw (k * Pw < 2^32)
+};
+
+template <typename V, typename In>
+__global__ void __launch_bounds__(kSelThreads)
+mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
+                   const In* __restrict__ goals, const In* __restrict__ rocks,
+                   int64_t* __restrict__ actions, double* __restrict__ shown,
+                   int64_t* __restrict__ best, const MaskSelectParams q) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  constexpr int NW = kSelThreads / 32;
+  __shared__ double s_score[NW];
+  __shared__ int s_view[NW];
+  __shared__ int s_action[NW];
+  const int R = q.R, H = q.H, W = q.W, h = q.h, Ph = q.Ph, Pw = q.Pw, P = Ph * Pw;
+  uint32_t* below = reinterpret_cast<uint32_t*>(sel_smem);          // [H][nW]
+  uint32_t* foot = below + H * q.nW;                                // [R][ng] row-packed
+  uint32_t* win = foot + R * q.ng;                                  // [H][Pw] row-packed
+  uint16_t* cnt = reinterpret_cast<uint16_t*>(win + H * Pw);        // [NW][P]
+
+  const int e = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t hmask = h >= 32 ? 0xffffffffu : ((1u << h) - 1u);
+
+  // ---- bit images of the raw observation (baselines.py:153-154) -------------- //
+  const In* wall = walls + (size_t)e * H * W;
+  const In* goal = goals + (size_t)e * H * W;
+  const In* rock = rocks + (size_t)e * R * h * h;
+#pragma unroll 4
+  for (int k = warp; k < H * q.nW; k += NW) {
+    const int row = k / q.nW, col = (k % q.nW) * 32 + lane;
+    bool b = false;
+    if (col < W) b = wall[row * W + col] < goal[row * W + col];
+    const uint32_t bits = __ballot_sync(0xffffffffu, b);
+    if (lane == 0) below[k] = bits;
+  }
+  for (int k = warp; k < R * q.ng; k += NW) {
+    const int r = k / q.ng, grp = k % q.ng;
+    uint32_t packed = 0;
+    for (int s = 0; s < q.pf; ++s) {
+      const int u = grp * q.pf + s;
+      const bool b = u < h && lane < h && rock[(r * h + u) * h + lane] > In(0);
+      packed |= (__ballot_sync(0xffffffffu, b) & hmask) << (s * q.hb);
+    }
+    if (lane == 0) foot[k] = packed;
+  }
+  __syncthreads();
+  for (int k = tid; k < H * Pw; k += kSelThreads) {
+    const int row = __umulhi((uint32_t)k, q.mulPw), j = k - row * Pw;
+    uint32_t packed = 0;
+    for (int s = 0; s < q.pf && row + s < H; ++s) {
+      const uint32_t* b = below + (row + s) * q.nW + (j >> 5);
+      packed |= (__funnelshift_r(b[0], b[1], j & 31) & hmask) << (s * q.hb);
+    }
+    win[k] = packed;
+  }
+  __syncthreads();
+
+  // ---- per view: counts -> cut -> candidates (one warp, shuffle reductions) ----- //
+  uint16_t* mine = cnt + (size_t)warp * P;
+  double my_score = 0.;
+  int my_view = -1, my_action = 0;
+  for (int r = warp; r < R; r += NW) {
+    const V* v = values + ((size_t)e * R + r) * P;
+    double* sh = shown ? shown + ((size_t)e * R + r) * P : nullptr;
+    const uint32_t* fp = foot + r * q.ng;
+    int cm = 0;
+    for (int k = lane; k < P; k += 32) {
+      const int i = __umulhi((uint32_t)k, q.mulPw);
+      const uint32_t* wp = win + k;                       // (i*Pw + j) == k
+      int c = 0;
+      for (int g = 0; g < q.ng; ++g) c += __popc(wp[g * q.pf * Pw] & fp[g]);
+      (void)i;
+      mine[k] = (uint16_t)c;
+      cm = max(cm, c);
+    }
+    cm = warp_max(cm);
+    __syncwarp();
+    // count >= threshold*max  <=>  count >= ceil(threshold*max) for integer counts
+    const int cmin = (int)ceil(q.overlap_threshold * (double)cm);
+    double vm = -CUDART_INF;
+    Best bmin = {0., -1};
+    Best bmask = {0., -1};
+    const int m = q.minorder;
+    for (int k = lane; k < P; k += 32) {
+      if ((int)mine[k] < cmin) continue;
+      const V xv = __ldg(v + k);
+      const double x = (double)xv;
+      vm = fmax(vm, x);
+      Best cand = {x, k};
+      bmask = better(bmask, cand);
+      if (m > 0) {
+        const int i = __umulhi((uint32_t)k, q.mulPw), j = k - i * Pw;
+        bool low = true;
+        if (i < m || j < m || i + m >= Ph || j + m >= Pw) low = x <= 0.;
+        for (int di = -m; low && di <= m; ++di) {
+          const int ii = i + di;
+          if (ii < 0 || ii >= Ph) continue;
+          for (int dj = -m; dj <= m; ++dj) {
+            const int jj = j + dj;
+            if (jj < 0 || jj >= Pw) continue;
+            if (__ldg(v + ii * Pw + jj) < xv) {
+              low = false;
+              break;
+            }
+          }
+        }
+        if (low) bmin = better(bmin, cand);
+      }
+    }
+    vm = warp_max(vm);
+    bmin = warp_best(bmin);
+    bmask = warp_best(bmask);
+    const Best pick = bmin.idx >= 0 ? bmin : bmask;
+    if (lane == 0) actions[(size_t)e * R + r] = pick.idx;
+    if (my_view < 0 || -pick.v > my_score) {
+      my_score = -pick.v;
+      my_view = r;
+      my_action = pick.idx;
+    }
+    if (sh) {
+      const double fill = vm + 0.001;
+      for (int k = lane; k < P; k += 32)
+        sh[k] = -((int)mine[k] >= cmin ? (double)__ldg(v + k) : fill);
+    }
+    __syncwarp();
+  }
+  if (!best) return;
+  if (lane == 0) {
+    s_score[warp] = my_score;
+    s_view[warp] = my_view;
+    s_action[warp] = my_action;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int bv = -1, ba = 0;
+    double bs = 0.;
+    for (int w = 0; w < NW; ++w) {
+      if (s_view[w] < 0) continue;
+      if (bv < 0 || s_score[w] > bs || (s_score[w] == bs && s_view[w] < bv)) {
+        bs = s_score[w];
+        bv = s_view[w];
+        ba = s_action[w];
+      }
+    }
+    best[2 * (size_t)e] = bv;
+    best[2 * (size_t)e + 1] = ba;
+  }
+}
+
+template <typename V, typename In>
+int launch_mask_select(const V* values, const In* walls, const In* goals, const In* rocks,
+                       int64_t* actions, double* shown, int64_t* best, int E, int R, int H,
+                       int W, int h, int minorder, double overlap_threshold,
+                       cudaStream_t stream) {
+  SRL_REQUIRE(E >= 0 && R >= 1 && h >= 1 && H >= h && W >= h && minorder >= 0, SRL_E_INVALID,
+              "mask_select: bad shape E=%d R=%d H=%d W=%d h=%d minorder=%d", E, R, H, W, h,
+              minorder);
+  if (E == 0) return SRL_OK;
+  SRL_REQUIRE(values && walls && goals && rocks && actions, SRL_E_INVALID,
+              "mask_select: null pointer");
+  SRL_REQUIRE(h <= 32, SRL_E_UNSUPPORTED, "mask_select: rock side %d > 32", h);
+  MaskSelectParams q;
+  q.R = R; q.H = H; q.W = W; q.h = h; q.Ph = H - h + 1; q.Pw = W - h + 1;
+  q.minorder = minorder; q.overlap_threshold = overlap_threshold;
+  q.nW = (W + 31) / 32 + 1;
+  q.pf = h > 16 ? 1 : (h > 8 ? 2 : 4);
+  q.hb = 32 / q.pf;
+  q.ng = (h + q.pf - 1) / q.pf;
+  q.mulPw = q.Pw == 1 ? 0u : (uint32_t)(((1ull << 32) + q.Pw - 1) / q.Pw);
+  SRL_REQUIRE(q.Pw > 1, SRL_E_UNSUPPORTED, "mask_select: single-column maps");
+  const size_t P = (size_t)q.Ph * q.Pw;
+  SRL_REQUIRE((size_t)H * q.Pw * q.Pw < (1ull << 32) && P * q.Pw < (1ull << 32),
+              SRL_E_UNSUPPORTED, "mask_select: map too large");
+  const size_t smem = 4 * ((size_t)H * q.nW + (size_t)R * q.ng + (size_t)H * q.Pw) +
+                      2 * (size_t)(kSelThreads / 32) * P;
+  SRL_REQUIRE(smem <= 220 * 1024, SRL_E_UNSUPPORTED,
+              "mask_select: %dx%d wall exceeds shared memory", H, W);
+  auto k = mask_select_kernel<V, In>;
+  SRL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<E, kSelThreads, smem, stream>>>(values, walls, goals, rocks, actions, shown, best, q);
+  return check_launch("mask_select_kernel");
+}
+
 // One warp per environment: max over the live cells of (window + rock).
 __global__ void __launch_bounds__(128)
 drop_height_kernel(const float* __restrict__ walls, const float* __restrict__ rocks,
@@ -212,6 +407,31 @@ int select_f64(const double* values, const int32_t* counts, int64_t* actions,
                double overlap_threshold, cudaStream_t stream) {
   return launch_select<double>(values, counts, actions, shown, best, E, R, Ph, Pw,
                                minorder, overlap_threshold, stream);
+}
+
+int mask_select_f32(const float* values, const float* walls, const float* goals,
+                    const float* rocks, int64_t* actions, double* shown, int64_t* best,
+                    int E, int R, int H, int W, int h, int minorder, double overlap_threshold,
+                    cudaStream_t stream) {
+  return launch_mask_select<float, float>(values, walls, goals, rocks, actions, shown, best, E,
+                                          R, H, W, h, minorder, overlap_threshold, stream);
+}
+
+int mask_select_f64(const double* values, const float* walls, const float* goals,
+                    const float* rocks, int64_t* actions, double* shown, int64_t* best,
+                    int E, int R, int H, int W, int h, int minorder, double overlap_threshold,
+                    cudaStream_t stream) {
+  return launch_mask_select<double, float>(values, walls, goals, rocks, actions, shown, best,
+                                           E, R, H, W, h, minorder, overlap_threshold, stream);
+}
+
+int mask_select_f64_u8(const double* values, const uint8_t* walls, const uint8_t* goals,
+                       const uint8_t* rocks, int64_t* actions, double* shown, int64_t* best,
+                       int E, int R, int H, int W, int h, int minorder,
+                       double overlap_threshold, cudaStream_t stream) {
+  return launch_mask_select<double, uint8_t>(values, walls, goals, rocks, actions, shown, best,
+                                             E, R, H, W, h, minorder, overlap_threshold,
+                                             stream);
 }
 
 int drop_height_f32(const float* walls, const float* rocks, const int32_t* picks,

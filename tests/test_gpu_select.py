@@ -152,7 +152,7 @@ def test_drop_height_matches_pose_formula():
     assert got[e] == S.drop_height(walls[e], rocks[e, r], (i, j))
 
 
-@pytest.mark.parametrize('shape', [(7, 8, 32, 32, 16), (5, 1, 64, 64, 16), (4, 4, 32, 48, 8),
+@pytest.mark.parametrize('shape', [(7, 8, 32, 32, 16), (5, 1, 64, 64, 16), (4, 4, 32, 48, 8), (2, 3, 128, 128, 32),
                                    (3, 2, 40, 40, 12), (9, 3, 24, 24, 4)])
 @pytest.mark.parametrize('goal,minorder', [(True, 1), (True, 0), (True, 2), (False, 1)])
 def test_fused_scoring_equals_separate_kernels(B, shape, goal, minorder):
@@ -173,8 +173,12 @@ def test_fused_scoring_equals_separate_kernels(B, shape, goal, minorder):
   assert torch.equal(values, sep['values'])
   assert torch.equal(actions, sep['actions'])
   assert torch.equal(best, sep['best'])
-  fused = scorer(wd, gd, rd)                      # the default path takes the fused kernel
-  assert fused['counts'] is None and torch.equal(fused['actions'], actions)
+  full = scorer(wd, gd, rd, fused='full')
+  assert torch.equal(full['actions'], actions) and torch.equal(full['best'], best)
+  default = scorer(wd, gd, rd, want_shown=True)   # max-plus + mask_select (2 launches)
+  assert torch.equal(default['actions'], actions) and torch.equal(default['best'], best)
+  sep_shown = scorer(wd, gd, rd, want_shown=True, fused=False)['shown']
+  assert torch.equal(default['shown'], sep_shown)
   for e in (0, E - 1):
     wg = np.stack([walls[e], goals[e]], -1)
     for r in range(R):
