@@ -184,7 +184,29 @@ int launch_select(const V* values, const int32_t* counts, int64_t* actions,
 // AND+POPC), so they never travel through HBM.  One CTA per environment; the
 // bit images are built by the whole block, then every warp owns whole views.
 // --------------------------------------------------------------------------- //
+// Cooperative global -> shared copy with every load independent (several 16-B
+// loads in flight per thread); falls back to bytes when the source is unaligned.
+__device__ __forceinline__ void stage_bytes(void* dst, const void* src, size_t nbytes,
+                                            int tid, int nthreads) {
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    const int n4 = (int)(nbytes >> 4);
+#pragma unroll 4
+    for (int k = tid; k < n4; k += nthreads) d4[k] = __ldg(s4 + k);
+    const unsigned char* sb = reinterpret_cast<const unsigned char*>(src);
+    unsigned char* db = reinterpret_cast<unsigned char*>(dst);
+    for (size_t k = ((size_t)n4 << 4) + tid; k < nbytes; k += nthreads) db[k] = sb[k];
+  } else {
+    const unsigned char* sb = reinterpret_cast<const unsigned char*>(src);
+    unsigned char* db = reinterpret_cast<unsigned char*>(dst);
+#pragma unroll 4
+    for (size_t k = tid; k < nbytes; k += nthreads) db[k] = sb[k];
+  }
+}
+
 struct MaskSelectParams {
+  int staged;                  // inputs + score maps of one environment fit shared memory
   int R, H, W, h, Ph, Pw, minorder;
   int nW, pf, hb, ng;          // words per bit row (+1 zero word); row packing
   double overlap_threshold;
@@ -212,10 +234,33 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t hmask = h >= 32 ? 0xffffffffu : ((1u << h) - 1u);
 
-  // ---- bit images of the raw observation (baselines.py:153-154) -------------- //
   const In* wall = walls + (size_t)e * H * W;
   const In* goal = goals + (size_t)e * H * W;
   const In* rock = rocks + (size_t)e * R * h * h;
+  const V* vals = values + (size_t)e * R * P;
+  if (q.staged) {
+    // One latency round trip for everything this environment needs.
+    unsigned char* at = reinterpret_cast<unsigned char*>(cnt + (size_t)NW * P);
+    at += (16 - (reinterpret_cast<uintptr_t>(at) & 15)) & 15;
+    V* v_s = reinterpret_cast<V*>(at);
+    at += ((size_t)R * P * sizeof(V) + 15) & ~(size_t)15;
+    In* wall_s = reinterpret_cast<In*>(at);
+    at += ((size_t)H * W * sizeof(In) + 15) & ~(size_t)15;
+    In* goal_s = reinterpret_cast<In*>(at);
+    at += ((size_t)H * W * sizeof(In) + 15) & ~(size_t)15;
+    In* rock_s = reinterpret_cast<In*>(at);
+    stage_bytes(v_s, vals, (size_t)R * P * sizeof(V), tid, kSelThreads);
+    stage_bytes(wall_s, wall, (size_t)H * W * sizeof(In), tid, kSelThreads);
+    stage_bytes(goal_s, goal, (size_t)H * W * sizeof(In), tid, kSelThreads);
+    stage_bytes(rock_s, rock, (size_t)R * h * h * sizeof(In), tid, kSelThreads);
+    __syncthreads();
+    vals = v_s;
+    wall = wall_s;
+    goal = goal_s;
+    rock = rock_s;
+  }
+
+  // ---- bit images of the raw observation (baselines.py:153-154) -------------- //
 #pragma unroll 4
   for (int k = warp; k < H * q.nW; k += NW) {
     const int row = k / q.nW, col = (k % q.nW) * 32 + lane;
@@ -251,7 +296,7 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
   double my_score = 0.;
   int my_view = -1, my_action = 0;
   for (int r = warp; r < R; r += NW) {
-    const V* v = values + ((size_t)e * R + r) * P;
+    const V* v = vals + (size_t)r * P;
     double* sh = shown ? shown + ((size_t)e * R + r) * P : nullptr;
     const uint32_t* fp = foot + r * q.ng;
     int cm = 0;
@@ -274,7 +319,7 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
     const int m = q.minorder;
     for (int k = lane; k < P; k += 32) {
       if ((int)mine[k] < cmin) continue;
-      const V xv = __ldg(v + k);
+      const V xv = v[k];
       const double x = (double)xv;
       vm = fmax(vm, x);
       Best cand = {x, k};
@@ -289,7 +334,7 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
           for (int dj = -m; dj <= m; ++dj) {
             const int jj = j + dj;
             if (jj < 0 || jj >= Pw) continue;
-            if (__ldg(v + ii * Pw + jj) < xv) {
+            if (v[ii * Pw + jj] < xv) {
               low = false;
               break;
             }
@@ -311,7 +356,7 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
     if (sh) {
       const double fill = vm + 0.001;
       for (int k = lane; k < P; k += 32)
-        sh[k] = -((int)mine[k] >= cmin ? (double)__ldg(v + k) : fill);
+        sh[k] = -((int)mine[k] >= cmin ? (double)v[k] : fill);
     }
     __syncwarp();
   }
@@ -362,10 +407,16 @@ int launch_mask_select(const V* values, const In* walls, const In* goals, const 
   const size_t P = (size_t)q.Ph * q.Pw;
   SRL_REQUIRE((size_t)H * q.Pw * q.Pw < (1ull << 32) && P * q.Pw < (1ull << 32),
               SRL_E_UNSUPPORTED, "mask_select: map too large");
-  const size_t smem = 4 * ((size_t)H * q.nW + (size_t)R * q.ng + (size_t)H * q.Pw) +
-                      2 * (size_t)(kSelThreads / 32) * P;
+  size_t smem = 4 * ((size_t)H * q.nW + (size_t)R * q.ng + (size_t)H * q.Pw) +
+                2 * (size_t)(kSelThreads / 32) * P;
   SRL_REQUIRE(smem <= 220 * 1024, SRL_E_UNSUPPORTED,
               "mask_select: %dx%d wall exceeds shared memory", H, W);
+  auto pad16 = [](size_t n) { return (n + 15) & ~(size_t)15; };
+  const size_t staged = 16 + pad16((size_t)R * P * sizeof(V)) +
+                        2 * pad16((size_t)H * W * sizeof(In)) +
+                        pad16((size_t)R * h * h * sizeof(In));
+  q.staged = smem + staged <= 56 * 1024;        // keep >= 4 CTAs per SM
+  if (q.staged) smem += staged;
   auto k = mask_select_kernel<V, In>;
   SRL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<E, kSelThreads, smem, stream>>>(values, walls, goals, rocks, actions, shown, best, q);
