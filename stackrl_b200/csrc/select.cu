@@ -213,7 +213,71 @@ struct MaskSelectParams {
   uint32_t mulPw;              // ceil(2^32 / Pw) for k / Pw (k * Pw < 2^32)
 };
 
-template <typename V, typename In>
+// Arg-min candidate in the score type itself (float compares are exact; only
+// the returned value map is float64).
+template <typename V>
+struct Cand {
+  V v;
+  int idx;
+};
+template <typename V>
+__device__ __forceinline__ void take(Cand<V>& a, V v, int idx) {
+  if (a.idx < 0 || v < a.v || (v == a.v && idx < a.idx)) {
+    a.v = v;
+    a.idx = idx;
+  }
+}
+template <typename V>
+__device__ __forceinline__ Cand<V> warp_cand(Cand<V> x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const V v = __shfl_xor_sync(0xffffffffu, x.v, o);
+    const int i = __shfl_xor_sync(0xffffffffu, x.idx, o);
+    if (i >= 0) take(x, v, i);
+  }
+  return x;
+}
+template <typename V>
+__device__ __forceinline__ V warp_vmax(V x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const V y = __shfl_xor_sync(0xffffffffu, x, o);
+    x = y > x ? y : x;
+  }
+  return x;
+}
+
+// Is v[i,j] a minimum of its zero-padded (2M+1)^2 window (baselines.py:209)?
+template <typename V, int M>
+__device__ __forceinline__ bool local_min(const V* v, V x, int i, int j, int Ph, int Pw,
+                                          int m_runtime) {
+  const int m = M >= 0 ? M : m_runtime;
+  if (i >= m && j >= m && i + m < Ph && j + m < Pw) {
+    const V* c = v + i * Pw + j;
+    if (M == 1) {
+      return !(c[-Pw - 1] < x) && !(c[-Pw] < x) && !(c[-Pw + 1] < x) && !(c[-1] < x) &&
+             !(c[1] < x) && !(c[Pw - 1] < x) && !(c[Pw] < x) && !(c[Pw + 1] < x);
+    }
+    for (int di = -m; di <= m; ++di)
+      for (int dj = -m; dj <= m; ++dj)
+        if (c[di * Pw + dj] < x) return false;
+    return true;
+  }
+  // window leaves the map: the padding contributes 0 (quirk Q6)
+  if (!(x <= V(0))) return false;
+  for (int di = -m; di <= m; ++di) {
+    const int ii = i + di;
+    if (ii < 0 || ii >= Ph) continue;
+    for (int dj = -m; dj <= m; ++dj) {
+      const int jj = j + dj;
+      if (jj < 0 || jj >= Pw) continue;
+      if (v[ii * Pw + jj] < x) return false;
+    }
+  }
+  return true;
+}
+
+template <typename V, typename In, bool STAGED, int M>
 __global__ void __launch_bounds__(kSelThreads)
 mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
                    const In* __restrict__ goals, const In* __restrict__ rocks,
@@ -221,7 +285,7 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
                    int64_t* __restrict__ best, const MaskSelectParams q) {
   extern __shared__ __align__(16) unsigned char sel_smem[];
   constexpr int NW = kSelThreads / 32;
-  __shared__ double s_score[NW];
+  __shared__ V s_score[NW];
   __shared__ int s_view[NW];
   __shared__ int s_action[NW];
   const int R = q.R, H = q.H, W = q.W, h = q.h, Ph = q.Ph, Pw = q.Pw, P = Ph * Pw;
@@ -238,7 +302,7 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
   const In* goal = goals + (size_t)e * H * W;
   const In* rock = rocks + (size_t)e * R * h * h;
   const V* vals = values + (size_t)e * R * P;
-  if (q.staged) {
+  if constexpr (STAGED) {
     // One latency round trip for everything this environment needs.
     unsigned char* at = reinterpret_cast<unsigned char*>(cnt + (size_t)NW * P);
     at += (16 - (reinterpret_cast<uintptr_t>(at) & 15)) & 15;
@@ -261,23 +325,25 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
   }
 
   // ---- bit images of the raw observation (baselines.py:153-154) -------------- //
-#pragma unroll 4
-  for (int k = warp; k < H * q.nW; k += NW) {
-    const int row = k / q.nW, col = (k % q.nW) * 32 + lane;
-    bool b = false;
-    if (col < W) b = wall[row * W + col] < goal[row * W + col];
-    const uint32_t bits = __ballot_sync(0xffffffffu, b);
-    if (lane == 0) below[k] = bits;
-  }
-  for (int k = warp; k < R * q.ng; k += NW) {
-    const int r = k / q.ng, grp = k % q.ng;
-    uint32_t packed = 0;
-    for (int s = 0; s < q.pf; ++s) {
-      const int u = grp * q.pf + s;
-      const bool b = u < h && lane < h && rock[(r * h + u) * h + lane] > In(0);
-      packed |= (__ballot_sync(0xffffffffu, b) & hmask) << (s * q.hb);
+  for (int row = warp; row < H; row += NW) {
+    for (int word = 0; word < q.nW; ++word) {
+      const int col = word * 32 + lane;
+      bool b = false;
+      if (col < W) b = wall[row * W + col] < goal[row * W + col];
+      const uint32_t bits = __ballot_sync(0xffffffffu, b);
+      if (lane == 0) below[row * q.nW + word] = bits;
     }
-    if (lane == 0) foot[k] = packed;
+  }
+  for (int r = warp; r < R; r += NW) {
+    for (int grp = 0; grp < q.ng; ++grp) {
+      uint32_t packed = 0;
+      for (int s = 0; s < q.pf; ++s) {
+        const int u = grp * q.pf + s;
+        const bool b = u < h && lane < h && rock[(r * h + u) * h + lane] > In(0);
+        packed |= (__ballot_sync(0xffffffffu, b) & hmask) << (s * q.hb);
+      }
+      if (lane == 0) foot[r * q.ng + grp] = packed;
+    }
   }
   __syncthreads();
   for (int k = tid; k < H * Pw; k += kSelThreads) {
@@ -293,19 +359,18 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
 
   // ---- per view: counts -> cut -> candidates (one warp, shuffle reductions) ----- //
   uint16_t* mine = cnt + (size_t)warp * P;
-  double my_score = 0.;
+  const int gstride = q.pf * Pw;
+  V my_score = V(0);
   int my_view = -1, my_action = 0;
   for (int r = warp; r < R; r += NW) {
     const V* v = vals + (size_t)r * P;
-    double* sh = shown ? shown + ((size_t)e * R + r) * P : nullptr;
     const uint32_t* fp = foot + r * q.ng;
     int cm = 0;
     for (int k = lane; k < P; k += 32) {
-      const int i = __umulhi((uint32_t)k, q.mulPw);
       const uint32_t* wp = win + k;                       // (i*Pw + j) == k
       int c = 0;
-      for (int g = 0; g < q.ng; ++g) c += __popc(wp[g * q.pf * Pw] & fp[g]);
-      (void)i;
+#pragma unroll 4
+      for (int g = 0; g < q.ng; ++g) c += __popc(wp[g * gstride] & fp[g]);
       mine[k] = (uint16_t)c;
       cm = max(cm, c);
     }
@@ -313,48 +378,39 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
     __syncwarp();
     // count >= threshold*max  <=>  count >= ceil(threshold*max) for integer counts
     const int cmin = (int)ceil(q.overlap_threshold * (double)cm);
-    double vm = -CUDART_INF;
-    Best bmin = {0., -1};
-    Best bmask = {0., -1};
-    const int m = q.minorder;
+    bool any = false;
+    V vm = V(0);
+    Cand<V> bmin = {V(0), -1}, bmask = {V(0), -1};
     for (int k = lane; k < P; k += 32) {
       if ((int)mine[k] < cmin) continue;
-      const V xv = v[k];
-      const double x = (double)xv;
-      vm = fmax(vm, x);
-      Best cand = {x, k};
-      bmask = better(bmask, cand);
-      if (m > 0) {
+      const V x = v[k];
+      vm = (!any || x > vm) ? x : vm;
+      any = true;
+      take(bmask, x, k);
+      if (M != 0) {
         const int i = __umulhi((uint32_t)k, q.mulPw), j = k - i * Pw;
-        bool low = true;
-        if (i < m || j < m || i + m >= Ph || j + m >= Pw) low = x <= 0.;
-        for (int di = -m; low && di <= m; ++di) {
-          const int ii = i + di;
-          if (ii < 0 || ii >= Ph) continue;
-          for (int dj = -m; dj <= m; ++dj) {
-            const int jj = j + dj;
-            if (jj < 0 || jj >= Pw) continue;
-            if (v[ii * Pw + jj] < xv) {
-              low = false;
-              break;
-            }
-          }
-        }
-        if (low) bmin = better(bmin, cand);
+        if (local_min<V, M>(v, x, i, j, Ph, Pw, q.minorder)) take(bmin, x, k);
       }
     }
-    vm = warp_max(vm);
-    bmin = warp_best(bmin);
-    bmask = warp_best(bmask);
-    const Best pick = bmin.idx >= 0 ? bmin : bmask;
+    bmin = warp_cand(bmin);
+    bmask = warp_cand(bmask);
+    const Cand<V> pick = bmin.idx >= 0 ? bmin : bmask;
     if (lane == 0) actions[(size_t)e * R + r] = pick.idx;
-    if (my_view < 0 || -pick.v > my_score) {
-      my_score = -pick.v;
+    // PyGreedy batchwise: first argmax over views of -value (strict <: first wins)
+    if (my_view < 0 || pick.v < my_score) {
+      my_score = pick.v;
       my_view = r;
       my_action = pick.idx;
     }
-    if (sh) {
-      const double fill = vm + 0.001;
+    if (shown) {
+      // every lane holds at least... not necessarily a masked cell: reduce the max
+      // over the lanes that saw one (the mask is never empty)
+      const unsigned who = __ballot_sync(0xffffffffu, any);
+      V m2 = __shfl_sync(0xffffffffu, vm, __ffs(who) - 1);
+      m2 = any ? vm : m2;
+      m2 = warp_vmax(m2);
+      const double fill = (double)m2 + 0.001;
+      double* sh = shown + ((size_t)e * R + r) * P;
       for (int k = lane; k < P; k += 32)
         sh[k] = -((int)mine[k] >= cmin ? (double)v[k] : fill);
     }
@@ -369,10 +425,10 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
   __syncthreads();
   if (threadIdx.x == 0) {
     int bv = -1, ba = 0;
-    double bs = 0.;
+    V bs = V(0);
     for (int w = 0; w < NW; ++w) {
       if (s_view[w] < 0) continue;
-      if (bv < 0 || s_score[w] > bs || (s_score[w] == bs && s_view[w] < bv)) {
+      if (bv < 0 || s_score[w] < bs || (s_score[w] == bs && s_view[w] < bv)) {
         bs = s_score[w];
         bv = s_view[w];
         ba = s_action[w];
@@ -417,9 +473,24 @@ int launch_mask_select(const V* values, const In* walls, const In* goals, const 
                         pad16((size_t)R * h * h * sizeof(In));
   q.staged = smem + staged <= 56 * 1024;        // keep >= 4 CTAs per SM
   if (q.staged) smem += staged;
-  auto k = mask_select_kernel<V, In>;
-  SRL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<E, kSelThreads, smem, stream>>>(values, walls, goals, rocks, actions, shown, best, q);
+#define SRL_MS_LAUNCH(ST, MM)                                                              \
+  do {                                                                                     \
+    auto k = mask_select_kernel<V, In, ST, MM>;                                            \
+    SRL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                  (int)smem));                                             \
+    k<<<E, kSelThreads, smem, stream>>>(values, walls, goals, rocks, actions, shown, best, \
+                                        q);                                                \
+  } while (0)
+  if (q.staged) {
+    if (minorder == 0) SRL_MS_LAUNCH(true, 0);
+    else if (minorder == 1) SRL_MS_LAUNCH(true, 1);
+    else SRL_MS_LAUNCH(true, -1);
+  } else {
+    if (minorder == 0) SRL_MS_LAUNCH(false, 0);
+    else if (minorder == 1) SRL_MS_LAUNCH(false, 1);
+    else SRL_MS_LAUNCH(false, -1);
+  }
+#undef SRL_MS_LAUNCH
   return check_launch("mask_select_kernel");
 }
 
