@@ -44,7 +44,7 @@ namespace srl {
 // --------------------------------------------------------------------------- //
 // Staged persistent kernel (small walls).
 // --------------------------------------------------------------------------- //
-template <int T, int VC, bool PAIRED>
+template <int T, int VC, int PAIRED>
 __global__ void __launch_bounds__(288, 2)
 maxplus_staged_kernel(const MaxPlusParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -129,7 +129,7 @@ maxplus_staged_kernel(const MaxPlusParams p) {
       if (dead) flags[slot] = 1;
       float* dst = rock_s + slot * p.rock_stride + u * hp + 4 * c4;
       *reinterpret_cast<float4*>(dst) = x;
-      if constexpr (PAIRED) {
+      if constexpr (PAIRED != 0) {
         float* sh = rock_sh + slot * p.rock_stride + u * hp + 4 * c4;
         if (c4 != 0) sh[-1] = x.x;
         sh[0] = x.y;
@@ -192,7 +192,7 @@ maxplus_staged_kernel(const MaxPlusParams p) {
 // --------------------------------------------------------------------------- //
 // Direct kernel (big walls): one CTA per (environment group, rotation chunk).
 // --------------------------------------------------------------------------- //
-template <int T, int VC, bool PAIRED>
+template <int T, int VC, int PAIRED>
 __global__ void __launch_bounds__(288, 2)
 maxplus_direct_kernel(const MaxPlusParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -300,7 +300,7 @@ maxplus_direct_kernel(const MaxPlusParams p) {
       if (dead) masked[slot] = 1;
     }
     *q = n;
-    if constexpr (PAIRED) {
+    if constexpr (PAIRED != 0) {
       float* sh = rock_sh + slot * p.rock_stride + u * hp + c;
       if (c != 0) sh[-1] = n;
       if ((int)c == hp - 1) sh[0] = kNegInf;
@@ -341,7 +341,7 @@ namespace {
 
 template <int T, int VC>
 int launch(const MaxPlusParams& p, bool staged, int blocks, int threads, size_t smem,
-           bool paired, cudaStream_t stream) {
+           int paired, cudaStream_t stream) {
 #define SRL_LAUNCH(...)                                                              \
   do {                                                                               \
     auto k = __VA_ARGS__;                                                            \
@@ -350,11 +350,13 @@ int launch(const MaxPlusParams& p, bool staged, int blocks, int threads, size_t 
     k<<<blocks, threads, smem, stream>>>(p);                                         \
   } while (0)
   if (staged) {
-    if (paired) SRL_LAUNCH(maxplus_staged_kernel<T, VC, true>);
-    else SRL_LAUNCH(maxplus_staged_kernel<T, VC, false>);
+    if (paired == 0) SRL_LAUNCH(maxplus_staged_kernel<T, VC, 0>);
+    else if (paired == 1) SRL_LAUNCH(maxplus_staged_kernel<T, VC, 1>);
+    else if (paired == 3) SRL_LAUNCH(maxplus_staged_kernel<T, VC, 3>);
+    else SRL_LAUNCH(maxplus_staged_kernel<T, VC, 5>);
   } else {
-    if (paired) SRL_LAUNCH(maxplus_direct_kernel<T, VC, true>);
-    else SRL_LAUNCH(maxplus_direct_kernel<T, VC, false>);
+    if (paired == 0) SRL_LAUNCH(maxplus_direct_kernel<T, VC, 0>);
+    else SRL_LAUNCH(maxplus_direct_kernel<T, VC, 1>);
   }
 #undef SRL_LAUNCH
   return check_launch("maxplus_f32 kernel");
@@ -381,7 +383,7 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
 
   const Choice c = choose_tile(p.Pw, h);
   const int T = c.T, VC = c.VC;
-  const bool paired = variant != 0;
+  const int paired = variant;     // 0 plain, 1 paired, 3/5 paired + grouped issue order
   p.hp = round_up(h, VC);
   p.strips = strips_for(p.Pw, T);
   // Columns a thread may touch: strip start + (hp - VC) + 4*NR4 floats.

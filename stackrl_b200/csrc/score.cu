@@ -236,7 +236,7 @@ score_fused_kernel(const ScoreParams sp) {
       fdivmod(rest, p.dStrips, slot, strip);
       const uint32_t el = fdiv(slot, p.dRC);
       float acc[T];
-      sweep_item<T, VC, true>(acc, wall_s + el * p.wall_stride + i * Ws + strip * S,
+      sweep_item<T, VC, 1>(acc, wall_s + el * p.wall_stride + i * Ws + strip * S,
                               rock_s + slot * p.rock_stride, rock_sh + slot * p.rock_stride,
                               h, hp, Ws);
       const bool floor0 = flags[slot] != 0;

@@ -288,6 +288,11 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
   __shared__ V s_score[NW];
   __shared__ int s_view[NW];
   __shared__ int s_action[NW];
+  __shared__ int s_cm[NW];
+  __shared__ Cand<V> s_bmin[NW], s_bmask[NW];
+  __shared__ V s_vm[NW];
+  __shared__ bool s_any[NW];
+  __shared__ double s_fill[NW];
   const int R = q.R, H = q.H, W = q.W, h = q.h, Ph = q.Ph, Pw = q.Pw, P = Ph * Pw;
   uint32_t* below = reinterpret_cast<uint32_t*>(sel_smem);          // [H][nW]
   uint32_t* foot = below + H * q.nW;                                // [R][ng] row-packed
@@ -357,76 +362,117 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
   }
   __syncthreads();
 
-  // ---- per view: counts -> cut -> candidates (one warp, shuffle reductions) ----- //
-  uint16_t* mine = cnt + (size_t)warp * P;
+  // ---- per view: counts -> cut -> candidates ------------------------------------- //
+  // `wpv` warps cooperate on one view (all 8 when there is a single view, one
+  // each when there are >= 8), so small-R batches still use the whole block.
+  int wpv = 1;
+  while (wpv * 2 * R <= NW) wpv *= 2;
+  const int vpr = NW / wpv;                 // views per round
+  const int sub = warp % wpv, slot = warp / wpv;
   const int gstride = q.pf * Pw;
-  V my_score = V(0);
+  uint16_t* mine = cnt + (size_t)slot * P;
+  V my_score = V(0);                        // batch-wise pick, kept by the slot leader
   int my_view = -1, my_action = 0;
-  for (int r = warp; r < R; r += NW) {
-    const V* v = vals + (size_t)r * P;
-    const uint32_t* fp = foot + r * q.ng;
-    int cm = 0;
-    for (int k = lane; k < P; k += 32) {
-      const uint32_t* wp = win + k;                       // (i*Pw + j) == k
-      int c = 0;
+  for (int r0 = 0; r0 < R; r0 += vpr) {
+    const int r = r0 + slot;
+    const bool active = r < R;
+    const V* v = vals + (size_t)(active ? r : 0) * P;
+    if (active) {
+      const uint32_t* fp = foot + r * q.ng;
+      int cm = 0;
+      for (int k = sub * 32 + lane; k < P; k += 32 * wpv) {
+        const uint32_t* wp = win + k;                       // (i*Pw + j) == k
+        int c = 0;
 #pragma unroll 4
-      for (int g = 0; g < q.ng; ++g) c += __popc(wp[g * gstride] & fp[g]);
-      mine[k] = (uint16_t)c;
-      cm = max(cm, c);
+        for (int g = 0; g < q.ng; ++g) c += __popc(wp[g * gstride] & fp[g]);
+        mine[k] = (uint16_t)c;
+        cm = max(cm, c);
+      }
+      cm = warp_max(cm);
+      if (lane == 0) s_cm[warp] = cm;
     }
-    cm = warp_max(cm);
-    __syncwarp();
-    // count >= threshold*max  <=>  count >= ceil(threshold*max) for integer counts
-    const int cmin = (int)ceil(q.overlap_threshold * (double)cm);
-    bool any = false;
-    V vm = V(0);
+    __syncthreads();
+    int cmin = 0;
     Cand<V> bmin = {V(0), -1}, bmask = {V(0), -1};
-    for (int k = lane; k < P; k += 32) {
-      if ((int)mine[k] < cmin) continue;
-      const V x = v[k];
-      vm = (!any || x > vm) ? x : vm;
-      any = true;
-      take(bmask, x, k);
-      if (M != 0) {
-        const int i = __umulhi((uint32_t)k, q.mulPw), j = k - i * Pw;
-        if (local_min<V, M>(v, x, i, j, Ph, Pw, q.minorder)) take(bmin, x, k);
+    V vm = V(0);
+    bool any = false;
+    if (active) {
+      int cm = 0;
+      for (int w = 0; w < wpv; ++w) cm = max(cm, s_cm[slot * wpv + w]);
+      // count >= threshold*max  <=>  count >= ceil(threshold*max) for integer counts
+      cmin = (int)ceil(q.overlap_threshold * (double)cm);
+      for (int k = sub * 32 + lane; k < P; k += 32 * wpv) {
+        if ((int)mine[k] < cmin) continue;
+        const V x = v[k];
+        vm = (!any || x > vm) ? x : vm;
+        any = true;
+        take(bmask, x, k);
+        if (M != 0) {
+          const int i = __umulhi((uint32_t)k, q.mulPw), j = k - i * Pw;
+          if (local_min<V, M>(v, x, i, j, Ph, Pw, q.minorder)) take(bmin, x, k);
+        }
+      }
+      bmin = warp_cand(bmin);
+      bmask = warp_cand(bmask);
+      // masked maximum over the lanes that saw a masked cell
+      const unsigned who = __ballot_sync(0xffffffffu, any);
+      if (who) {
+        const V seed = __shfl_sync(0xffffffffu, vm, __ffs(who) - 1);
+        vm = warp_vmax(any ? vm : seed);
+      }
+      if (lane == 0) {
+        s_bmin[warp] = bmin;
+        s_bmask[warp] = bmask;
+        s_vm[warp] = vm;
+        s_any[warp] = who != 0;
       }
     }
-    bmin = warp_cand(bmin);
-    bmask = warp_cand(bmask);
-    const Cand<V> pick = bmin.idx >= 0 ? bmin : bmask;
-    if (lane == 0) actions[(size_t)e * R + r] = pick.idx;
-    // PyGreedy batchwise: first argmax over views of -value (strict <: first wins)
-    if (my_view < 0 || pick.v < my_score) {
-      my_score = pick.v;
-      my_view = r;
-      my_action = pick.idx;
+    __syncthreads();
+    if (active && sub == 0 && lane == 0) {
+      Cand<V> a = {V(0), -1}, b = {V(0), -1};
+      V m2 = V(0);
+      bool have = false;
+      for (int w = 0; w < wpv; ++w) {
+        const int ww = slot * wpv + w;
+        if (s_bmin[ww].idx >= 0) take(a, s_bmin[ww].v, s_bmin[ww].idx);
+        if (s_bmask[ww].idx >= 0) take(b, s_bmask[ww].v, s_bmask[ww].idx);
+        if (s_any[ww]) {
+          m2 = (!have || s_vm[ww] > m2) ? s_vm[ww] : m2;
+          have = true;
+        }
+      }
+      const Cand<V> pick = a.idx >= 0 ? a : b;
+      actions[(size_t)e * R + r] = pick.idx;
+      // PyGreedy batchwise: first argmax over views of -value (strict <: first wins)
+      if (my_view < 0 || pick.v < my_score) {
+        my_score = pick.v;
+        my_view = r;
+        my_action = pick.idx;
+      }
+      s_fill[slot] = (double)m2 + 0.001;
     }
     if (shown) {
-      // every lane holds at least... not necessarily a masked cell: reduce the max
-      // over the lanes that saw one (the mask is never empty)
-      const unsigned who = __ballot_sync(0xffffffffu, any);
-      V m2 = __shfl_sync(0xffffffffu, vm, __ffs(who) - 1);
-      m2 = any ? vm : m2;
-      m2 = warp_vmax(m2);
-      const double fill = (double)m2 + 0.001;
-      double* sh = shown + ((size_t)e * R + r) * P;
-      for (int k = lane; k < P; k += 32)
-        sh[k] = -((int)mine[k] >= cmin ? (double)v[k] : fill);
+      __syncthreads();
+      if (active) {
+        const double fill = s_fill[slot];
+        double* sh = shown + ((size_t)e * R + r) * P;
+        for (int k = sub * 32 + lane; k < P; k += 32 * wpv)
+          sh[k] = -((int)mine[k] >= cmin ? (double)v[k] : fill);
+      }
     }
-    __syncwarp();
+    __syncthreads();
   }
   if (!best) return;
-  if (lane == 0) {
-    s_score[warp] = my_score;
-    s_view[warp] = my_view;
-    s_action[warp] = my_action;
+  if (sub == 0 && lane == 0) {
+    s_score[slot] = my_score;
+    s_view[slot] = my_view;
+    s_action[slot] = my_action;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     int bv = -1, ba = 0;
     V bs = V(0);
-    for (int w = 0; w < NW; ++w) {
+    for (int w = 0; w < vpr; ++w) {
       if (s_view[w] < 0) continue;
       if (bv < 0 || s_score[w] < bs || (s_score[w] == bs && s_view[w] < bv)) {
         bs = s_score[w];
