@@ -50,8 +50,9 @@ void oracle_maxplus_f32(const float* wall, const float* rocks, float level,
 
 /* ---- software z-buffer (stand-in for pybullet.getCameraImage) -------------- */
 /* Geometry contract shared with stackrl_b200/csrc/raster.cu (DESIGN.md "raster"):
- *  - per vertex, in float64, fixed left-to-right op order:
- *      world = rot * v + pos;  eye = view * world;  clip = proj * eye
+ *  - per instance, in float64: M = proj * (view * [rot pos; 0 1]), each entry
+ *    summed left to right; per vertex, in float64, left to right:
+ *      clip = M * (x, y, z, 1)
  *      sx = (clip.x / clip.w * 0.5 + 0.5) * cols        (column coordinate)
  *      sy = (0.5 - clip.y / clip.w * 0.5) * rows        (row coordinate)
  *      d  = clip.z / clip.w * 0.5 + 0.5                 (GL depth in [0,1])
@@ -87,23 +88,38 @@ void oracle_raster_depth(const float* verts, const int32_t* tris,
   for (int q = 0; q < job->inst_count; ++q) {
     const oracle_instance* in = insts + job->inst_begin + q;
     float* s = (float*)malloc(sizeof(float) * 3 * (in->vert_count > 0 ? in->vert_count : 1));
+    /* M = proj * (view * [rot pos; 0 1]) in float64, every entry summed left to
+     * right over k = 0..3 (matrices: view/proj column-major, rot row-major). */
+    double Tm[4][4], VT[4][4], M[4][4];
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) Tm[r][c] = in->rot[3 * r + c];
+      Tm[r][3] = in->pos[r];
+    }
+    Tm[3][0] = Tm[3][1] = Tm[3][2] = 0.0;
+    Tm[3][3] = 1.0;
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) {
+        double a = job->view[0 * 4 + r] * Tm[0][c];
+        a = a + job->view[1 * 4 + r] * Tm[1][c];
+        a = a + job->view[2 * 4 + r] * Tm[2][c];
+        a = a + job->view[3 * 4 + r] * Tm[3][c];
+        VT[r][c] = a;
+      }
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) {
+        double a = job->proj[0 * 4 + r] * VT[0][c];
+        a = a + job->proj[1 * 4 + r] * VT[1][c];
+        a = a + job->proj[2 * 4 + r] * VT[2][c];
+        a = a + job->proj[3 * 4 + r] * VT[3][c];
+        M[r][c] = a;
+      }
     for (int k = 0; k < in->vert_count; ++k) {
       const float* v = verts + 3 * (size_t)(in->vert_begin + k);
       const double x = v[0], y = v[1], z = v[2];
-      const double* R = in->rot;
-      const double wx = R[0] * x + R[1] * y + R[2] * z + in->pos[0];
-      const double wy = R[3] * x + R[4] * y + R[5] * z + in->pos[1];
-      const double wz = R[6] * x + R[7] * y + R[8] * z + in->pos[2];
-      const double* V = job->view;
-      const double ex = V[0] * wx + V[4] * wy + V[8] * wz + V[12];
-      const double ey = V[1] * wx + V[5] * wy + V[9] * wz + V[13];
-      const double ez = V[2] * wx + V[6] * wy + V[10] * wz + V[14];
-      const double ew = V[3] * wx + V[7] * wy + V[11] * wz + V[15];
-      const double* P = job->proj;
-      const double cx = P[0] * ex + P[4] * ey + P[8] * ez + P[12] * ew;
-      const double cy = P[1] * ex + P[5] * ey + P[9] * ez + P[13] * ew;
-      const double cz = P[2] * ex + P[6] * ey + P[10] * ez + P[14] * ew;
-      const double cw = P[3] * ex + P[7] * ey + P[11] * ez + P[15] * ew;
+      const double cx = M[0][0] * x + M[0][1] * y + M[0][2] * z + M[0][3];
+      const double cy = M[1][0] * x + M[1][1] * y + M[1][2] * z + M[1][3];
+      const double cz = M[2][0] * x + M[2][1] * y + M[2][2] * z + M[2][3];
+      const double cw = M[3][0] * x + M[3][1] * y + M[3][2] * z + M[3][3];
       s[3 * k + 0] = (float)((cx / cw * 0.5 + 0.5) * cols);
       s[3 * k + 1] = (float)((0.5 - cy / cw * 0.5) * rows);
       s[3 * k + 2] = (float)(cz / cw * 0.5 + 0.5);
