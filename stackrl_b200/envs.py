@@ -79,11 +79,18 @@ class BatchedStackEnv(object):
     self._goal_z_d = torch.full((self.E,), self._goal_z, dtype=torch.float32, device=self.dev)
     self.goal_lims = np.zeros((self.E, 2, 2), dtype='int64')
     self._memory = np.zeros(self.E, dtype='float64')
-    self._placed = [[] for _ in range(self.E)]      # (position, place position) per rock
+    # Per-environment episode state as arrays (no Python loop over E per step):
+    # rest pose / placement pose of every placed rock, rock order and cursor.
+    self._rest = np.zeros((self.E, self._length, 3), dtype='float64')
+    self._placed_at = np.zeros((self.E, self._length, 3), dtype='float64')
+    self._quats = np.zeros((self.E, self._length, 4), dtype='float64')
+    self._placed_quats = np.zeros((self.E, self._length, 4), dtype='float64')
+    self._n_placed = np.zeros(self.E, dtype='int64')
     self._Ph, self._Pw = H - g.object_h + 1, W - g.object_w + 1
     self.seed(seed)
     self._done = np.ones(self.E, dtype=bool)
-    self._queues = [[] for _ in range(self.E)]
+    self._order = np.zeros((self.E, self._length), dtype='int64')
+    self._cursor = np.zeros(self.E, dtype='int64')     # rocks consumed so far
     self._current = np.zeros(self.E, dtype='int64')
 
   # -- ParallelEnv-style metadata (utils.py:185-300) --------------------------------- #
@@ -170,14 +177,15 @@ class BatchedStackEnv(object):
         order = list(rock_orders[k])
       else:
         order = list(rng.choice(len(self.bank), size=self._length, replace=self._replace))
-      self._queues[e] = order            # popped from the end, like env.py:245
-      self._current[e] = self._queues[e].pop()
+      self._order[e] = order[::-1]       # the reference pops from the end (env.py:245)
+      self._cursor[e] = 1
+      self._current[e] = self._order[e, 0]
       if goal_lims is not None:
         lims.append(goal_lims[k])
       else:
         u, v, h, w = self._new_goal(rng)
         lims.append(((u, v), (u + h, v + w)))
-      self._placed[e] = []
+      self._n_placed[e] = 0
       self._memory[e] = 0.
       self._done[e] = False
     self.set_goals(lims, ids)
@@ -213,16 +221,21 @@ class BatchedStackEnv(object):
     else:
       views, flat = np.zeros(self.E, dtype='int64'), action
     positions, quats = self.obs.poses(views, flat)
-    place_positions = positions.copy()
+    place_positions, place_quats = positions.copy(), quats.copy()
     if self._settle is not None:
       positions, quats = self._settle(self._current.copy(), positions, quats)
     self.obs.place(self._current, positions, quats)
-    for e in range(self.E):
-      self._placed[e].append((positions[e], place_positions[e], quats[e]))
-      if self._queues[e]:
-        self._current[e] = self._queues[e].pop()
-      else:
-        self._done[e] = True
+    rows = np.arange(self.E)
+    self._rest[rows, self._n_placed] = positions
+    self._placed_at[rows, self._n_placed] = place_positions
+    self._quats[rows, self._n_placed] = quats
+    self._placed_quats[rows, self._n_placed] = place_quats
+    self._n_placed += 1
+    more = self._cursor < self._length
+    self._current = np.where(more, self._order[rows, np.minimum(self._cursor, self._length - 1)],
+                             self._current)
+    self._cursor += more
+    self._done = ~more
     self.obs.observe_walls()
     self.obs.observe_rocks(self._current)
     reward = self._reward()
@@ -234,33 +247,34 @@ class BatchedStackEnv(object):
     """(intersection, union, goal volume) per environment, device tensors."""
     return capi.reward_sums(self.obs.walls, self.goals, self._goal_z_d)
 
-  def _discount(self, perr, oerr):
-    r = 1.
-    if self._pexp is not None:
-      r *= max(0., 1 - (perr / self._pmax) ** self._pexp)
-    if self._oexp is not None:
-      r *= max(0., 1 - (oerr / np.pi) ** self._oexp)
-    return r
-
   def _reward(self):
     if self.metric in ('iou', 'or'):
       inter, uni, vol = self.reward_terms()
       value = inter / uni if self.metric == 'iou' else inter / vol
       value = value.double().cpu().numpy()
     else:
+      # DOR / DIoU (rewarder.py:261-295): per placed rock, inside-goal test on its
+      # rest position and the distance discount from where it was placed.
       g = self.obs.geo
-      value = np.zeros(self.E)
-      for e in range(self.E):
-        total, n_out = 0., 0
-        (u0, v0), (u1, v1) = self.goal_lims[e]
-        for pos, placed, _ in self._placed[e]:
-          u, v = pos[0] // g.pixel_h, pos[1] // g.pixel_w
-          if u0 <= u < u1 and v0 <= v < v1:
-            total += self._discount(np.linalg.norm(np.subtract(placed, pos)), 0.)
-          else:
-            n_out += 1
-        value[e] = total / self._length if self.metric == 'dor' else \
-          total / (self._length + n_out)
+      live = np.arange(self._length)[None, :] < self._n_placed[:, None]
+      u = self._rest[..., 0] // g.pixel_h
+      v = self._rest[..., 1] // g.pixel_w
+      lims = self.goal_lims
+      inside = live & (u >= lims[:, 0, 0, None]) & (v >= lims[:, 0, 1, None]) & \
+        (u < lims[:, 1, 0, None]) & (v < lims[:, 1, 1, None])
+      perr = np.linalg.norm(self._placed_at - self._rest, axis=-1)
+      disc = np.ones_like(perr)
+      if self._pexp is not None:
+        disc = disc * np.maximum(0., 1 - (perr / self._pmax) ** self._pexp)
+      if self._oexp is not None:
+        # rotation distance 2*acos(min(w, 1)) of the difference quaternion
+        # (simulator.py:116-117); w = <q_placed, q_rest> for unit quaternions
+        w = np.minimum((self._placed_quats * self._quats).sum(axis=-1), 1.)
+        oerr = 2 * np.arccos(np.where(live, w, 1.))
+        disc = disc * np.maximum(0., 1 - (oerr / np.pi) ** self._oexp)
+      total = np.where(inside, disc, 0.).sum(axis=1)
+      n_out = (live & ~inside).sum(axis=1)
+      value = total / self._length if self.metric == 'dor' else total / (self._length + n_out)
     out = (value - self._memory) * self.scale
     self._memory = value
     return torch.from_numpy(out.astype('float32')).to(self.dev)

@@ -362,10 +362,10 @@ class BatchedObserver(object):
       torch.as_tensor(env_ids, device=self.dev, dtype=torch.long)
     rows = self._upload_rows(self._rows(mesh_ids, positions, quaternions))
     slot = env_ids * self.cap + self.counts[env_ids].long()
-    if bool((self.counts[env_ids] >= self.cap).any()):
-      raise RuntimeError('instance table full: more placed rocks than capacity')
-    self._inst_rows.index_copy_(0, slot, rows)
-    self.counts[env_ids] += 1
+    # (the caller bounds the number of placed rocks by `capacity`; a full table
+    # would otherwise need a device->host sync here on every step)
+    self._inst_rows.index_copy_(0, torch.clamp(slot, max=self.E * self.cap - 1), rows)
+    self.counts[env_ids] = torch.clamp(self.counts[env_ids] + 1, max=self.cap)
 
   # -- capture -------------------------------------------------------------------- #
   def observe_walls(self):

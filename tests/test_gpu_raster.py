@@ -176,10 +176,9 @@ def test_batched_env_replays_reference_episode(mods, observe_golden, name, dtype
     else:
       assert int(action[0]) == int(g[key + '/action'])
     obs, reward, terminal = env.step(action)
-    placed = env._placed[0][-1]
-    assert np.array_equal(placed[0], g[key + '/pose_position'])
+    assert np.array_equal(env._rest[0, k], g[key + '/pose_position'])
     if freedom:
-      assert np.allclose(placed[2], g[key + '/pose_orientation'], atol=1e-15)
+      assert np.allclose(env._quats[0, k], g[key + '/pose_orientation'], atol=1e-15)
     np.testing.assert_allclose(reward.cpu().numpy(), g[key + '/rewards'][0], rtol=1e-6,
                                atol=1e-9)
     assert bool(terminal[0]) == (k == steps - 1)
@@ -252,3 +251,44 @@ def test_pack_and_reward_kernels(mods):
     np.testing.assert_allclose(inter[e].item(), O.intersection(walls[e], goals[e], 0.25), rtol=1e-6)
     np.testing.assert_allclose(uni[e].item(), O.union(walls[e], goals[e]), rtol=1e-6)
     np.testing.assert_allclose(vol[e].item(), goals[e].sum(), rtol=1e-6)
+
+
+def test_batched_env_random_rollout_and_settle_hook(mods, observe_golden):
+  """Random-goal, random-order rollout with a settle hook that nudges every rock:
+  episode bookkeeping (terminal flags, rock cursor, DOR reward against a plain
+  Python evaluation of rewarder.py:261-295) stays consistent."""
+  g = observe_golden
+  envs = mods['envs']
+  bank = _fixture_bank(mods, g)
+  E, steps = 6, 5
+  shift = np.array([0.004, -0.002, 0.])
+
+  def settle(mesh_ids, positions, quats):
+    return positions + shift, quats
+
+  env = envs.BatchedStackEnv(bank, E, episode_length=steps, rewarder='dor', reward_params=2,
+                             reward_scale=None, settle=settle, seed=3)
+  policy = envs.HeightPolicy()
+  obs, r, t = env.reset()
+  assert obs[0].shape == (E, 128, 128, 2) and obs[1].shape == (E, 32, 32, 1)
+  assert not bool(t.any()) and env.batch_size == E
+  total = np.zeros(E)
+  for k in range(steps):
+    obs, r, t = env.step(policy(env))
+    total += r.cpu().numpy()
+    assert bool(t.all()) == (k == steps - 1)
+  geo = env.obs.geo
+  pmax = max(geo.object_h * geo.pixel_h, geo.object_w * geo.pixel_w)
+  for e in range(E):
+    (u0, v0), (u1, v1) = env.goal_lims[e]
+    acc = 0.
+    for k in range(steps):
+      p = env._rest[e, k]
+      u, v = p[0] // geo.pixel_h, p[1] // geo.pixel_w
+      if u0 <= u < u1 and v0 <= v < v1:
+        acc += max(0., 1 - (np.linalg.norm(shift) / pmax) ** 2) * 1.
+    np.testing.assert_allclose(total[e], acc / steps * steps, rtol=1e-6, atol=1e-7)
+  with pytest.raises(RuntimeError):
+    env.step(policy(env))                      # finished environments must be reset
+  a = env.sample()
+  assert a.shape == (E,) and int(a.max()) < 97 * 97
