@@ -320,6 +320,11 @@ class BatchedObserver(object):
     jobs['zrange'] = g.object_z
     self._rock_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(self.dev)
     self._rock_inst = torch.zeros(E * isz, dtype=torch.uint8, device=self.dev)
+    # Instance row of every mesh of the bank at the spawn pose: observing a new
+    # rock is then a device-side gather by mesh id, no per-step host work.
+    n = len(bank)
+    spawn_rows = self._rows(np.arange(n), [self.spawn_pose[0]] * n, [self.spawn_pose[1]] * n)
+    self._spawn_rows = self._upload_rows(spawn_rows)
     self.walls = torch.zeros((E, g.overhead_h, g.overhead_w), dtype=torch.float32,
                              device=self.dev)
     self.rocks = torch.zeros((E, R, g.object_h, g.object_w), dtype=torch.float32,
@@ -382,9 +387,9 @@ class BatchedObserver(object):
     spawned at ``spawn_pose``) at every orientation into ``rocks``
     (observer.py:262-293)."""
     g = self.geo
-    n = len(mesh_ids)
-    rows = self._rows(mesh_ids, [self.spawn_pose[0]] * n, [self.spawn_pose[1]] * n)
-    self._rock_inst.view(torch.float64).view(self.E, -1).copy_(self._upload_rows(rows))
+    ids = torch.as_tensor(np.asarray(mesh_ids, dtype='int64')).to(self.dev, non_blocking=True)
+    torch.index_select(self._spawn_rows, 0, ids,
+                       out=self._rock_inst.view(torch.float64).view(self.E, -1))
     capi.raster(self._verts, self._tris, self._rock_inst, self._rock_jobs, g.object_h,
                 g.object_w, capi.RASTER_ROCK, far_plane=FAR,
                 out=self.rocks.view(self.E * self.R, g.object_h, g.object_w))
