@@ -485,6 +485,188 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
   }
 }
 
+// Same computation with lanes mapped to (view, position) pairs: R (a power of
+// two <= 32) consecutive lanes share one window word and each keeps the packed
+// footprint of ITS view in registers, so an overlap step is LDS + LOP3 + POPC +
+// IADD with no footprint traffic, and all eight warps work on all views at once.
+template <typename V, typename In, int M, int NG>
+__global__ void __launch_bounds__(kSelThreads)
+mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ walls,
+                          const In* __restrict__ goals, const In* __restrict__ rocks,
+                          int64_t* __restrict__ actions, double* __restrict__ shown,
+                          int64_t* __restrict__ best, const MaskSelectParams q) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  constexpr int NW = kSelThreads / 32;
+  __shared__ int s_cmax[32];
+  __shared__ Cand<V> s_bmin[NW][32], s_bmask[NW][32];
+  __shared__ V s_vm[NW][32];
+  __shared__ bool s_any[NW][32];
+  __shared__ V s_pick[32];
+  __shared__ int s_pick_i[32];
+  __shared__ double s_fill[32];
+  const int R = q.R, H = q.H, W = q.W, h = q.h, Ph = q.Ph, Pw = q.Pw, P = Ph * Pw;
+  uint32_t* below = reinterpret_cast<uint32_t*>(sel_smem);          // [H][nW]
+  uint32_t* foot = below + H * q.nW;                                // [R][ng] row-packed
+  uint32_t* win = foot + R * q.ng;                                  // [H][Pw] row-packed
+  uint16_t* cnt = reinterpret_cast<uint16_t*>(win + H * Pw);        // [R][P]
+  unsigned char* at = reinterpret_cast<unsigned char*>(cnt + (size_t)R * P);
+  at += (16 - (reinterpret_cast<uintptr_t>(at) & 15)) & 15;
+  V* vals = reinterpret_cast<V*>(at);
+  at += ((size_t)R * P * sizeof(V) + 15) & ~(size_t)15;
+  In* wall = reinterpret_cast<In*>(at);
+  at += ((size_t)H * W * sizeof(In) + 15) & ~(size_t)15;
+  In* goal = reinterpret_cast<In*>(at);
+  at += ((size_t)H * W * sizeof(In) + 15) & ~(size_t)15;
+  In* rock = reinterpret_cast<In*>(at);
+
+  const int e = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t hmask = h >= 32 ? 0xffffffffu : ((1u << h) - 1u);
+  stage_bytes(vals, values + (size_t)e * R * P, (size_t)R * P * sizeof(V), tid, kSelThreads);
+  stage_bytes(wall, walls + (size_t)e * H * W, (size_t)H * W * sizeof(In), tid, kSelThreads);
+  stage_bytes(goal, goals + (size_t)e * H * W, (size_t)H * W * sizeof(In), tid, kSelThreads);
+  stage_bytes(rock, rocks + (size_t)e * R * h * h, (size_t)R * h * h * sizeof(In), tid,
+              kSelThreads);
+  if (tid < 32) s_cmax[tid] = 0;
+  __syncthreads();
+
+  // ---- bit images of the raw observation (baselines.py:153-154) ---------------- //
+  for (int row = warp; row < H; row += NW) {
+    for (int word = 0; word < q.nW; ++word) {
+      const int col = word * 32 + lane;
+      bool b = false;
+      if (col < W) b = wall[row * W + col] < goal[row * W + col];
+      const uint32_t bits = __ballot_sync(0xffffffffu, b);
+      if (lane == 0) below[row * q.nW + word] = bits;
+    }
+  }
+  for (int r = warp; r < R; r += NW) {
+    const In* rk = rock + (size_t)r * h * h;
+    uint32_t packed = 0;
+    for (int u = 0; u < h; ++u) {
+      const uint32_t bits = __ballot_sync(0xffffffffu, lane < h && rk[u * h + lane] > In(0));
+      const int sft = (u % q.pf) * q.hb;
+      packed |= (bits & hmask) << sft;
+      if (u % q.pf == q.pf - 1 || u == h - 1) {
+        if (lane == 0) foot[r * q.ng + u / q.pf] = packed;
+        packed = 0;
+      }
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < H * Pw; k += kSelThreads) {
+    const int row = __umulhi((uint32_t)k, q.mulPw), j = k - row * Pw;
+    uint32_t packed = 0;
+    for (int s = 0; s < q.pf && row + s < H; ++s) {
+      const uint32_t* b = below + (row + s) * q.nW + (j >> 5);
+      packed |= (__funnelshift_r(b[0], b[1], j & 31) & hmask) << (s * q.hb);
+    }
+    win[k] = packed;
+  }
+  __syncthreads();
+
+  // ---- lanes = (view r, position slot): counts ------------------------------------ //
+  const int r = lane & (R - 1);
+  const int ppw = 32 / R;                       // positions per warp iteration
+  const int qpos = lane / R;
+  const int step = NW * ppw;
+  const int gstride = q.pf * Pw;
+  uint32_t f[NG > 0 ? NG : 1];
+  if (NG > 0) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) f[g] = foot[r * NG + g];
+  }
+  uint16_t* mine = cnt + (size_t)r * P;
+  const V* v = vals + (size_t)r * P;
+  int cm = 0;
+  for (int pos = warp * ppw + qpos; pos < P; pos += step) {
+    const uint32_t* wp = win + pos;
+    int c = 0;
+    if (NG > 0) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) c += __popc(wp[g * gstride] & f[g]);
+    } else {
+      for (int g = 0; g < q.ng; ++g) c += __popc(wp[g * gstride] & foot[r * q.ng + g]);
+    }
+    mine[pos] = (uint16_t)c;
+    cm = max(cm, c);
+  }
+  for (int o = R; o < 32; o <<= 1) cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+  if (qpos == 0) atomicMax(s_cmax + r, cm);
+  __syncthreads();
+
+  // ---- mask cut, masked maximum, arg-min candidates --------------------------------- //
+  const int cmin = (int)ceil(q.overlap_threshold * (double)s_cmax[r]);
+  Cand<V> bmin = {V(0), -1}, bmask = {V(0), -1};
+  V vm = V(0);
+  bool any = false;
+  for (int pos = warp * ppw + qpos; pos < P; pos += step) {
+    if ((int)mine[pos] < cmin) continue;
+    const V x = v[pos];
+    vm = (!any || x > vm) ? x : vm;
+    any = true;
+    take(bmask, x, pos);
+    if (M != 0) {
+      const int i = __umulhi((uint32_t)pos, q.mulPw), j = pos - i * Pw;
+      if (local_min<V, M>(v, x, i, j, Ph, Pw, q.minorder)) take(bmin, x, pos);
+    }
+  }
+  for (int o = R; o < 32; o <<= 1) {
+    const V xv = __shfl_xor_sync(0xffffffffu, bmin.v, o);
+    const int xi = __shfl_xor_sync(0xffffffffu, bmin.idx, o);
+    if (xi >= 0) take(bmin, xv, xi);
+    const V yv = __shfl_xor_sync(0xffffffffu, bmask.v, o);
+    const int yi = __shfl_xor_sync(0xffffffffu, bmask.idx, o);
+    if (yi >= 0) take(bmask, yv, yi);
+    const V zv = __shfl_xor_sync(0xffffffffu, vm, o);
+    const bool za = __shfl_xor_sync(0xffffffffu, (int)any, o) != 0;
+    if (za) {
+      vm = (!any || zv > vm) ? zv : vm;
+      any = true;
+    }
+  }
+  if (qpos == 0) {
+    s_bmin[warp][r] = bmin;
+    s_bmask[warp][r] = bmask;
+    s_vm[warp][r] = vm;
+    s_any[warp][r] = any;
+  }
+  __syncthreads();
+  if (tid < R) {
+    Cand<V> a = {V(0), -1}, b = {V(0), -1};
+    V m2 = V(0);
+    bool have = false;
+    for (int w = 0; w < NW; ++w) {
+      if (s_bmin[w][tid].idx >= 0) take(a, s_bmin[w][tid].v, s_bmin[w][tid].idx);
+      if (s_bmask[w][tid].idx >= 0) take(b, s_bmask[w][tid].v, s_bmask[w][tid].idx);
+      if (s_any[w][tid]) {
+        m2 = (!have || s_vm[w][tid] > m2) ? s_vm[w][tid] : m2;
+        have = true;
+      }
+    }
+    const Cand<V> pick = a.idx >= 0 ? a : b;
+    actions[(size_t)e * R + tid] = pick.idx;
+    s_pick[tid] = pick.v;
+    s_pick_i[tid] = pick.idx;
+    s_fill[tid] = (double)m2 + 0.001;
+  }
+  __syncthreads();
+  if (best && tid == 0) {
+    // PyGreedy batchwise: first argmax over views of -value (policies.py:78-80)
+    int bv = 0;
+    for (int k = 1; k < R; ++k)
+      if (s_pick[k] < s_pick[bv]) bv = k;
+    best[2 * (size_t)e] = bv;
+    best[2 * (size_t)e + 1] = s_pick_i[bv];
+  }
+  if (shown) {
+    const double fill = s_fill[r];
+    double* sh = shown + ((size_t)e * R + r) * P;
+    for (int pos = warp * ppw + qpos; pos < P; pos += step)
+      sh[pos] = -((int)mine[pos] >= cmin ? (double)v[pos] : fill);
+  }
+}
+
 template <typename V, typename In>
 int launch_mask_select(const V* values, const In* walls, const In* goals, const In* rocks,
                        int64_t* actions, double* shown, int64_t* best, int E, int R, int H,
@@ -527,6 +709,30 @@ int launch_mask_select(const V* values, const In* walls, const In* goals, const 
     k<<<E, kSelThreads, smem, stream>>>(values, walls, goals, rocks, actions, shown, best, \
                                         q);                                                \
   } while (0)
+  const bool pow2 = R <= 32 && (R & (R - 1)) == 0;
+  const size_t packed_smem = 4 * ((size_t)H * q.nW + (size_t)R * q.ng + (size_t)H * q.Pw) +
+                             2 * (size_t)R * P + staged;
+  if (pow2 && packed_smem <= 56 * 1024 && minorder <= 1) {
+#define SRL_MSP_LAUNCH(MM, NGG)                                                            \
+  do {                                                                                     \
+    auto k = mask_select_packed_kernel<V, In, MM, NGG>;                                    \
+    SRL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                  (int)packed_smem));                                      \
+    k<<<E, kSelThreads, packed_smem, stream>>>(values, walls, goals, rocks, actions,       \
+                                               shown, best, q);                            \
+  } while (0)
+    if (minorder == 0) {
+      if (q.ng == 8) SRL_MSP_LAUNCH(0, 8);
+      else if (q.ng == 32) SRL_MSP_LAUNCH(0, 32);
+      else SRL_MSP_LAUNCH(0, 0);
+    } else {
+      if (q.ng == 8) SRL_MSP_LAUNCH(1, 8);
+      else if (q.ng == 32) SRL_MSP_LAUNCH(1, 32);
+      else SRL_MSP_LAUNCH(1, 0);
+    }
+#undef SRL_MSP_LAUNCH
+    return check_launch("mask_select_packed_kernel");
+  }
   if (q.staged) {
     if (minorder == 0) SRL_MS_LAUNCH(true, 0);
     else if (minorder == 1) SRL_MS_LAUNCH(true, 1);
