@@ -156,6 +156,15 @@ SRL_API int srl_difference_f32(const float* walls, const float* rocks,
                        float* top, int E, int R, int H, int W, int h,
                        int difference_exponent, srl_stream_t stream);
 
+/* ---- a8: baselines.correlate / baselines.corrcoef (baselines.py:141-143, 79-85) --
+ * corr = correlate2d(o, n, 'valid') / n.sum(); coef = TM_CCOEFF_NORMED(o, n), with
+ * o, n the normalised maps.  The reference values come from scipy / OpenCV library
+ * code (summation order outside the reference tree): matched to a tolerance, not
+ * bit for bit (float64 window sums, rounded once).  Either output may be NULL. */
+SRL_API int srl_correlate_f32(const float* walls, const float* rocks, const float* level,
+                              float* corr, float* coef, int E, int R, int H, int W, int h,
+                              srl_stream_t stream);
+
 /* ---- a2/a3: Observer.__call__ rasterisation + depth->elevation
  *      (observer.py:252-260, 267-277; pybullet.getCameraImage) ----------------
  * One job = one image: a camera (column-major GL view and projection matrices,

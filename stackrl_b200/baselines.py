@@ -121,6 +121,32 @@ def difference(inputs, mask=None, difference_exponent=2, weights_exponent=2,
   return f
 
 
+# ---- baselines.py:141-143 ---------------------------------------------------- #
+def correlate(inputs, **kwargs):
+  """Cross-correlation heuristic: correlate2d(o, n, 'valid') / n.sum(), float32.
+  Matches scipy to ~1e-6 relative (library summation order)."""
+  walls, goals, rocks = _planes(inputs)
+  if walls.dtype != torch.float32:
+    raise TypeError('correlate is wired for float32 observations')
+  corr, _ = capi.correlate_f32(walls, rocks, goals.amax(dim=(1, 2)), want_coef=False)
+  return corr[0, 0].cpu().numpy()
+
+
+# ---- baselines.py:79-114 ----------------------------------------------------- #
+def corrcoef(inputs, mask=None, localized=False, **kwargs):
+  """Correlation-coefficient heuristic (the reference's OpenCV
+  TM_CCOEFF_NORMED path, baselines.py:84-85).  float32, matched to ~1e-5
+  absolute.  ``localized=True`` (masked Python loop in the reference) is not
+  accelerated."""
+  if localized:
+    raise NotImplementedError('corrcoef(localized=True) has no GPU kernel')
+  walls, goals, rocks = _planes(inputs)
+  if walls.dtype != torch.float32:
+    raise TypeError('corrcoef is wired for float32 observations')
+  _, coef = capi.correlate_f32(walls, rocks, goals.amax(dim=(1, 2)), want_corr=False)
+  return coef[0, 0].cpu().numpy()
+
+
 # ---- baselines.py:145-150 ---------------------------------------------------- #
 def random(inputs, seed=None, **kwargs):
   """Random values in the shape of the heuristics (host RNG, like the reference:
@@ -140,8 +166,10 @@ def goal_overlap(inputs, threshold=0.75, **kwargs):
 
 methods = {
   'random': random,
+  'correlate': correlate,
   'height': height,
   'difference': difference,
+  'corrcoef': corrcoef,
 }
 
 

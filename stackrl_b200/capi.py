@@ -50,6 +50,7 @@ _SIGNATURES = {
   'srl_score_f32': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_difference_weights': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
   'srl_difference_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+  'srl_correlate_f32': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
   'srl_raster': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_reward_sums_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
   'srl_pack_obs': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_float, _I, _P]),
@@ -342,6 +343,21 @@ def score_f32(walls, goals, rocks, level=None, level_mode=2, minorder=1,
                              int(level_mode), int(minorder), float(overlap_threshold),
                              _stream()))
   return values, actions, best
+
+
+def correlate_f32(walls, rocks, level=None, want_corr=True, want_coef=True):
+  """-> (correlate [E,R,Ph,Pw] f32 | None, corrcoef [E,R,Ph,Pw] f32 | None)."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  dev = walls.device
+  args = (_dev(walls, torch.float32, 'walls'), _dev(rocks, torch.float32, 'rocks'),
+          _opt(level, torch.float32, 'level'))
+  shape = (E, R, H - h + 1, W - h + 1)
+  corr = torch.empty(shape, dtype=torch.float32, device=dev) if want_corr else None
+  coef = torch.empty(shape, dtype=torch.float32, device=dev) if want_coef else None
+  with torch.cuda.device(dev):
+    _check(lib.srl_correlate_f32(*args, _opt(corr, torch.float32, 'corr'),
+                                 _opt(coef, torch.float32, 'coef'), E, R, H, W, h, _stream()))
+  return corr, coef
 
 
 def microbench_addmax(variant, iters=2000):

@@ -171,6 +171,13 @@ int srl_mask_select_f64_u8(const double* values, const uint8_t* walls, const uin
                                  h, minorder, overlap_threshold, (cudaStream_t)stream);
 }
 
+int srl_correlate_f32(const float* walls, const float* rocks, const float* level,
+                      float* corr, float* coef, int E, int R, int H, int W, int h,
+                      srl_stream_t stream) {
+  return srl::correlate_f32(walls, rocks, level, corr, coef, E, R, H, W, h,
+                            (cudaStream_t)stream);
+}
+
 int srl_microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   return srl::microbench_addmax(variant, iters, host_cells_per_s);
 }

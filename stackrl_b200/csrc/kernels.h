@@ -66,6 +66,9 @@ int score_f32(const float* walls, const float* goals, const float* rocks, const 
               int h, int level_mode, int minorder, double overlap_threshold,
               cudaStream_t stream);
 
+int correlate_f32(const float* walls, const float* rocks, const float* level, float* corr,
+                  float* coef, int E, int R, int H, int W, int h, cudaStream_t stream);
+
 int microbench_addmax(int variant, int iters, double* host_cells_per_s);
 
 }  // namespace srl

@@ -114,3 +114,21 @@ def test_baseline_difference_actions(B, scoring_golden):
 def test_random_method_is_numpy_stream(B):
   obs = synth.observation(2, 16, 16, 4)
   assert np.array_equal(B.random(obs, seed=5), S.random(obs, seed=5))
+
+
+@pytest.mark.parametrize('case', ['c2like_f32', 'nonsquare_wall_f32', 'dense_rock_f32',
+                                  'ties_f32', 'c4like_f32', 'c5like_f32'])
+def test_correlate_and_corrcoef_within_tolerance(B, scoring_golden, case):
+  """correlate / corrcoef are defined by scipy / OpenCV library summation order
+  (not part of the reference tree): tolerance match, stated here -- 1e-5 relative
+  for correlate, 2e-5 absolute for the correlation coefficient."""
+  obs = scoring_golden.obs(case)
+  want = scoring_golden[case + '/correlate']
+  got = B.correlate(obs)
+  assert got.dtype == want.dtype and got.shape == want.shape
+  np.testing.assert_allclose(got, want, rtol=1e-5, atol=0)
+  want = scoring_golden[case + '/corrcoef']
+  got = B.corrcoef(obs)
+  assert got.dtype == want.dtype and got.shape == want.shape
+  np.testing.assert_allclose(got, want, rtol=0, atol=2e-5)
+  assert set(B.methods) == {'random', 'correlate', 'height', 'difference', 'corrcoef'}
