@@ -108,10 +108,11 @@ maxplus_staged_kernel(const MaxPlusParams p) {
       float4 x = lds128(raw_wall + 4 * q);
       if (scaled) {
         const float lv = __ldg(p.level + e0 + fdiv(row, p.dH));
-        x.x = div_level(x.x, lv);
-        x.y = div_level(x.y, lv);
-        x.z = div_level(x.z, lv);
-        x.w = div_level(x.w, lv);
+        const float inv = pow2_inverse(lv);
+        x.x = div_level(x.x, lv, inv);
+        x.y = div_level(x.y, lv, inv);
+        x.z = div_level(x.z, lv, inv);
+        x.w = div_level(x.w, lv, inv);
       }
       *reinterpret_cast<float4*>(wall_s + row * Ws + 4 * c4) = x;
     }
@@ -122,10 +123,11 @@ maxplus_staged_kernel(const MaxPlusParams p) {
       const float lv = scaled ? __ldg(p.level + e0 + fdiv(slot, p.dRC)) : 1.f;
       float4 x = lds128(raw_rock + 4 * q);
       bool dead = false;
-      x.x = prep_rock(x.x, scaled, lv, p.threshold, dead);
-      x.y = prep_rock(x.y, scaled, lv, p.threshold, dead);
-      x.z = prep_rock(x.z, scaled, lv, p.threshold, dead);
-      x.w = prep_rock(x.w, scaled, lv, p.threshold, dead);
+      const float inv = scaled ? pow2_inverse(lv) : 0.f;
+      x.x = prep_rock(x.x, scaled, lv, inv, p.threshold, dead);
+      x.y = prep_rock(x.y, scaled, lv, inv, p.threshold, dead);
+      x.z = prep_rock(x.z, scaled, lv, inv, p.threshold, dead);
+      x.w = prep_rock(x.w, scaled, lv, inv, p.threshold, dead);
       if (dead) flags[slot] = 1;
       float* dst = rock_s + slot * p.rock_stride + u * hp + 4 * c4;
       *reinterpret_cast<float4*>(dst) = x;
@@ -295,7 +297,7 @@ maxplus_direct_kernel(const MaxPlusParams p) {
     float n = kNegInf;
     if ((int)c < h) {
       bool dead = false;
-      n = prep_rock(*q, scaled, scaled ? __ldg(p.level + e0 + el) : 1.f, p.threshold,
+      n = prep_rock(*q, scaled, scaled ? __ldg(p.level + e0 + el) : 1.f, 0.f, p.threshold,
                     dead);
       if (dead) masked[slot] = 1;
     }

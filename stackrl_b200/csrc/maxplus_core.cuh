@@ -161,6 +161,7 @@ __device__ __forceinline__ void sweep_item(float (&acc)[T], const float* wbase,
   static_assert((T - 1) % 4 == 0 && 4 * NR4 >= T + VC - 1, "tile shape");
 #pragma unroll
   for (int t = 0; t < T; ++t) acc[t] = kNegInf;
+#pragma unroll 2
   for (int u = 0; u < h; ++u) {
     for (int vc = 0; vc < hp; vc += VC) {
       float row[4 * NR4];
@@ -202,10 +203,26 @@ __device__ __forceinline__ float div_level(float x, float level) {
   return x == 0.f ? __fmul_rn(x, level) : __fdiv_rn(x, level);
 }
 
+// Division by a goal level that is a power of two (the reference default,
+// max_z - object_z = 0.25, is one) is an exact scaling: x / 2^k == x * 2^-k bit
+// for bit (both are the correctly rounded value of the same real number, also in
+// the subnormal and overflow ranges), so the prep pass may multiply instead.
+// `inv` is 0 when the level is not a (normal) power of two whose inverse is
+// normal too, and the IEEE division is used.
+__device__ __forceinline__ float pow2_inverse(float level) {
+  const uint32_t b = __float_as_uint(level);
+  const uint32_t ex = (b >> 23) & 0xff;
+  if ((b & 0x807fffffu) != 0u || ex < 64 || ex > 190) return 0.f;
+  return __uint_as_float((254u - ex) << 23);
+}
+__device__ __forceinline__ float div_level(float x, float level, float inv) {
+  return inv != 0.f ? __fmul_rn(x, inv) : div_level(x, level);
+}
+
 // Normalise + mask one rock value (baselines.py:24-25, :32).
-__device__ __forceinline__ float prep_rock(float n, bool scaled, float level,
+__device__ __forceinline__ float prep_rock(float n, bool scaled, float level, float inv,
                                            float thr, bool& dead) {
-  if (scaled) n = div_level(n, level);
+  if (scaled) n = div_level(n, level, inv);
   const bool live = n > thr;
   dead = dead || !live;
   return live ? n : kNegInf;

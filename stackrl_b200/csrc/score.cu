@@ -171,10 +171,11 @@ score_fused_kernel(const ScoreParams sp) {
         const uint32_t el = fdiv(row, p.dH);
         const float lv = sp.level_mode == 1 ? __ldg(p.level + e0 + el)
                                             : __uint_as_float(level_bits[el]);
-        x.x = div_level(x.x, lv);
-        x.y = div_level(x.y, lv);
-        x.z = div_level(x.z, lv);
-        x.w = div_level(x.w, lv);
+        const float inv = pow2_inverse(lv);
+        x.x = div_level(x.x, lv, inv);
+        x.y = div_level(x.y, lv, inv);
+        x.z = div_level(x.z, lv, inv);
+        x.w = div_level(x.w, lv, inv);
       }
       *reinterpret_cast<float4*>(wall_s + row * Ws + 4 * c4) = x;
     }
@@ -189,10 +190,11 @@ score_fused_kernel(const ScoreParams sp) {
       }
       float4 x = lds128(raw_rock + 4 * q);
       bool dead = false;
-      x.x = prep_rock(x.x, scaled, lv, p.threshold, dead);
-      x.y = prep_rock(x.y, scaled, lv, p.threshold, dead);
-      x.z = prep_rock(x.z, scaled, lv, p.threshold, dead);
-      x.w = prep_rock(x.w, scaled, lv, p.threshold, dead);
+      const float inv = scaled ? pow2_inverse(lv) : 0.f;
+      x.x = prep_rock(x.x, scaled, lv, inv, p.threshold, dead);
+      x.y = prep_rock(x.y, scaled, lv, inv, p.threshold, dead);
+      x.z = prep_rock(x.z, scaled, lv, inv, p.threshold, dead);
+      x.w = prep_rock(x.w, scaled, lv, inv, p.threshold, dead);
       if (dead) flags[slot] = 1;
       *reinterpret_cast<float4*>(rock_s + slot * p.rock_stride + u * hp + 4 * c4) = x;
       float* sh = rock_sh + slot * p.rock_stride + u * hp + 4 * c4;
