@@ -353,9 +353,7 @@ int launch(const MaxPlusParams& p, bool staged, int blocks, int threads, size_t 
   } while (0)
   if (staged) {
     if (paired == 0) SRL_LAUNCH(maxplus_staged_kernel<T, VC, 0>);
-    else if (paired == 1) SRL_LAUNCH(maxplus_staged_kernel<T, VC, 1>);
-    else if (paired == 3) SRL_LAUNCH(maxplus_staged_kernel<T, VC, 3>);
-    else SRL_LAUNCH(maxplus_staged_kernel<T, VC, 5>);
+    else SRL_LAUNCH(maxplus_staged_kernel<T, VC, 1>);
   } else {
     if (paired == 0) SRL_LAUNCH(maxplus_direct_kernel<T, VC, 0>);
     else SRL_LAUNCH(maxplus_direct_kernel<T, VC, 1>);
@@ -385,7 +383,7 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
 
   const Choice c = choose_tile(p.Pw, h);
   const int T = c.T, VC = c.VC;
-  const int paired = variant;     // 0 plain, 1 paired, 3/5 paired + grouped issue order
+  const int paired = variant != 0;   // 0: FADD + FMNMX, 1: FADD2 + FMNMX3 (default)
   p.hp = round_up(h, VC);
   p.strips = strips_for(p.Pw, T);
   // Columns a thread may touch: strip start + (hp - VC) + 4*NR4 floats.

@@ -93,67 +93,8 @@ __device__ __forceinline__ void cell_block(float (&acc)[T],
   }
 }
 
-// Same cells as cell_block<.., true>, issued in runs that share one rock pair:
-// GROUP FADD2s with the same second operand back to back (ptxas can then flag
-// it .reuse and the add reads only the wall pair from the register file),
-// followed by the GROUP FMNMX3s that consume them.  Measured limiter of the
-// sweep is register-file operand bandwidth, not the FMA/ALU pipes.
-template <int T, int VC, int GROUP>
-__device__ __forceinline__ void cell_block_grouped(float (&acc)[T],
-                                                   const float (&row)[4 * ((T + VC + 2) / 4)],
-                                                   const float (&nv)[VC],
-                                                   const float (&nvs)[VC]) {
-  constexpr int NE = (T + 1) / 2;    // even output columns 0, 2, ..
-  constexpr int NO = T / 2;          // odd output columns 1, 3, ..
-#pragma unroll
-  for (int v = 0; v < VC; v += 2) {
-#pragma unroll
-    for (int c0 = 0; c0 < NE; c0 += GROUP) {
-      float s0[GROUP], s1[GROUP];
-#pragma unroll
-      for (int c = 0; c < GROUP; ++c)
-        if (c0 + c < NE) {
-          const int t = 2 * (c0 + c);
-          fadd2(s0[c], s1[c], row[t + v], row[t + v + 1], nv[v], nv[v + 1]);
-        }
-#pragma unroll
-      for (int c = 0; c < GROUP; ++c)
-        if (c0 + c < NE) {
-          const int t = 2 * (c0 + c);
-          acc[t] = fmax3(acc[t], s0[c], s1[c]);
-        }
-    }
-    if (v + 2 < VC) {
-      // odd columns: cells (v+1, v+2) with the shifted pair (nv[v+1], nv[v+2])
-#pragma unroll
-      for (int c0 = 0; c0 < NO; c0 += GROUP) {
-        float s0[GROUP], s1[GROUP];
-#pragma unroll
-        for (int c = 0; c < GROUP; ++c)
-          if (c0 + c < NO) {
-            const int t = 2 * (c0 + c) + 1;
-            fadd2(s0[c], s1[c], row[t + v + 1], row[t + v + 2], nvs[v], nvs[v + 1]);
-          }
-#pragma unroll
-        for (int c = 0; c < GROUP; ++c)
-          if (c0 + c < NO) {
-            const int t = 2 * (c0 + c) + 1;
-            acc[t] = fmax3(acc[t], s0[c], s1[c]);
-          }
-      }
-    }
-  }
-  // odd columns: the two unpaired cells v = 0 and v = VC-1
-#pragma unroll
-  for (int t = 1; t < T; t += 2) {
-    const float e0 = row[t] + nv[0];
-    const float e1 = row[t + VC - 1] + nv[VC - 1];
-    acc[t] = fmax3(acc[t], e0, e1);
-  }
-}
-
 // All (add, max) cells of one item: T outputs of one output row against one rock.
-template <int T, int VC, int PAIRED>   // 0 plain, 1 paired (interleaved), 2.. paired, grouped
+template <int T, int VC, int PAIRED>   // 0: FADD + FMNMX per cell, 1: FADD2 + FMNMX3 per cell pair
 __device__ __forceinline__ void sweep_item(float (&acc)[T], const float* wbase,
                                            const float* rbase, const float* sbase,
                                            int h, int hp, int Ws) {
@@ -190,8 +131,7 @@ __device__ __forceinline__ void sweep_item(float (&acc)[T], const float* wbase,
           nvs[4 * k + 3] = y.w;
         }
       }
-      if constexpr (PAIRED >= 2) cell_block_grouped<T, VC, PAIRED>(acc, row, nv, nvs);
-      else cell_block<T, VC, PAIRED == 1>(acc, row, nv, nvs);
+      cell_block<T, VC, PAIRED == 1>(acc, row, nv, nvs);
     }
   }
 }
