@@ -540,15 +540,17 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
       if (lane == 0) below[row * q.nW + word] = bits;
     }
   }
+  // pf (rows packed per word) is 1, 2 or 4: shifts and masks, no divisions
+  const int lp = q.pf == 4 ? 2 : (q.pf == 2 ? 1 : 0);
   for (int r = warp; r < R; r += NW) {
     const In* rk = rock + (size_t)r * h * h;
     uint32_t packed = 0;
     for (int u = 0; u < h; ++u) {
       const uint32_t bits = __ballot_sync(0xffffffffu, lane < h && rk[u * h + lane] > In(0));
-      const int sft = (u % q.pf) * q.hb;
-      packed |= (bits & hmask) << sft;
-      if (u % q.pf == q.pf - 1 || u == h - 1) {
-        if (lane == 0) foot[r * q.ng + u / q.pf] = packed;
+      const int sub = u & (q.pf - 1);
+      packed |= (bits & hmask) << (sub * q.hb);
+      if (sub == q.pf - 1 || u == h - 1) {
+        if (lane == 0) foot[r * q.ng + (u >> lp)] = packed;
         packed = 0;
       }
     }
