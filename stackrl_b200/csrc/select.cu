@@ -714,7 +714,7 @@ int launch_mask_select(const V* values, const In* walls, const In* goals, const 
   const bool pow2 = R <= 32 && (R & (R - 1)) == 0;
   const size_t packed_smem = 4 * ((size_t)H * q.nW + (size_t)R * q.ng + (size_t)H * q.Pw) +
                              2 * (size_t)R * P + staged;
-  if (pow2 && packed_smem <= 56 * 1024 && minorder <= 1) {
+  if (pow2 && packed_smem <= 110 * 1024 && minorder <= 1) {     // >= 2 CTAs per SM
 #define SRL_MSP_LAUNCH(MM, NGG)                                                            \
   do {                                                                                     \
     auto k = mask_select_packed_kernel<V, In, MM, NGG>;                                    \
