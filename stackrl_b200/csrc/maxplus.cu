@@ -192,6 +192,238 @@ maxplus_staged_kernel(const MaxPlusParams p) {
 }
 
 // --------------------------------------------------------------------------- //
+// Stream kernel (small walls; default): warp-specialised, no CTA-wide barrier.
+//
+// One persistent CTA per SM = kConsumers sweep warps + kProducers prep warps.
+// The CTA owns a contiguous range of the global item stream (item = one strip of
+// one output row of one (environment, rotation); 32 consecutive items = one
+// "unit" = one warp pass), cut in whole units so that every SM sub-partition
+// carries the same number of warp passes whatever the map size (the 17 x 17 maps
+// of the 32/16 geometry give 136 items per environment = 4.25 warps).
+//   producers: raw wall + rocks of environment k arrive by bulk TMA into the
+//     producer's raw buffer; the warp converts them to the compute layout in ring
+//     slot k % nslot (division by the goal level, mask as -inf, shifted copy,
+//     "has masked cell" and "has negative value" flags), re-arms the TMA for its
+//     next environment and arrives on full[slot].
+//   consumers: wait full[slot] of the environment(s) of their 32 items, sweep,
+//     stage the 32 row segments (contiguous in the output tensor) in a per-warp
+//     buffer, arrive on empty[slot] with the number of items they finished, and
+//     send the segment block off with one bulk TMA store.
+// --------------------------------------------------------------------------- //
+constexpr int kConsumers = 16, kProducers = 2;
+constexpr int kStreamThreads = (kConsumers + kProducers) * 32;
+
+template <int T, int VC>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+maxplus_stream_kernel(const MaxPlusParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int H = p.H, W = p.W, h = p.h, hp = p.hp, Ws = p.Ws, R = p.R;
+  const int Ph = p.Ph, Pw = p.Pw, P = Ph * Pw, nslot = p.nslot, ipe = p.ipe;
+  constexpr int S = T - 1;
+
+  // ---- shared memory carve-up ---------------------------------------------- //
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + nslot;
+  uint64_t* rawbar = empty + nslot;
+  int* masked = reinterpret_cast<int*>(rawbar + kProducers);      // [nslot][R]
+  int* negative = masked + nslot * R;                              // [nslot]
+  const int head = round_up((2 * nslot + kProducers) * 8 + (nslot * R + nslot) * 4, 16);
+  const int raw_floats = H * W + R * h * h;
+  const int env_floats = p.wall_stride + 2 * R * p.rock_stride;
+  float* raw = reinterpret_cast<float*>(smem_raw + head);          // [kProducers][raw]
+  float* ring = raw + kProducers * raw_floats;                     // [nslot][env]
+  float* stage = ring + (size_t)nslot * env_floats;                // [kConsumers][32*T]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- this CTA's share of the item stream ----------------------------------- //
+  const long long u0 = (long long)p.units * blockIdx.x / gridDim.x;
+  const long long u1 = (long long)p.units * (blockIdx.x + 1) / gridDim.x;
+  const long long it0 = u0 * 32, it1 = min(u1 * 32, p.items);
+  if (it0 >= it1) return;
+  const int env_first = (int)(it0 / ipe), env_last = (int)((it1 - 1) / ipe);
+  const int nenv = env_last - env_first + 1;
+  const long long base = (long long)env_first * ipe;   // stream position of local 0
+
+  if (tid == 0) {
+    for (int s = 0; s < nslot; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, ipe);
+    }
+    for (int k = 0; k < kProducers; ++k) mbar_init(rawbar + k, 1);
+    fence_barrier_init();
+  }
+  // One-time fills of what the producers never rewrite: wall pad columns
+  // [W, Ws) (finite), rock pad columns and the last column of the shifted copy
+  // (-inf: never win, never count as masked).
+  for (int k = tid; k < nslot * env_floats; k += kStreamThreads) {
+    const int q = k % env_floats;
+    ring[k] = q < p.wall_stride ? 0.f : kNegInf;
+  }
+  __syncthreads();
+
+  if (warp >= kConsumers) {
+    // =========================== producer warp ============================== //
+    const int pw = warp - kConsumers;
+    float* myraw = raw + pw * raw_floats;
+    uint64_t* mybar = rawbar + pw;
+    const uint32_t wb = (uint32_t)H * W * 4, rb = (uint32_t)R * h * h * 4;
+    auto issue = [&](int k) {
+      const size_t e = (size_t)(env_first + k);
+      mbar_arrive_expect_tx(mybar, wb + rb);
+      tma_load_1d(myraw, p.walls + e * H * W, wb, mybar);
+      tma_load_1d(myraw + H * W, p.rocks + e * R * h * h, rb, mybar);
+    };
+    if (lane == 0 && pw < nenv) issue(pw);
+    const bool scaled = p.level != nullptr;
+    const int W4 = W / 4, h4 = h / 4;
+    int round = 0;
+    for (int k = pw; k < nenv; k += kProducers, ++round) {
+      uint32_t use, s;
+      fdivmod((uint32_t)k, p.dNslot, use, s);
+      float* wall_s = ring + (size_t)s * env_floats;
+      float* rock_s = wall_s + p.wall_stride;
+      float* rock_sh = rock_s + R * p.rock_stride;
+      int* flags = masked + s * R;
+      const float lv = scaled ? __ldg(p.level + env_first + k) : 1.f;
+      const float inv = scaled ? pow2_inverse(lv) : 0.f;
+      if (use > 0) mbar_wait(empty + s, (use - 1) & 1);   // slot drained
+      for (int r = lane; r < R; r += 32) flags[r] = 0;
+      __syncwarp();
+      mbar_wait(mybar, round & 1);                           // raw data landed
+      uint32_t neg = 0;
+      for (uint32_t q = lane; q < (uint32_t)(H * W4); q += 32) {
+        uint32_t row, c4;
+        fdivmod(q, p.dW4, row, c4);
+        float4 x = lds128(myraw + 4 * q);
+        if (scaled) {
+          x.x = div_level(x.x, lv, inv);
+          x.y = div_level(x.y, lv, inv);
+          x.z = div_level(x.z, lv, inv);
+          x.w = div_level(x.w, lv, inv);
+        }
+        neg |= __float_as_uint(x.x) | __float_as_uint(x.y) | __float_as_uint(x.z) |
+               __float_as_uint(x.w);
+        *reinterpret_cast<float4*>(wall_s + row * Ws + 4 * c4) = x;
+      }
+      for (uint32_t q = lane; q < (uint32_t)(R * h * h4); q += 32) {
+        uint32_t rrow, c4, slot, u;
+        fdivmod(q, p.dh4, rrow, c4);
+        fdivmod(rrow, p.dh, slot, u);
+        float4 x = lds128(myraw + H * W + 4 * q);
+        bool dead = false;
+        x.x = prep_rock(x.x, scaled, lv, inv, p.threshold, dead);
+        x.y = prep_rock(x.y, scaled, lv, inv, p.threshold, dead);
+        x.z = prep_rock(x.z, scaled, lv, inv, p.threshold, dead);
+        x.w = prep_rock(x.w, scaled, lv, inv, p.threshold, dead);
+        if (dead) flags[slot] = 1;
+        // sign bits of the live values (-inf marks a masked cell, not a negative)
+        neg |= (x.x == kNegInf ? 0u : __float_as_uint(x.x)) |
+               (x.y == kNegInf ? 0u : __float_as_uint(x.y)) |
+               (x.z == kNegInf ? 0u : __float_as_uint(x.z)) |
+               (x.w == kNegInf ? 0u : __float_as_uint(x.w));
+        float* dst = rock_s + slot * p.rock_stride + u * hp + 4 * c4;
+        *reinterpret_cast<float4*>(dst) = x;
+        float* sh = rock_sh + slot * p.rock_stride + u * hp + 4 * c4;
+        if (c4 != 0) sh[-1] = x.x;
+        sh[0] = x.y;
+        sh[1] = x.z;
+        sh[2] = x.w;
+      }
+      const bool any_neg = __any_sync(0xffffffffu, (neg >> 31) != 0u);
+      if (lane == 0) negative[s] = any_neg ? 1 : 0;
+      __syncwarp();
+      if (lane == 0) {
+        if (k + kProducers < nenv) {
+          fence_proxy_async();        // generic reads of myraw before the async rewrite
+          issue(k + kProducers);
+        }
+        mbar_arrive(full + s);
+        // Items of a boundary environment that belong to a neighbouring CTA.
+        uint32_t missing = 0;
+        if (k == 0) missing += (uint32_t)(it0 - base);
+        if (k == nenv - 1) missing += (uint32_t)(base + (long long)nenv * ipe - it1);
+        if (missing) mbar_arrive_count(empty + s, missing);
+      }
+    }
+    return;
+  }
+
+  // ============================= consumer warp ================================ //
+  float* mystage = stage + warp * (32 * T);
+  const bool out_aligned = (((uintptr_t)p.out) & 15) == 0;
+  for (long long q = u0 + warp; q < u1; q += kConsumers) {
+    const long long pos0 = q * 32;
+    const int nvalid = (int)min((long long)32, it1 - pos0);
+    const bool valid = lane < nvalid;
+    // local position (clamped for the idle lanes of the very last unit)
+    const uint32_t lp = (uint32_t)(pos0 - base) + (uint32_t)min(lane, nvalid - 1);
+    uint32_t k, rem, slot_i, rest, i, strip, use, s;
+    fdivmod(lp, p.dIpe, k, rem);
+    fdivmod(rem, p.dStrips, rest, strip);
+    fdivmod(rest, p.dPh, slot_i, i);
+    fdivmod(k, p.dNslot, use, s);
+    {
+      // Wait (warp-uniformly) for every environment the unit touches.
+      const uint32_t k_lo = __shfl_sync(0xffffffffu, k, 0);
+      const uint32_t k_hi = __shfl_sync(0xffffffffu, k, 31);
+      for (uint32_t kk = k_lo; kk <= k_hi; ++kk) {
+        uint32_t uu, ss;
+        fdivmod(kk, p.dNslot, uu, ss);
+        mbar_wait(full + ss, uu & 1);
+      }
+      __syncwarp();
+    }
+    const float* wall_s = ring + (size_t)s * env_floats;
+    const float* rock_s = wall_s + p.wall_stride + slot_i * p.rock_stride;
+    const float* rock_sh = rock_s + R * p.rock_stride;
+    const bool any_neg = __any_sync(0xffffffffu, negative[s] != 0);
+    float acc[T];
+    if (any_neg)
+      sweep_item<T, VC, 1, false>(acc, wall_s + i * Ws + strip * S, rock_s, rock_sh, h, hp,
+                                  Ws);
+    else
+      sweep_item<T, VC, 1, true>(acc, wall_s + i * Ws + strip * S, rock_s, rock_sh, h, hp,
+                                 Ws);
+    const bool floor0 = masked[s * R + slot_i] != 0;
+    const int ncols = ((int)strip == p.strips - 1) ? min(T, Pw - (int)strip * S) : S;
+    // Output offset of this item relative to the first item of the unit: the
+    // row segments of consecutive items are contiguous in out [E,R,Ph,Pw].
+    const long long goff = (long long)(env_first + k) * R * P + (long long)slot_i * P +
+                           i * Pw + strip * S;
+    const long long goff0 = __shfl_sync(0xffffffffu, goff, 0);
+    const int so = (int)(goff - goff0);
+
+    if (lane == 0) tma_store_wait_read();    // previous block has left mystage
+    __syncwarp();
+    if (valid) {
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+        if (t < ncols) mystage[so + t] = floor0 ? fmaxf(acc[t], 0.f) : acc[t];
+    }
+    // Everything this warp read from the ring is in registers now: release the
+    // environments.  The last lane of each environment inside the unit arrives
+    // with the number of its items in the unit.
+    const int total = __shfl_sync(0xffffffffu, so + ncols, nvalid - 1);
+    fence_proxy_async();
+    __syncwarp();
+    if (valid && (lane == nvalid - 1 || rem == (uint32_t)ipe - 1))
+      mbar_arrive_count(empty + s, min(rem, (uint32_t)lane) + 1);
+    float* gdst = p.out + goff0;
+    if (out_aligned && ((goff0 | total) & 3) == 0) {
+      if (lane == 0) {
+        tma_store_1d(gdst, mystage, (uint32_t)total * 4);
+        tma_store_commit();
+      }
+    } else {
+      for (int t = lane; t < total; t += 32) __stcs(gdst + t, mystage[t]);
+      __syncwarp();
+    }
+  }
+  if (lane == 0) tma_store_wait_all();
+}
+
+// --------------------------------------------------------------------------- //
 // Direct kernel (big walls): one CTA per (environment group, rotation chunk).
 // --------------------------------------------------------------------------- //
 template <int T, int VC, int PAIRED>
@@ -419,6 +651,59 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
   bool staged = p.tma_wall && p.tma_rock && staged_fits(1, can_stage_out, kBudget);
   if (const char* s = getenv("SRL_MP_MODE")) {
     if (atoi(s) == 0) staged = false;
+  }
+
+  // ---- stream kernel: warp-specialised, one persistent CTA per SM -------------- //
+  {
+    const int T1 = T;
+    p.ipe = R * p.Ph * p.strips;
+    p.items = (long long)E * p.ipe;
+    p.units = (int)((p.items + 31) / 32);
+    const size_t raw_b = ((size_t)H * W + (size_t)R * h * h) * 4;
+    const size_t env_b = wall_bytes + (size_t)R * rock_bytes;
+    const size_t stage_b = (size_t)kConsumers * 32 * T1 * 4;
+    auto stream_smem = [&](int ns) {
+      return (size_t)round_up((2 * ns + kProducers) * 8 + (ns * R + ns) * 4, 16) +
+             kProducers * raw_b + ns * env_b + stage_b;
+    };
+    const size_t kStreamMax = 227 * 1024;
+    int ns = 0;
+    while (ns < 24 && stream_smem(ns + 1) <= kStreamMax) ++ns;
+    int mode = 2;
+    if (const char* sm = getenv("SRL_MP_MODE")) mode = atoi(sm);
+    const int blocks_s = p.units < sms ? p.units : sms;
+    // index spaces of the fast divisions (n * d < 2^32) and the TMA tx count
+    const double per_cta = (double)p.items / blocks_s + 2.0 * p.ipe + 64;
+    const bool ok = paired && p.tma_wall && p.tma_rock && ns >= 3 && mode == 2 &&
+                    raw_b < (1u << 20) && per_cta * p.ipe < 4.0e9 && p.ipe < (1 << 20) &&
+                    (size_t)H * W < 65536 && (size_t)R * h * p.hp < 65536 &&
+                    p.items < (1ll << 40);
+    if (ok) {
+      p.nslot = ns;
+      p.G = 1; p.RC = R; p.rchunks = 1; p.stage_out = 1; p.ngroups = E;
+      p.dPh = make_fastdiv(p.Ph); p.dStrips = make_fastdiv(p.strips);
+      p.dRC = make_fastdiv(R); p.dW = make_fastdiv(W); p.dH = make_fastdiv(H);
+      p.dh = make_fastdiv(h); p.dhp = make_fastdiv(p.hp);
+      p.dW4 = make_fastdiv(W / 4); p.dh4 = make_fastdiv(h / 4);
+      p.dIpe = make_fastdiv(p.ipe); p.dNslot = make_fastdiv(ns);
+      const size_t smem_s = stream_smem(ns);
+#define SRL_MP_CASE(TT, VV)                                                          \
+  if (T == TT && VC == VV) {                                                         \
+    auto k = maxplus_stream_kernel<TT, VV>;                                          \
+    SRL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                  (int)smem_s));                                     \
+    k<<<blocks_s, kStreamThreads, smem_s, stream>>>(p);                              \
+    return check_launch("maxplus_stream_kernel");                                    \
+  }
+#define SRL_MP_ROW(VV)                                                            \
+  SRL_MP_CASE(5, VV) SRL_MP_CASE(9, VV) SRL_MP_CASE(13, VV) SRL_MP_CASE(17, VV)   \
+  SRL_MP_CASE(21, VV) SRL_MP_CASE(25, VV)
+      SRL_MP_ROW(4)
+      SRL_MP_ROW(8)
+      SRL_MP_ROW(16)
+#undef SRL_MP_ROW
+#undef SRL_MP_CASE
+    }
   }
 
   int G = 1, RC = R, blocks, threads;

@@ -47,14 +47,35 @@ struct MaxPlusParams {
   int tma_wall;     // wall rows can be bulk-copied (W % 4 == 0, 16-B aligned base)
   int tma_rock;     // rock rows can be bulk-copied (h % 4 == 0, 16-B aligned base)
   int stage_out;    // staged kernel: score maps leave by bulk TMA store
-  FastDiv dPh, dStrips, dRC, dW, dH, dh, dhp, dW4, dh4;
+  // stream kernel (maxplus_stream_kernel)
+  int nslot;        // environments resident in the compute-layout ring
+  int ipe;          // items (rotation, output row, strip) per environment
+  long long items;  // E * ipe
+  int units;        // ceil(items / 32): one warp-pass each
+  FastDiv dPh, dStrips, dRC, dW, dH, dh, dhp, dW4, dh4, dIpe, dNslot;
 };
 
 // Block of T x VC (add, max) cells: acc[t] = max(acc[t], row[t+v] + nv[v]).
 // PAIRED: nvs[v] = nv[v+1] is the one-column-shifted rock row, loaded from its
 // own smem copy so that (nvs[v], nvs[v+1]) for even v is an aligned register
 // pair holding (nv[v+1], nv[v+2]).
-template <int T, int VC, bool PAIRED>
+//
+// IMAX: the 3-input max is VIMNMX3 on the float bit patterns (signed 32-bit
+// integer order) instead of FMNMX3.  Exact whenever every operand is a
+// non-negative float or -inf, i.e. no wall or live rock value of the tile has
+// its sign bit set: non-negative floats order like their bit patterns, and -inf
+// (0xff800000) is below all of them as a signed integer too.  The callers test
+// that precondition per environment and fall back to FMNMX3 otherwise.
+template <bool IMAX>
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  if constexpr (IMAX)
+    return __int_as_float(__vimax3_s32(__float_as_int(a), __float_as_int(b),
+                                       __float_as_int(c)));
+  else
+    return fmax3(a, b, c);
+}
+
+template <int T, int VC, bool PAIRED, bool IMAX = false>
 __device__ __forceinline__ void cell_block(float (&acc)[T],
                                            const float (&row)[4 * ((T + VC + 2) / 4)],
                                            const float (&nv)[VC],
@@ -74,19 +95,19 @@ __device__ __forceinline__ void cell_block(float (&acc)[T],
         for (int v = 0; v < VC; v += 2) {
           float s0, s1;
           fadd2(s0, s1, row[t + v], row[t + v + 1], nv[v], nv[v + 1]);
-          acc[t] = fmax3(acc[t], s0, s1);
+          acc[t] = max3<IMAX>(acc[t], s0, s1);
         }
       } else {
         // odd output column: pair odd v with v+1 (k = t+v even), using the
         // shifted rock row; v = 0 and v = VC-1 stay single.
         float e0 = row[t] + nv[0];
         float e1 = row[t + VC - 1] + nv[VC - 1];
-        acc[t] = fmax3(acc[t], e0, e1);
+        acc[t] = max3<IMAX>(acc[t], e0, e1);
 #pragma unroll
         for (int v = 1; v + 1 < VC; v += 2) {
           float s0, s1;
           fadd2(s0, s1, row[t + v], row[t + v + 1], nvs[v - 1], nvs[v]);
-          acc[t] = fmax3(acc[t], s0, s1);
+          acc[t] = max3<IMAX>(acc[t], s0, s1);
         }
       }
     }
@@ -94,7 +115,7 @@ __device__ __forceinline__ void cell_block(float (&acc)[T],
 }
 
 // All (add, max) cells of one item: T outputs of one output row against one rock.
-template <int T, int VC, int PAIRED>   // 0: FADD + FMNMX per cell, 1: FADD2 + FMNMX3 per cell pair
+template <int T, int VC, int PAIRED, bool IMAX = false>   // PAIRED 0: FADD + FMNMX per cell, 1: FADD2 + 3-input max per cell pair
 __device__ __forceinline__ void sweep_item(float (&acc)[T], const float* wbase,
                                            const float* rbase, const float* sbase,
                                            int h, int hp, int Ws) {
@@ -131,7 +152,7 @@ __device__ __forceinline__ void sweep_item(float (&acc)[T], const float* wbase,
           nvs[4 * k + 3] = y.w;
         }
       }
-      cell_block<T, VC, PAIRED == 1>(acc, row, nv, nvs);
+      cell_block<T, VC, PAIRED == 1, IMAX>(acc, row, nv, nvs);
     }
   }
 }

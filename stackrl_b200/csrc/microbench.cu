@@ -61,7 +61,7 @@ __device__ __forceinline__ float vimax(float a, float b) {
 // in cell units (2 cells per FADD2 / FMNMX3 / VIMNMX3, 1 per FADD / FMNMX).
 template <int VARIANT>
 __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out,
-                                                      int iters) {
+                                                      int iters, int never) {
   float nv[kV];
   float acc[kT];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,11 +70,13 @@ __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out
 #pragma unroll
   for (int t = 0; t < kT; ++t) acc[t] = in[(tid + t) & 1023];
 
+  float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const float magic = __int_as_float(never);
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int v = 0; v < kV; v += 2) {
 #pragma unroll
-      for (int t = 0; t < kT; ++t) {
+      for (int t = 0; t < (VARIANT >= 10 ? 0 : kT); ++t) {
         const int k = ((t + 8) % kT) & ~1;     // even-aligned register pair
         const int k1 = (t + 8) % kT, k2 = (t + 9) % kT;
         if constexpr (VARIANT == 0) {
@@ -112,9 +114,76 @@ __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out
           acc[t] = vimax(acc[t], vadd(acc[k2], nv[v + 1]));
         }
       }
+      // Variants 10-13: the FADD2 + 3-input max mix issued in groups of G adds
+      // that share the rock pair (operand-reuse cache) followed by G maxes.
+      if constexpr (VARIANT >= 10 && VARIANT <= 13) {
+        constexpr int G = (VARIANT == 12) ? 4 : (VARIANT == 13) ? 16 : 8;
+#pragma unroll
+        for (int t0 = 0; t0 < kT; t0 += G) {
+          float s0[G], s1[G];
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const int k = ((t0 + g + 8) % kT) & ~1;
+            // even/odd t share the wall pair; add it to the pair of the next
+            // rock column for odd t so that no two adds are identical
+            if ((t0 + g) & 1) vadd2(s0[g], s1[g], acc[k], acc[k + 1], nv[(v + 2) % kV], nv[(v + 3) % kV]);
+            else vadd2(s0[g], s1[g], acc[k], acc[k + 1], nv[v], nv[v + 1]);
+          }
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if constexpr (VARIANT == 11) acc[t0 + g] = vmax3(acc[t0 + g], s0[g], s1[g]);
+            else acc[t0 + g] = vimax3(acc[t0 + g], s0[g], s1[g]);
+          }
+        }
+      }
+      // Variant 14: warp-specialised -- even warps issue only FADD2 (rock pair
+      // reused), odd warps only VIMNMX3: do the two pipes overlap when the
+      // instructions come from different warps?
+      if constexpr (VARIANT == 14) {
+        if ((threadIdx.x >> 5) & 1) {
+#pragma unroll
+          for (int t = 0; t < kT; ++t)
+            acc[t] = vimax3(acc[(t + 8) % kT], acc[(t + 9) % kT], nv[v]);
+        } else {
+#pragma unroll
+          for (int t = 0; t < kT; ++t) {
+            const int k = (2 * t + 8) % kT;
+            float s0, s1;
+            vadd2(s0, s1, acc[k], acc[k + 1], nv[v], nv[v + 1]);
+            acc[(2 * t + 4) % kT] = s0;
+            acc[(2 * t + 5) % kT] = s1;
+          }
+        }
+      }
+      // Variants 15/16: groups of 8 adds and 8 maxes kept apart by never-taken
+      // loop exits (basic-block boundaries ptxas cannot schedule across).
+      if constexpr (VARIANT == 15 || VARIANT == 16) {
+        constexpr int G = 8;
+#pragma unroll
+        for (int t0 = 0; t0 < kT; t0 += G) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            // G distinct wall pairs, one rock pair per group (as in the sweep)
+            const int k = (2 * g + 8) % kT, vv = (v + (t0 ? 2 : 0)) % kV;
+            vadd2(s0[g], s1[g], acc[k], acc[k + 1], nv[vv], nv[vv + 1]);
+          }
+          if (s1[G - 1] == magic) goto done;      // never true; ends the add block
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if constexpr (VARIANT == 16) acc[t0 + g] = vmax3(acc[t0 + g], s0[g], s1[g]);
+            else acc[t0 + g] = vimax3(acc[t0 + g], s0[g], s1[g]);
+          }
+          if (acc[t0 + G - 1] == magic) goto done;  // ends the max block
+        }
+      }
     }
   }
+done:
   float r = acc[0];
+  if constexpr (VARIANT == 15 || VARIANT == 16) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) r = fmaxf(r, fmaxf(s0[g], s1[g]));
+  }
 #pragma unroll
   for (int t = 1; t < kT; ++t) r = fmaxf(r, acc[t]);
   out[tid] = r;
@@ -123,7 +192,7 @@ __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out
 }  // namespace
 
 int microbench_addmax(int variant, int iters, double* host_cells_per_s) {
-  SRL_REQUIRE(host_cells_per_s != nullptr && iters > 0 && variant >= 0 && variant <= 9,
+  SRL_REQUIRE(host_cells_per_s != nullptr && iters > 0 && variant >= 0 && variant <= 16,
               SRL_E_INVALID, "microbench_addmax: bad arguments");
   const int sms = sm_count();
   SRL_REQUIRE(sms > 0, SRL_E_CUDA, "microbench_addmax: no device");
@@ -141,9 +210,9 @@ int microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   for (int rep = 0; rep < 4; ++rep) {   // rep 0 is the warm-up
     SRL_CUDA(cudaEventRecord(t0));
     switch (variant) {
-#define SRL_MB(V) case V: addmax_kernel<V><<<blocks, threads>>>(in, out, iters); break;
+#define SRL_MB(V) case V: addmax_kernel<V><<<blocks, threads>>>(in, out, iters, 0x7fc12345); break;
       SRL_MB(0) SRL_MB(1) SRL_MB(2) SRL_MB(3) SRL_MB(4) SRL_MB(5) SRL_MB(6) SRL_MB(7)
-      SRL_MB(8) SRL_MB(9)
+      SRL_MB(8) SRL_MB(9) SRL_MB(10) SRL_MB(11) SRL_MB(12) SRL_MB(13) SRL_MB(14) SRL_MB(15) SRL_MB(16)
 #undef SRL_MB
     }
     SRL_CUDA(cudaEventRecord(t1));
@@ -159,7 +228,7 @@ int microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   cudaFree(out);
   if (rc != SRL_OK) return rc;
   double cells = (double)blocks * threads * (double)iters * kT * kV;
-  if (variant == 6) cells *= 0.5;   // one FADD2 per two (v, t) steps
+  if (variant == 6 || variant == 14) cells *= 0.5;   // one FADD2 per two (v, t) steps
   *host_cells_per_s = cells / (best_ms * 1e-3);
   return SRL_OK;
 }
