@@ -95,6 +95,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
       : "memory");
 }
 
+// Named barrier among `count` threads (count % 32 == 0) of the CTA.
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void st_release_shared(int* p, int v) {
+  asm volatile("st.release.cta.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v)
+               : "memory");
+}
+__device__ __forceinline__ int ld_acquire_shared(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p))
+               : "memory");
+  return v;
+}
+
 // global -> shared::cta bulk copy; bytes % 16 == 0, both addresses 16-B aligned.
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem,
                                             uint32_t bytes, uint64_t* bar) {

@@ -200,18 +200,24 @@ maxplus_staged_kernel(const MaxPlusParams p) {
 // "unit" = one warp pass), cut in whole units so that every SM sub-partition
 // carries the same number of warp passes whatever the map size (the 17 x 17 maps
 // of the 32/16 geometry give 136 items per environment = 4.25 warps).
-//   producers: raw wall + rocks of environment k arrive by bulk TMA into the
-//     producer's raw buffer; the warp converts them to the compute layout in ring
-//     slot k % nslot (division by the goal level, mask as -inf, shifted copy,
-//     "has masked cell" and "has negative value" flags), re-arms the TMA for its
-//     next environment and arrives on full[slot].
-//   consumers: wait full[slot] of the environment(s) of their 32 items, sweep,
-//     stage the 32 row segments (contiguous in the output tensor) in a per-warp
-//     buffer, arrive on empty[slot] with the number of items they finished, and
-//     send the segment block off with one bulk TMA store.
+//   producers (one group of kProducers warps, environments strictly in order):
+//     raw wall + rocks of environment k arrive by bulk TMA into raw buffer
+//     k % kRawDepth; the group converts them to the compute layout in ring slot
+//     k % nslot (division by the goal level, mask as -inf, shifted copy, "has
+//     masked cell" / "has negative value" flags), re-arms the TMA for
+//     environment k + kRawDepth and publishes ready[slot] = k + 1.
+//   consumers: wait until ready[slot] names the environment(s) of their 32
+//     items, sweep, stage the 32 row segments (contiguous in the output tensor)
+//     in a per-warp buffer, arrive on empty[slot] with the number of items they
+//     finished, and send the segment block off with one bulk TMA store.
+// A slot is rewritten only after all `ipe` items of its previous environment
+// arrived on empty[slot]; production is sequential, so a waiter is never more
+// than one mbarrier phase away, and `ready` carries the environment number
+// itself, so a consumer that runs far ahead cannot mistake an older tenant.
 // --------------------------------------------------------------------------- //
-constexpr int kConsumers = 16, kProducers = 2;
+constexpr int kConsumers = 16, kProducers = 4, kRawDepth = 2;
 constexpr int kStreamThreads = (kConsumers + kProducers) * 32;
+constexpr int kProducerThreads = kProducers * 32;
 
 template <int T, int VC>
 __global__ void __launch_bounds__(kStreamThreads, 1)
@@ -222,16 +228,16 @@ maxplus_stream_kernel(const MaxPlusParams p) {
   constexpr int S = T - 1;
 
   // ---- shared memory carve-up ---------------------------------------------- //
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* empty = full + nslot;
-  uint64_t* rawbar = empty + nslot;
-  int* masked = reinterpret_cast<int*>(rawbar + kProducers);      // [nslot][R]
-  int* negative = masked + nslot * R;                              // [nslot]
-  const int head = round_up((2 * nslot + kProducers) * 8 + (nslot * R + nslot) * 4, 16);
+  uint64_t* empty = reinterpret_cast<uint64_t*>(smem_raw);         // [nslot]
+  uint64_t* rawbar = empty + nslot;                                // [kRawDepth]
+  int* ready = reinterpret_cast<int*>(rawbar + kRawDepth);         // [nslot]
+  int* negative = ready + nslot;                                   // [nslot]
+  int* masked = negative + nslot;                                  // [nslot][R]
+  const int head = round_up((nslot + kRawDepth) * 8 + (2 * nslot + nslot * R) * 4, 16);
   const int raw_floats = H * W + R * h * h;
   const int env_floats = p.wall_stride + 2 * R * p.rock_stride;
-  float* raw = reinterpret_cast<float*>(smem_raw + head);          // [kProducers][raw]
-  float* ring = raw + kProducers * raw_floats;                     // [nslot][env]
+  float* raw = reinterpret_cast<float*>(smem_raw + head);          // [kRawDepth][raw]
+  float* ring = raw + kRawDepth * raw_floats;                      // [nslot][env]
   float* stage = ring + (size_t)nslot * env_floats;                // [kConsumers][32*T]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -246,13 +252,11 @@ maxplus_stream_kernel(const MaxPlusParams p) {
   const long long base = (long long)env_first * ipe;   // stream position of local 0
 
   if (tid == 0) {
-    for (int s = 0; s < nslot; ++s) {
-      mbar_init(full + s, 1);
-      mbar_init(empty + s, ipe);
-    }
-    for (int k = 0; k < kProducers; ++k) mbar_init(rawbar + k, 1);
+    for (int s = 0; s < nslot; ++s) mbar_init(empty + s, ipe);
+    for (int k = 0; k < kRawDepth; ++k) mbar_init(rawbar + k, 1);
     fence_barrier_init();
   }
+  for (int k = tid; k < nslot; k += kStreamThreads) ready[k] = 0;
   // One-time fills of what the producers never rewrite: wall pad columns
   // [W, Ws) (finite), rock pad columns and the last column of the shifted copy
   // (-inf: never win, never count as masked).
@@ -263,24 +267,25 @@ maxplus_stream_kernel(const MaxPlusParams p) {
   __syncthreads();
 
   if (warp >= kConsumers) {
-    // =========================== producer warp ============================== //
-    const int pw = warp - kConsumers;
-    float* myraw = raw + pw * raw_floats;
-    uint64_t* mybar = rawbar + pw;
+    // ============================ producer group ============================ //
+    const int pt = tid - kConsumers * 32;          // 0 .. kProducerThreads-1
     const uint32_t wb = (uint32_t)H * W * 4, rb = (uint32_t)R * h * h * 4;
     auto issue = [&](int k) {
       const size_t e = (size_t)(env_first + k);
-      mbar_arrive_expect_tx(mybar, wb + rb);
-      tma_load_1d(myraw, p.walls + e * H * W, wb, mybar);
-      tma_load_1d(myraw + H * W, p.rocks + e * R * h * h, rb, mybar);
+      float* dst = raw + (k % kRawDepth) * raw_floats;
+      uint64_t* bar = rawbar + (k % kRawDepth);
+      mbar_arrive_expect_tx(bar, wb + rb);
+      tma_load_1d(dst, p.walls + e * H * W, wb, bar);
+      tma_load_1d(dst + H * W, p.rocks + e * R * h * h, rb, bar);
     };
-    if (lane == 0 && pw < nenv) issue(pw);
+    if (pt == 0)
+      for (int k = 0; k < kRawDepth && k < nenv; ++k) issue(k);
     const bool scaled = p.level != nullptr;
     const int W4 = W / 4, h4 = h / 4;
-    int round = 0;
-    for (int k = pw; k < nenv; k += kProducers, ++round) {
+    for (int k = 0; k < nenv; ++k) {
       uint32_t use, s;
       fdivmod((uint32_t)k, p.dNslot, use, s);
+      const float* myraw = raw + (k % kRawDepth) * raw_floats;
       float* wall_s = ring + (size_t)s * env_floats;
       float* rock_s = wall_s + p.wall_stride;
       float* rock_sh = rock_s + R * p.rock_stride;
@@ -288,11 +293,12 @@ maxplus_stream_kernel(const MaxPlusParams p) {
       const float lv = scaled ? __ldg(p.level + env_first + k) : 1.f;
       const float inv = scaled ? pow2_inverse(lv) : 0.f;
       if (use > 0) mbar_wait(empty + s, (use - 1) & 1);   // slot drained
-      for (int r = lane; r < R; r += 32) flags[r] = 0;
-      __syncwarp();
-      mbar_wait(mybar, round & 1);                           // raw data landed
+      for (int r = pt; r < R; r += kProducerThreads) flags[r] = 0;
+      if (pt == 0) negative[s] = 0;
+      mbar_wait(rawbar + (k % kRawDepth), (k / kRawDepth) & 1);   // raw data landed
+      named_bar_sync(1, kProducerThreads);
       uint32_t neg = 0;
-      for (uint32_t q = lane; q < (uint32_t)(H * W4); q += 32) {
+      for (uint32_t q = pt; q < (uint32_t)(H * W4); q += kProducerThreads) {
         uint32_t row, c4;
         fdivmod(q, p.dW4, row, c4);
         float4 x = lds128(myraw + 4 * q);
@@ -306,7 +312,7 @@ maxplus_stream_kernel(const MaxPlusParams p) {
                __float_as_uint(x.w);
         *reinterpret_cast<float4*>(wall_s + row * Ws + 4 * c4) = x;
       }
-      for (uint32_t q = lane; q < (uint32_t)(R * h * h4); q += 32) {
+      for (uint32_t q = pt; q < (uint32_t)(R * h * h4); q += kProducerThreads) {
         uint32_t rrow, c4, slot, u;
         fdivmod(q, p.dh4, rrow, c4);
         fdivmod(rrow, p.dh, slot, u);
@@ -330,15 +336,14 @@ maxplus_stream_kernel(const MaxPlusParams p) {
         sh[1] = x.z;
         sh[2] = x.w;
       }
-      const bool any_neg = __any_sync(0xffffffffu, (neg >> 31) != 0u);
-      if (lane == 0) negative[s] = any_neg ? 1 : 0;
-      __syncwarp();
-      if (lane == 0) {
-        if (k + kProducers < nenv) {
-          fence_proxy_async();        // generic reads of myraw before the async rewrite
-          issue(k + kProducers);
+      if ((neg >> 31) != 0u) negative[s] = 1;
+      named_bar_sync(1, kProducerThreads);   // slot written, raw buffer read
+      if (pt == 0) {
+        if (k + kRawDepth < nenv) {
+          fence_proxy_async();        // generic reads of the raw buffer before its async rewrite
+          issue(k + kRawDepth);
         }
-        mbar_arrive(full + s);
+        st_release_shared(ready + s, k + 1);
         // Items of a boundary environment that belong to a neighbouring CTA.
         uint32_t missing = 0;
         if (k == 0) missing += (uint32_t)(it0 - base);
@@ -364,13 +369,13 @@ maxplus_stream_kernel(const MaxPlusParams p) {
     fdivmod(rest, p.dPh, slot_i, i);
     fdivmod(k, p.dNslot, use, s);
     {
-      // Wait (warp-uniformly) for every environment the unit touches.
+      // Wait (warp-uniformly) until every environment the unit touches is in
+      // its ring slot.
       const uint32_t k_lo = __shfl_sync(0xffffffffu, k, 0);
       const uint32_t k_hi = __shfl_sync(0xffffffffu, k, 31);
       for (uint32_t kk = k_lo; kk <= k_hi; ++kk) {
-        uint32_t uu, ss;
-        fdivmod(kk, p.dNslot, uu, ss);
-        mbar_wait(full + ss, uu & 1);
+        const uint32_t ss = kk - fdiv(kk, p.dNslot) * (uint32_t)nslot;
+        while (ld_acquire_shared(ready + ss) != (int)kk + 1) __nanosleep(32);
       }
       __syncwarp();
     }
@@ -385,6 +390,16 @@ maxplus_stream_kernel(const MaxPlusParams p) {
     else
       sweep_item<T, VC, 1, true>(acc, wall_s + i * Ws + strip * S, rock_s, rock_sh, h, hp,
                                  Ws);
+    // Decode the item again instead of keeping its indices live across the
+    // sweep (the register file is the scarce resource there).
+    {
+      uint32_t lp2 = lp;
+      asm volatile("" : "+r"(lp2));
+      fdivmod(lp2, p.dIpe, k, rem);
+      fdivmod(rem, p.dStrips, rest, strip);
+      fdivmod(rest, p.dPh, slot_i, i);
+      fdivmod(k, p.dNslot, use, s);
+    }
     const bool floor0 = masked[s * R + slot_i] != 0;
     const int ncols = ((int)strip == p.strips - 1) ? min(T, Pw - (int)strip * S) : S;
     // Output offset of this item relative to the first item of the unit: the
@@ -663,8 +678,8 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
     const size_t env_b = wall_bytes + (size_t)R * rock_bytes;
     const size_t stage_b = (size_t)kConsumers * 32 * T1 * 4;
     auto stream_smem = [&](int ns) {
-      return (size_t)round_up((2 * ns + kProducers) * 8 + (ns * R + ns) * 4, 16) +
-             kProducers * raw_b + ns * env_b + stage_b;
+      return (size_t)round_up((ns + kRawDepth) * 8 + (2 * ns + ns * R) * 4, 16) +
+             kRawDepth * raw_b + ns * env_b + stage_b;
     };
     const size_t kStreamMax = 227 * 1024;
     int ns = 0;

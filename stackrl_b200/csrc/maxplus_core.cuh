@@ -4,6 +4,8 @@
 // design notes.
 #pragma once
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace srl {
@@ -123,36 +125,46 @@ __device__ __forceinline__ void sweep_item(float (&acc)[T], const float* wbase,
   static_assert((T - 1) % 4 == 0 && 4 * NR4 >= T + VC - 1, "tile shape");
 #pragma unroll
   for (int t = 0; t < T; ++t) acc[t] = kNegInf;
+  // One flat loop over the (rock row, column chunk) pairs: rock rows are
+  // contiguous (hp floats each), the wall pointer skips to the next row after
+  // the last chunk of a row.
+  const int cpr = hp / VC, nchunks = h * cpr, wskip = Ws - hp;
+  int j = 0;
 #pragma unroll 2
-  for (int u = 0; u < h; ++u) {
-    for (int vc = 0; vc < hp; vc += VC) {
-      float row[4 * NR4];
-      float nv[VC];
-      float nvs[VC];
+  for (int c = 0; c < nchunks; ++c) {
+    float row[4 * NR4];
+    float nv[VC];
+    float nvs[VC];
 #pragma unroll
-      for (int k = 0; k < NR4; ++k) {
-        const float4 x = lds128(wbase + u * Ws + vc + 4 * k);
-        row[4 * k + 0] = x.x;
-        row[4 * k + 1] = x.y;
-        row[4 * k + 2] = x.z;
-        row[4 * k + 3] = x.w;
-      }
+    for (int k = 0; k < NR4; ++k) {
+      const float4 x = lds128(wbase + 4 * k);
+      row[4 * k + 0] = x.x;
+      row[4 * k + 1] = x.y;
+      row[4 * k + 2] = x.z;
+      row[4 * k + 3] = x.w;
+    }
 #pragma unroll
-      for (int k = 0; k < VC / 4; ++k) {
-        const float4 x = lds128(rbase + u * hp + vc + 4 * k);
-        nv[4 * k + 0] = x.x;
-        nv[4 * k + 1] = x.y;
-        nv[4 * k + 2] = x.z;
-        nv[4 * k + 3] = x.w;
-        if constexpr (PAIRED != 0) {
-          const float4 y = lds128(sbase + u * hp + vc + 4 * k);
-          nvs[4 * k + 0] = y.x;
-          nvs[4 * k + 1] = y.y;
-          nvs[4 * k + 2] = y.z;
-          nvs[4 * k + 3] = y.w;
-        }
+    for (int k = 0; k < VC / 4; ++k) {
+      const float4 x = lds128(rbase + 4 * k);
+      nv[4 * k + 0] = x.x;
+      nv[4 * k + 1] = x.y;
+      nv[4 * k + 2] = x.z;
+      nv[4 * k + 3] = x.w;
+      if constexpr (PAIRED != 0) {
+        const float4 y = lds128(sbase + 4 * k);
+        nvs[4 * k + 0] = y.x;
+        nvs[4 * k + 1] = y.y;
+        nvs[4 * k + 2] = y.z;
+        nvs[4 * k + 3] = y.w;
       }
-      cell_block<T, VC, PAIRED == 1, IMAX>(acc, row, nv, nvs);
+    }
+    cell_block<T, VC, PAIRED == 1, IMAX>(acc, row, nv, nvs);
+    wbase += VC;
+    rbase += VC;
+    sbase += VC;
+    if (++j == cpr) {
+      j = 0;
+      wbase += wskip;
     }
   }
 }
@@ -206,6 +218,10 @@ inline int strips_for(int Pw, int T) {
 inline Choice choose_tile(int Pw, int h) {
   Choice c;
   c.VC = h >= 13 ? 16 : (h >= 5 ? 8 : 4);
+  if (const char* s = getenv("SRL_MP_VC")) {   // tuning override
+    const int v = atoi(s);
+    if (v == 4 || v == 8 || v == 16) c.VC = v;
+  }
   int best = kTs[0];
   double best_cost = 1e30;
   for (int T : kTs) {
