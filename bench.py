@@ -427,14 +427,14 @@ def run_graft(args, rank, local_rank, world):
   alg_bytes = 4 * (E * H * W + E * R * h * h + E * R * P)
   roofline = {
     'bound': 'fp32-alu',
-    'kernel': 'score_fused_kernel<17,16>' if fused else 'maxplus_staged_kernel<17,16,paired>',
+    'kernel': 'score_fused_kernel<17,16>' if fused else 'maxplus_stream_kernel<17,16>',
     'kernel_ms': maxplus_ms,
     'share_of_step': maxplus_ms / ms_per_step,
     'achieved': 2 * cells / kernel_s / 1e12,
     'peak': 2 * peak_cells / 1e12,
     'unit': 'Tops/s',
     'frac': (cells / kernel_s) / peak_cells,
-    'traffic': ncu_traffic('score_fused_kernel' if fused else 'maxplus_staged_kernel'),
+    'traffic': ncu_traffic('score_fused_kernel' if fused else 'maxplus_stream_kernel'),
     'peak_source': 'srl_microbench_addmax, best (add,max) issue rate measured in this run '
                    '(FADD+FMNMX {:.3g}, FADD2+FMNMX3 {:.3g}, FADD2+VIMNMX3 {:.3g} cells/s); '
                    'MEASURED_PEAKS.json has no non-tensor FP32 figure'.format(
@@ -463,8 +463,8 @@ def run_graft(args, rank, local_rank, world):
                    'observations -> actions'},
     'gpu_launches': (1 if fused else 2 if masked else 3) * args.steps,
     'kernels_per_step': ['score_fused_kernel'] if fused else
-    ['maxplus_staged_kernel', 'mask_select_kernel'] if masked else
-    ['maxplus_staged_kernel', 'goal_overlap_kernel', 'select_kernel'],
+    ['maxplus_stream_kernel', 'mask_select_packed_kernel'] if masked else
+    ['maxplus_stream_kernel', 'goal_overlap_kernel', 'select_kernel'],
     'roofline': roofline,
   }
   if world == 1 and not args.no_extra:
@@ -473,7 +473,7 @@ def run_graft(args, rank, local_rank, world):
     except Exception as exc:   # the headline must survive a failure of the extras
       line['extra'] = {'error': repr(exc)}
   if world == 1 and not args.no_cpu_baseline:
-    maps = 1024
+    maps = 8192
     v, wall = cpu_baseline_one_core(maps)
     line['cpu_baseline'] = {
       'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',

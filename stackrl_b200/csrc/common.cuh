@@ -110,6 +110,29 @@ __device__ __forceinline__ int ld_acquire_shared(const int* p) {
   return v;
 }
 
+// One try_wait with a suspend-time hint (ns): the warp is parked by the hardware
+// until the phase completes or the hint expires.  Returns true when the phase
+// with the given parity has completed.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t phase,
+                                                   uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(phase), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// Blocking wait that parks the warp instead of spinning.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t phase) {
+  while (!mbar_try_wait_hint(bar, phase, 1000000u)) {
+  }
+}
+
 // global -> shared::cta bulk copy; bytes % 16 == 0, both addresses 16-B aligned.
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem,
                                             uint32_t bytes, uint64_t* bar) {

@@ -215,7 +215,91 @@ maxplus_staged_kernel(const MaxPlusParams p) {
 // than one mbarrier phase away, and `ready` carries the environment number
 // itself, so a consumer that runs far ahead cannot mistake an older tenant.
 // --------------------------------------------------------------------------- //
-constexpr int kConsumers = 16, kProducers = 4, kRawDepth = 2;
+#ifndef SRL_CONSUMERS
+#define SRL_CONSUMERS 16
+#endif
+constexpr int kConsumers = SRL_CONSUMERS, kProducers = 4, kRawDepth = 2;
+
+// Producer-side conversion of one environment, raw -> compute layout, by the
+// kProducerThreads threads of the producer group (thread index pt).  Returns the
+// OR of the bit patterns of every value that takes part in a sum (sign bit set
+// <=> some value is negative: the integer-max sweep is not usable then).
+template <int MODE>
+__device__ __forceinline__ float scale_level(float x, float lv, float inv) {
+  if constexpr (MODE == 0) return x;
+  else if constexpr (MODE == 1) return __fmul_rn(x, inv);
+  else return div_level(x, lv);
+}
+template <int MODE>
+__device__ __forceinline__ uint32_t convert_env(const MaxPlusParams& p, const float* raw,
+                                                float* wall_s, float* rock_s,
+                                                float* rock_sh, int* flags, float lv,
+                                                float inv, int pt) {
+  const int H = p.H, W = p.W, h = p.h, hp = p.hp, Ws = p.Ws, R = p.R;
+  const uint32_t W4 = W / 4, h4 = h / 4;
+  const int lane = pt & 31;
+  uint32_t neg = 0;
+  const uint32_t nw = (uint32_t)H * W4;
+#pragma unroll 2
+  for (uint32_t q = pt; q < nw; q += (kProducers * 32)) {
+    uint32_t row, c4;
+    fdivmod(q, p.dW4, row, c4);
+    float4 x = lds128(raw + 4 * q);
+    x.x = scale_level<MODE>(x.x, lv, inv);
+    x.y = scale_level<MODE>(x.y, lv, inv);
+    x.z = scale_level<MODE>(x.z, lv, inv);
+    x.w = scale_level<MODE>(x.w, lv, inv);
+    neg |= __float_as_uint(x.x) | __float_as_uint(x.y) | __float_as_uint(x.z) |
+           __float_as_uint(x.w);
+    *reinterpret_cast<float4*>(wall_s + row * Ws + 4 * c4) = x;
+  }
+  // Live rock values are > threshold: they can only be negative when the
+  // threshold is.
+  const bool rock_sign = p.threshold < 0.f;
+  const float thr = p.threshold;
+  const float* rraw = raw + H * W;
+  const uint32_t nr = (uint32_t)R * h * h4;
+  // The trip count is the same for all lanes of a warp (the tail is handled by
+  // clamping q), so the shuffle below is always executed by full warps.
+  for (uint32_t q0 = pt - lane; q0 < nr; q0 += (kProducers * 32)) {
+    const uint32_t q = q0 + lane;
+    const bool in = q < nr;
+    const uint32_t qq = in ? q : nr - 1;
+    uint32_t rrow, c4, slot, u;
+    fdivmod(qq, p.dh4, rrow, c4);
+    fdivmod(rrow, p.dh, slot, u);
+    float4 x = lds128(rraw + 4 * qq);
+    x.x = scale_level<MODE>(x.x, lv, inv);
+    x.y = scale_level<MODE>(x.y, lv, inv);
+    x.z = scale_level<MODE>(x.z, lv, inv);
+    x.w = scale_level<MODE>(x.w, lv, inv);
+    const bool lx = x.x > thr, ly = x.y > thr, lz = x.z > thr, lw = x.w > thr;
+    x.x = lx ? x.x : kNegInf;
+    x.y = ly ? x.y : kNegInf;
+    x.z = lz ? x.z : kNegInf;
+    x.w = lw ? x.w : kNegInf;
+    if (in && !(lx && ly && lz && lw)) flags[slot] = 1;
+    if (rock_sign)   // -inf marks a masked cell, not a negative value
+      neg |= (lx ? __float_as_uint(x.x) : 0u) | (ly ? __float_as_uint(x.y) : 0u) |
+             (lz ? __float_as_uint(x.z) : 0u) | (lw ? __float_as_uint(x.w) : 0u);
+    // Shifted copy: sh[c] = n[c + 1]; the first value of the next float4 of the
+    // same rock row sits in the next lane (or is fetched directly by lane 31).
+    float nx = __shfl_down_sync(0xffffffffu, x.x, 1);
+    if (c4 == h4 - 1) {
+      nx = kNegInf;
+    } else if (lane == 31) {
+      nx = scale_level<MODE>(rraw[4 * qq + 4], lv, inv);
+      nx = nx > thr ? nx : kNegInf;
+    }
+    if (in) {
+      const uint32_t off = slot * p.rock_stride + u * hp + 4 * c4;
+      *reinterpret_cast<float4*>(rock_s + off) = x;
+      *reinterpret_cast<float4*>(rock_sh + off) = make_float4(x.y, x.z, x.w, nx);
+    }
+  }
+  return neg;
+}
+
 constexpr int kStreamThreads = (kConsumers + kProducers) * 32;
 constexpr int kProducerThreads = kProducers * 32;
 
@@ -229,11 +313,12 @@ maxplus_stream_kernel(const MaxPlusParams p) {
 
   // ---- shared memory carve-up ---------------------------------------------- //
   uint64_t* empty = reinterpret_cast<uint64_t*>(smem_raw);         // [nslot]
-  uint64_t* rawbar = empty + nslot;                                // [kRawDepth]
+  uint64_t* full = empty + nslot;                                  // [nslot]
+  uint64_t* rawbar = full + nslot;                                 // [kRawDepth]
   int* ready = reinterpret_cast<int*>(rawbar + kRawDepth);         // [nslot]
   int* negative = ready + nslot;                                   // [nslot]
   int* masked = negative + nslot;                                  // [nslot][R]
-  const int head = round_up((nslot + kRawDepth) * 8 + (2 * nslot + nslot * R) * 4, 16);
+  const int head = round_up((2 * nslot + kRawDepth) * 8 + (2 * nslot + nslot * R) * 4, 16);
   const int raw_floats = H * W + R * h * h;
   const int env_floats = p.wall_stride + 2 * R * p.rock_stride;
   float* raw = reinterpret_cast<float*>(smem_raw + head);          // [kRawDepth][raw]
@@ -252,17 +337,38 @@ maxplus_stream_kernel(const MaxPlusParams p) {
   const long long base = (long long)env_first * ipe;   // stream position of local 0
 
   if (tid == 0) {
-    for (int s = 0; s < nslot; ++s) mbar_init(empty + s, ipe);
+    for (int s = 0; s < nslot; ++s) {
+      mbar_init(empty + s, ipe);
+      mbar_init(full + s, 1);
+    }
     for (int k = 0; k < kRawDepth; ++k) mbar_init(rawbar + k, 1);
     fence_barrier_init();
   }
   for (int k = tid; k < nslot; k += kStreamThreads) ready[k] = 0;
   // One-time fills of what the producers never rewrite: wall pad columns
-  // [W, Ws) (finite), rock pad columns and the last column of the shifted copy
-  // (-inf: never win, never count as masked).
-  for (int k = tid; k < nslot * env_floats; k += kStreamThreads) {
-    const int q = k % env_floats;
-    ring[k] = q < p.wall_stride ? 0.f : kNegInf;
+  // [W, Ws) (finite) and, in both rock copies, the pad columns [h, hp) and the 4
+  // floats behind each rock (-inf: never win, never count as masked).
+  {
+    const int padw = Ws - W, padr = hp - h;
+    for (int k = tid; k < nslot * H * padw; k += kStreamThreads) {
+      const int row = k / padw, c = k - row * padw;
+      const int s = row / H, r = row - s * H;
+      ring[(size_t)s * env_floats + r * Ws + W + c] = 0.f;
+    }
+    for (int k = tid; k < nslot * 2 * R * 4; k += kStreamThreads) {
+      const int rk = k >> 2, s = rk / (2 * R), r = rk - s * 2 * R;
+      ring[(size_t)s * env_floats + p.wall_stride + r * p.rock_stride + h * hp + (k & 3)] =
+          kNegInf;
+    }
+    if (padr > 0) {
+      for (int k = tid; k < nslot * 2 * R * h * padr; k += kStreamThreads) {
+        const int row = k / padr, c = k - row * padr;
+        const int rk = row / h, u = row - rk * h;
+        const int s = rk / (2 * R), r = rk - s * 2 * R;
+        ring[(size_t)s * env_floats + p.wall_stride + r * p.rock_stride + u * hp + h + c] =
+            kNegInf;
+      }
+    }
   }
   __syncthreads();
 
@@ -292,50 +398,21 @@ maxplus_stream_kernel(const MaxPlusParams p) {
       int* flags = masked + s * R;
       const float lv = scaled ? __ldg(p.level + env_first + k) : 1.f;
       const float inv = scaled ? pow2_inverse(lv) : 0.f;
-      if (use > 0) mbar_wait(empty + s, (use - 1) & 1);   // slot drained
+      if (use > 0) mbar_wait_parked(empty + s, (use - 1) & 1);   // slot drained
       for (int r = pt; r < R; r += kProducerThreads) flags[r] = 0;
       if (pt == 0) negative[s] = 0;
-      mbar_wait(rawbar + (k % kRawDepth), (k / kRawDepth) & 1);   // raw data landed
+      mbar_wait_parked(rawbar + (k % kRawDepth), (k / kRawDepth) & 1);   // raw data landed
       named_bar_sync(1, kProducerThreads);
-      uint32_t neg = 0;
-      for (uint32_t q = pt; q < (uint32_t)(H * W4); q += kProducerThreads) {
-        uint32_t row, c4;
-        fdivmod(q, p.dW4, row, c4);
-        float4 x = lds128(myraw + 4 * q);
-        if (scaled) {
-          x.x = div_level(x.x, lv, inv);
-          x.y = div_level(x.y, lv, inv);
-          x.z = div_level(x.z, lv, inv);
-          x.w = div_level(x.w, lv, inv);
-        }
-        neg |= __float_as_uint(x.x) | __float_as_uint(x.y) | __float_as_uint(x.z) |
-               __float_as_uint(x.w);
-        *reinterpret_cast<float4*>(wall_s + row * Ws + 4 * c4) = x;
-      }
-      for (uint32_t q = pt; q < (uint32_t)(R * h * h4); q += kProducerThreads) {
-        uint32_t rrow, c4, slot, u;
-        fdivmod(q, p.dh4, rrow, c4);
-        fdivmod(rrow, p.dh, slot, u);
-        float4 x = lds128(myraw + H * W + 4 * q);
-        bool dead = false;
-        x.x = prep_rock(x.x, scaled, lv, inv, p.threshold, dead);
-        x.y = prep_rock(x.y, scaled, lv, inv, p.threshold, dead);
-        x.z = prep_rock(x.z, scaled, lv, inv, p.threshold, dead);
-        x.w = prep_rock(x.w, scaled, lv, inv, p.threshold, dead);
-        if (dead) flags[slot] = 1;
-        // sign bits of the live values (-inf marks a masked cell, not a negative)
-        neg |= (x.x == kNegInf ? 0u : __float_as_uint(x.x)) |
-               (x.y == kNegInf ? 0u : __float_as_uint(x.y)) |
-               (x.z == kNegInf ? 0u : __float_as_uint(x.z)) |
-               (x.w == kNegInf ? 0u : __float_as_uint(x.w));
-        float* dst = rock_s + slot * p.rock_stride + u * hp + 4 * c4;
-        *reinterpret_cast<float4*>(dst) = x;
-        float* sh = rock_sh + slot * p.rock_stride + u * hp + 4 * c4;
-        if (c4 != 0) sh[-1] = x.x;
-        sh[0] = x.y;
-        sh[1] = x.z;
-        sh[2] = x.w;
-      }
+      // Scale mode is uniform per environment: 0 none, 1 exact multiply by the
+      // inverse of a power-of-two level, 2 IEEE division.
+      const int mode = !scaled ? 0 : (inv != 0.f ? 1 : 2);
+      uint32_t neg;
+      if (mode == 0)
+        neg = convert_env<0>(p, myraw, wall_s, rock_s, rock_sh, flags, lv, inv, pt);
+      else if (mode == 1)
+        neg = convert_env<1>(p, myraw, wall_s, rock_s, rock_sh, flags, lv, inv, pt);
+      else
+        neg = convert_env<2>(p, myraw, wall_s, rock_s, rock_sh, flags, lv, inv, pt);
       if ((neg >> 31) != 0u) negative[s] = 1;
       named_bar_sync(1, kProducerThreads);   // slot written, raw buffer read
       if (pt == 0) {
@@ -344,6 +421,7 @@ maxplus_stream_kernel(const MaxPlusParams p) {
           issue(k + kRawDepth);
         }
         st_release_shared(ready + s, k + 1);
+        mbar_arrive(full + s);
         // Items of a boundary environment that belong to a neighbouring CTA.
         uint32_t missing = 0;
         if (k == 0) missing += (uint32_t)(it0 - base);
@@ -355,9 +433,10 @@ maxplus_stream_kernel(const MaxPlusParams p) {
   }
 
   // ============================= consumer warp ================================ //
-  float* mystage = stage + warp * (32 * T);
+  const int cw = warp;                            // consumer index
+  float* mystage = stage + cw * (32 * T);
   const bool out_aligned = (((uintptr_t)p.out) & 15) == 0;
-  for (long long q = u0 + warp; q < u1; q += kConsumers) {
+  for (long long q = u0 + cw; q < u1; q += kConsumers) {
     const long long pos0 = q * 32;
     const int nvalid = (int)min((long long)32, it1 - pos0);
     const bool valid = lane < nvalid;
@@ -374,8 +453,13 @@ maxplus_stream_kernel(const MaxPlusParams p) {
       const uint32_t k_lo = __shfl_sync(0xffffffffu, k, 0);
       const uint32_t k_hi = __shfl_sync(0xffffffffu, k, 31);
       for (uint32_t kk = k_lo; kk <= k_hi; ++kk) {
-        const uint32_t ss = kk - fdiv(kk, p.dNslot) * (uint32_t)nslot;
-        while (ld_acquire_shared(ready + ss) != (int)kk + 1) __nanosleep(32);
+        uint32_t uu, ss;
+        fdivmod(kk, p.dNslot, uu, ss);
+        // `ready` decides; the mbarrier only parks the warp while it waits.  (Its
+        // parity alone cannot tell tenant k from tenant k - 2 * nslot.)
+        while (ld_acquire_shared(ready + ss) != (int)kk + 1) {
+          if (mbar_try_wait_hint(full + ss, uu & 1, 100000u)) __nanosleep(200);
+        }
       }
       __syncwarp();
     }
@@ -678,12 +762,16 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
     const size_t env_b = wall_bytes + (size_t)R * rock_bytes;
     const size_t stage_b = (size_t)kConsumers * 32 * T1 * 4;
     auto stream_smem = [&](int ns) {
-      return (size_t)round_up((ns + kRawDepth) * 8 + (2 * ns + ns * R) * 4, 16) +
+      return (size_t)round_up((2 * ns + kRawDepth) * 8 + (2 * ns + ns * R) * 4, 16) +
              kRawDepth * raw_b + ns * env_b + stage_b;
     };
     const size_t kStreamMax = 227 * 1024;
     int ns = 0;
     while (ns < 24 && stream_smem(ns + 1) <= kStreamMax) ++ns;
+    if (const char* sn = getenv("SRL_MP_NSLOT")) {   // tuning override
+      const int v = atoi(sn);
+      if (v >= 3 && v < ns) ns = v;
+    }
     int mode = 2;
     if (const char* sm = getenv("SRL_MP_MODE")) mode = atoi(sm);
     const int blocks_s = p.units < sms ? p.units : sms;

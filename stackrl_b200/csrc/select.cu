@@ -211,7 +211,22 @@ struct MaskSelectParams {
   int nW, pf, hb, ng;          // words per bit row (+1 zero word); row packing
   double overlap_threshold;
   uint32_t mulPw;              // ceil(2^32 / Pw) for k / Pw (k * Pw < 2^32)
+  int vec4;                    // packed kernel: bit images straight from 4-wide global loads
+  uint32_t mulW4, mulh4, mulhh4;   // ceil(2^32 / d) for d = W/4, h/4, h*h/4
 };
+
+// Four consecutive observation values (one 16-B or 4-B load).
+__device__ __forceinline__ void load4(const float* p, float (&x)[4]) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+}
+__device__ __forceinline__ void load4(const uint8_t* p, uint8_t (&x)[4]) {
+  const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(p));
+  x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+}
+__device__ __forceinline__ uint32_t udiv_mul(uint32_t k, uint32_t mul) {
+  return mul == 0u ? k : __umulhi(k, mul);
+}
 
 // Arg-min candidate in the score type itself (float compares are exact; only
 // the returned value map is float64).
@@ -522,6 +537,41 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
   const int e = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t hmask = h >= 32 ? 0xffffffffu : ((1u << h) - 1u);
+  // pf (rows packed per word) is 1, 2 or 4: shifts and masks, no divisions
+  const int lp = q.pf == 4 ? 2 : (q.pf == 2 ? 1 : 0);
+  if (q.vec4) {
+    // ---- bit images straight from global memory (baselines.py:153-154) --------- //
+    // Every thread turns 4 consecutive pixels into 4 bits and ORs them into the
+    // packed word; only the score maps are staged in shared memory.
+    for (int k = tid; k < H * q.nW + R * q.ng; k += kSelThreads) below[k] = 0u;
+    stage_bytes(vals, values + (size_t)e * R * P, (size_t)R * P * sizeof(V), tid,
+                kSelThreads);
+    if (tid < 32) s_cmax[tid] = 0;
+    __syncthreads();
+    const In* wsrc = walls + (size_t)e * H * W;
+    const In* gsrc = goals + (size_t)e * H * W;
+    for (uint32_t k = tid; k < (uint32_t)(H * W) / 4; k += kSelThreads) {
+      In a[4], b[4];
+      load4(wsrc + 4 * k, a);
+      load4(gsrc + 4 * k, b);
+      const uint32_t bits = (a[0] < b[0] ? 1u : 0u) | (a[1] < b[1] ? 2u : 0u) |
+                            (a[2] < b[2] ? 4u : 0u) | (a[3] < b[3] ? 8u : 0u);
+      const uint32_t row = udiv_mul(k, q.mulW4), col = 4 * (k - row * (W / 4));
+      if (bits) atomicOr(below + row * q.nW + (col >> 5), bits << (col & 31));
+    }
+    const In* rsrc = rocks + (size_t)e * R * h * h;
+    for (uint32_t k = tid; k < (uint32_t)(R * h * h) / 4; k += kSelThreads) {
+      In a[4];
+      load4(rsrc + 4 * k, a);
+      const uint32_t bits = (a[0] > In(0) ? 1u : 0u) | (a[1] > In(0) ? 2u : 0u) |
+                            (a[2] > In(0) ? 4u : 0u) | (a[3] > In(0) ? 8u : 0u);
+      const uint32_t rr = udiv_mul(k, q.mulhh4), rem = k - rr * (h * h / 4);
+      const uint32_t u = udiv_mul(rem, q.mulh4), col = 4 * (rem - u * (h / 4));
+      const uint32_t sub = u & (q.pf - 1);
+      if (bits) atomicOr(foot + rr * q.ng + (u >> lp), bits << (sub * q.hb + col));
+    }
+    __syncthreads();
+  } else {
   stage_bytes(vals, values + (size_t)e * R * P, (size_t)R * P * sizeof(V), tid, kSelThreads);
   stage_bytes(wall, walls + (size_t)e * H * W, (size_t)H * W * sizeof(In), tid, kSelThreads);
   stage_bytes(goal, goals + (size_t)e * H * W, (size_t)H * W * sizeof(In), tid, kSelThreads);
@@ -540,8 +590,6 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
       if (lane == 0) below[row * q.nW + word] = bits;
     }
   }
-  // pf (rows packed per word) is 1, 2 or 4: shifts and masks, no divisions
-  const int lp = q.pf == 4 ? 2 : (q.pf == 2 ? 1 : 0);
   for (int r = warp; r < R; r += NW) {
     const In* rk = rock + (size_t)r * h * h;
     uint32_t packed = 0;
@@ -556,6 +604,7 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
     }
   }
   __syncthreads();
+  }
   for (int k = tid; k < H * Pw; k += kSelThreads) {
     const int row = __umulhi((uint32_t)k, q.mulPw), j = k - row * Pw;
     uint32_t packed = 0;
@@ -712,8 +761,15 @@ int launch_mask_select(const V* values, const In* walls, const In* goals, const 
                                         q);                                                \
   } while (0)
   const bool pow2 = R <= 32 && (R & (R - 1)) == 0;
-  const size_t packed_smem = 4 * ((size_t)H * q.nW + (size_t)R * q.ng + (size_t)H * q.Pw) +
-                             2 * (size_t)R * P + staged;
+  auto mulc = [](uint32_t d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); };
+  const size_t al = sizeof(In) * 4;
+  q.vec4 = W % 4 == 0 && h % 4 == 0 && ((uintptr_t)walls % al) == 0 &&
+           ((uintptr_t)goals % al) == 0 && ((uintptr_t)rocks % al) == 0 &&
+           (size_t)R * h * h * (h * h / 4) < (1ull << 32);
+  q.mulW4 = mulc(W / 4); q.mulh4 = mulc(h / 4); q.mulhh4 = mulc(h * h / 4);
+  const size_t packed_smem =
+      4 * ((size_t)H * q.nW + (size_t)R * q.ng + (size_t)H * q.Pw) + 2 * (size_t)R * P +
+      (q.vec4 ? 16 + pad16((size_t)R * P * sizeof(V)) : staged);
   if (pow2 && packed_smem <= 110 * 1024 && minorder <= 1) {     // >= 2 CTAs per SM
 #define SRL_MSP_LAUNCH(MM, NGG)                                                            \
   do {                                                                                     \
