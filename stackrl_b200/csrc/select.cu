@@ -504,7 +504,9 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
 // two <= 32) consecutive lanes share one window word and each keeps the packed
 // footprint of ITS view in registers, so an overlap step is LDS + LOP3 + POPC +
 // IADD with no footprint traffic, and all eight warps work on all views at once.
-template <typename V, typename In, int M, int NG>
+// GEO = (H << 20 | W << 10 | h) << 6 | R fixes the geometry at compile time (0:
+// run-time geometry from the parameters): all index arithmetic folds.
+template <typename V, typename In, int M, int NG, long long GEO = 0>
 __global__ void __launch_bounds__(kSelThreads)
 mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ walls,
                           const In* __restrict__ goals, const In* __restrict__ rocks,
@@ -519,10 +521,18 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
   __shared__ V s_pick[32];
   __shared__ int s_pick_i[32];
   __shared__ double s_fill[32];
-  const int R = q.R, H = q.H, W = q.W, h = q.h, Ph = q.Ph, Pw = q.Pw, P = Ph * Pw;
+  constexpr bool kFixed = GEO != 0;
+  const int R = kFixed ? (int)(GEO & 63) : q.R, H = kFixed ? (int)(GEO >> 26) : q.H;
+  const int W = kFixed ? (int)((GEO >> 16) & 1023) : q.W;
+  const int h = kFixed ? (int)((GEO >> 6) & 1023) : q.h;
+  const int Ph = H - h + 1, Pw = W - h + 1, P = Ph * Pw;
+  const int g_nW = kFixed ? (W + 31) / 32 + 1 : q.nW;
+  const int g_pf = kFixed ? (h > 16 ? 1 : (h > 8 ? 2 : 4)) : q.pf;
+  const int g_hb = kFixed ? 32 / g_pf : q.hb;
+  const int g_ng = kFixed ? (h + g_pf - 1) / g_pf : q.ng;
   uint32_t* below = reinterpret_cast<uint32_t*>(sel_smem);          // [H][nW]
-  uint32_t* foot = below + H * q.nW;                                // [R][ng] row-packed
-  uint32_t* win = foot + R * q.ng;                                  // [H][Pw] row-packed
+  uint32_t* foot = below + H * g_nW;                                // [R][ng] row-packed
+  uint32_t* win = foot + R * g_ng;                                  // [H][Pw] row-packed
   uint16_t* cnt = reinterpret_cast<uint16_t*>(win + H * Pw);        // [R][P]
   unsigned char* at = reinterpret_cast<unsigned char*>(cnt + (size_t)R * P);
   at += (16 - (reinterpret_cast<uintptr_t>(at) & 15)) & 15;
@@ -538,12 +548,12 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t hmask = h >= 32 ? 0xffffffffu : ((1u << h) - 1u);
   // pf (rows packed per word) is 1, 2 or 4: shifts and masks, no divisions
-  const int lp = q.pf == 4 ? 2 : (q.pf == 2 ? 1 : 0);
-  if (q.vec4) {
+  const int lp = g_pf == 4 ? 2 : (g_pf == 2 ? 1 : 0);
+  if (kFixed || q.vec4) {
     // ---- bit images straight from global memory (baselines.py:153-154) --------- //
     // Every thread turns 4 consecutive pixels into 4 bits and ORs them into the
     // packed word; only the score maps are staged in shared memory.
-    for (int k = tid; k < H * q.nW + R * q.ng; k += kSelThreads) below[k] = 0u;
+    for (int k = tid; k < H * g_nW + R * g_ng; k += kSelThreads) below[k] = 0u;
     stage_bytes(vals, values + (size_t)e * R * P, (size_t)R * P * sizeof(V), tid,
                 kSelThreads);
     if (tid < 32) s_cmax[tid] = 0;
@@ -556,8 +566,8 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
       load4(gsrc + 4 * k, b);
       const uint32_t bits = (a[0] < b[0] ? 1u : 0u) | (a[1] < b[1] ? 2u : 0u) |
                             (a[2] < b[2] ? 4u : 0u) | (a[3] < b[3] ? 8u : 0u);
-      const uint32_t row = udiv_mul(k, q.mulW4), col = 4 * (k - row * (W / 4));
-      if (bits) atomicOr(below + row * q.nW + (col >> 5), bits << (col & 31));
+      const uint32_t row = kFixed ? k / (uint32_t)(W / 4) : udiv_mul(k, q.mulW4), col = 4 * (k - row * (W / 4));
+      if (bits) atomicOr(below + row * g_nW + (col >> 5), bits << (col & 31));
     }
     const In* rsrc = rocks + (size_t)e * R * h * h;
     for (uint32_t k = tid; k < (uint32_t)(R * h * h) / 4; k += kSelThreads) {
@@ -565,10 +575,10 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
       load4(rsrc + 4 * k, a);
       const uint32_t bits = (a[0] > In(0) ? 1u : 0u) | (a[1] > In(0) ? 2u : 0u) |
                             (a[2] > In(0) ? 4u : 0u) | (a[3] > In(0) ? 8u : 0u);
-      const uint32_t rr = udiv_mul(k, q.mulhh4), rem = k - rr * (h * h / 4);
-      const uint32_t u = udiv_mul(rem, q.mulh4), col = 4 * (rem - u * (h / 4));
-      const uint32_t sub = u & (q.pf - 1);
-      if (bits) atomicOr(foot + rr * q.ng + (u >> lp), bits << (sub * q.hb + col));
+      const uint32_t rr = kFixed ? k / (uint32_t)(h * h / 4) : udiv_mul(k, q.mulhh4), rem = k - rr * (h * h / 4);
+      const uint32_t u = kFixed ? rem / (uint32_t)(h / 4) : udiv_mul(rem, q.mulh4), col = 4 * (rem - u * (h / 4));
+      const uint32_t sub = u & (g_pf - 1);
+      if (bits) atomicOr(foot + rr * g_ng + (u >> lp), bits << (sub * g_hb + col));
     }
     __syncthreads();
   } else {
@@ -582,12 +592,12 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
 
   // ---- bit images of the raw observation (baselines.py:153-154) ---------------- //
   for (int row = warp; row < H; row += NW) {
-    for (int word = 0; word < q.nW; ++word) {
+    for (int word = 0; word < g_nW; ++word) {
       const int col = word * 32 + lane;
       bool b = false;
       if (col < W) b = wall[row * W + col] < goal[row * W + col];
       const uint32_t bits = __ballot_sync(0xffffffffu, b);
-      if (lane == 0) below[row * q.nW + word] = bits;
+      if (lane == 0) below[row * g_nW + word] = bits;
     }
   }
   for (int r = warp; r < R; r += NW) {
@@ -595,10 +605,10 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
     uint32_t packed = 0;
     for (int u = 0; u < h; ++u) {
       const uint32_t bits = __ballot_sync(0xffffffffu, lane < h && rk[u * h + lane] > In(0));
-      const int sub = u & (q.pf - 1);
-      packed |= (bits & hmask) << (sub * q.hb);
-      if (sub == q.pf - 1 || u == h - 1) {
-        if (lane == 0) foot[r * q.ng + (u >> lp)] = packed;
+      const int sub = u & (g_pf - 1);
+      packed |= (bits & hmask) << (sub * g_hb);
+      if (sub == g_pf - 1 || u == h - 1) {
+        if (lane == 0) foot[r * g_ng + (u >> lp)] = packed;
         packed = 0;
       }
     }
@@ -606,11 +616,11 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
   __syncthreads();
   }
   for (int k = tid; k < H * Pw; k += kSelThreads) {
-    const int row = __umulhi((uint32_t)k, q.mulPw), j = k - row * Pw;
+    const int row = kFixed ? k / Pw : (int)__umulhi((uint32_t)k, q.mulPw), j = k - row * Pw;
     uint32_t packed = 0;
-    for (int s = 0; s < q.pf && row + s < H; ++s) {
-      const uint32_t* b = below + (row + s) * q.nW + (j >> 5);
-      packed |= (__funnelshift_r(b[0], b[1], j & 31) & hmask) << (s * q.hb);
+    for (int s = 0; s < g_pf && row + s < H; ++s) {
+      const uint32_t* b = below + (row + s) * g_nW + (j >> 5);
+      packed |= (__funnelshift_r(b[0], b[1], j & 31) & hmask) << (s * g_hb);
     }
     win[k] = packed;
   }
@@ -621,7 +631,7 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
   const int ppw = 32 / R;                       // positions per warp iteration
   const int qpos = lane / R;
   const int step = NW * ppw;
-  const int gstride = q.pf * Pw;
+  const int gstride = g_pf * Pw;
   uint32_t f[NG > 0 ? NG : 1];
   if (NG > 0) {
 #pragma unroll
@@ -637,7 +647,7 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
 #pragma unroll
       for (int g = 0; g < NG; ++g) c += __popc(wp[g * gstride] & f[g]);
     } else {
-      for (int g = 0; g < q.ng; ++g) c += __popc(wp[g * gstride] & foot[r * q.ng + g]);
+      for (int g = 0; g < g_ng; ++g) c += __popc(wp[g * gstride] & foot[r * g_ng + g]);
     }
     mine[pos] = (uint16_t)c;
     cm = max(cm, c);
@@ -658,7 +668,7 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
     any = true;
     take(bmask, x, pos);
     if (M != 0) {
-      const int i = __umulhi((uint32_t)pos, q.mulPw), j = pos - i * Pw;
+      const int i = kFixed ? pos / Pw : (int)__umulhi((uint32_t)pos, q.mulPw), j = pos - i * Pw;
       if (local_min<V, M>(v, x, i, j, Ph, Pw, q.minorder)) take(bmin, x, pos);
     }
   }
@@ -779,6 +789,22 @@ int launch_mask_select(const V* values, const In* walls, const In* goals, const 
     k<<<E, kSelThreads, packed_smem, stream>>>(values, walls, goals, rocks, actions,       \
                                                shown, best, q);                            \
   } while (0)
+    // Reference geometries with every index folded at compile time.
+#define SRL_GEO(HH, WW, hh, RR) (((((long long)(HH) << 20) | ((WW) << 10) | (hh)) << 6) | (RR))
+#define SRL_MSP_FIXED(HH, WW, hh, RR, NGG)                                                 \
+  if (q.vec4 && minorder == 1 && H == HH && W == WW && h == hh && R == RR) {               \
+    auto k = mask_select_packed_kernel<V, In, 1, NGG, SRL_GEO(HH, WW, hh, RR)>;            \
+    SRL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                  (int)packed_smem));                                      \
+    k<<<E, kSelThreads, packed_smem, stream>>>(values, walls, goals, rocks, actions,       \
+                                               shown, best, q);                            \
+    return check_launch("mask_select_packed_kernel");                                      \
+  }
+    SRL_MSP_FIXED(32, 32, 16, 8, 8)
+    SRL_MSP_FIXED(64, 64, 16, 8, 8)
+    SRL_MSP_FIXED(64, 64, 16, 1, 8)
+#undef SRL_MSP_FIXED
+#undef SRL_GEO
     if (minorder == 0) {
       if (q.ng == 8) SRL_MSP_LAUNCH(0, 8);
       else if (q.ng == 32) SRL_MSP_LAUNCH(0, 32);
