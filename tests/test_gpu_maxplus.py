@@ -125,3 +125,58 @@ def test_empty_batch_and_bad_arguments(capi):
     capi.maxplus_f32(torch.zeros((1, 4, 4), device=dev),
                      torch.zeros((1, 1, 8, 8), device=dev),
                      out=torch.zeros((1, 1, 1, 1), device=dev))
+
+
+def _numpy_maps(walls, rocks, level, threshold=0.):
+  """Vectorised restatement of baselines.py:21-43 for planar batches (float32
+  division, float32 add, masked cells contribute 0)."""
+  E, R, h = rocks.shape[0], rocks.shape[1], rocks.shape[2]
+  out = []
+  for e in range(E):
+    o = walls[e] / level[e] if level is not None else walls[e]
+    win = np.lib.stride_tricks.sliding_window_view(o, (h, h))
+    maps = []
+    for r in range(R):
+      n = rocks[e, r] / level[e] if level is not None else rocks[e, r]
+      maps.append(np.where(n > np.float32(threshold), win + n, np.float32(0)).max(axis=(2, 3)))
+    out.append(maps)
+  return np.asarray(out, dtype='float32')
+
+
+@pytest.mark.parametrize('shape', [
+  (301, 1, 32, 32, 16),    # 17 items per environment: a warp pass spans 2-3 environments
+  (150, 3, 20, 20, 8),     # ring slots reused many times per CTA
+  (1200, 8, 32, 32, 16),   # CTA ranges that start and end inside an environment
+  (97, 2, 64, 64, 16),     # two strips per output row
+  (40, 8, 48, 48, 16),
+])
+def test_stream_kernel_item_stream(capi, monkeypatch, shape):
+  """maxplus_stream_kernel: the item stream is cut in 32-item units that ignore
+  environment boundaries; every cut must give the oracle's maps, and the same
+  bits as the barrier-synchronised staged kernel."""
+  E, R, H, W, h = shape
+  walls, rocks, level = synth.placement_batch(21, E, R, H, W, h)
+  level = (level * np.linspace(0.6, 1.4, E)).astype('float32')
+  dev = torch.device('cuda')
+  args = [torch.from_numpy(x).to(dev) for x in (walls, rocks, level)]
+  got = capi.maxplus_f32(*args)
+  pick = np.random.default_rng(1).choice(E, min(E, 48), replace=False)
+  want = _numpy_maps(walls[pick], rocks[pick], level[pick])
+  assert np.array_equal(got[torch.from_numpy(pick).to(dev)].cpu().numpy(), want)
+  monkeypatch.setenv('SRL_MP_MODE', '1')
+  assert torch.equal(got, capi.maxplus_f32(*args))
+
+
+def test_stream_kernel_negative_values(capi):
+  """Tiles with negative heights take the FMNMX3 sweep (the integer-max sweep
+  is only exact for non-negative operands); a batch mixes both kinds."""
+  E, R, H, W, h = 64, 8, 32, 32, 16
+  walls, rocks, level = synth.placement_batch(3, E, R, H, W, h)
+  rng = np.random.default_rng(9)
+  walls[::3] -= np.float32(0.2)                      # negative walls in every third env
+  rocks[1::4] -= rng.uniform(0, 0.05, rocks[1::4].shape).astype('float32')
+  dev = torch.device('cuda')
+  for thr in (0., -0.02):
+    got = capi.maxplus_f32(torch.from_numpy(walls).to(dev), torch.from_numpy(rocks).to(dev),
+                           torch.from_numpy(level).to(dev), threshold=thr).cpu().numpy()
+    assert np.array_equal(got, _numpy_maps(walls, rocks, level, thr))
