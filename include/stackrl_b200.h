@@ -155,6 +155,14 @@ SRL_API int srl_difference_f32(const float* walls, const float* rocks,
                        const float* level, const double* weights, double* out,
                        float* top, int E, int R, int H, int W, int h,
                        int difference_exponent, srl_stream_t stream);
+/* Same for uint8 observations: every step of baselines.py:64-69 is float64 then
+ * (uint8 / uint8 -> float64 in get_inputs); level [E] u8, top [E,R,P] f64 or NULL. */
+SRL_API int srl_difference_weights_u8(const uint8_t* rocks, double* weights, int E, int R,
+                                      int h, int weights_exponent, srl_stream_t stream);
+SRL_API int srl_difference_u8(const uint8_t* walls, const uint8_t* rocks,
+                              const uint8_t* level, const double* weights, double* out,
+                              double* top, int E, int R, int H, int W, int h,
+                              int difference_exponent, srl_stream_t stream);
 
 /* ---- a8: baselines.correlate / baselines.corrcoef (baselines.py:141-143, 79-85) --
  * corr = correlate2d(o, n, 'valid') / n.sum(); coef = TM_CCOEFF_NORMED(o, n), with
@@ -164,6 +172,17 @@ SRL_API int srl_difference_f32(const float* walls, const float* rocks,
 SRL_API int srl_correlate_f32(const float* walls, const float* rocks, const float* level,
                               float* corr, float* coef, int E, int R, int H, int W, int h,
                               srl_stream_t stream);
+
+/* corrcoef(localized=True) (baselines.py:87-114): the masked variant, every sum in
+ * numpy's pairwise order and in the observation's arithmetic type (float32, or
+ * float64 for uint8): bit-exact.  work: caller-owned scratch of
+ * E*R*(h*h + 2) elements of that type (4 or 8 bytes each); out [E,R,P] f64. */
+SRL_API int srl_corrcoef_localized_f32(const float* walls, const float* rocks,
+                                       const float* level, void* work, double* out, int E,
+                                       int R, int H, int W, int h, srl_stream_t stream);
+SRL_API int srl_corrcoef_localized_u8(const uint8_t* walls, const uint8_t* rocks,
+                                      const uint8_t* level, void* work, double* out, int E,
+                                      int R, int H, int W, int h, srl_stream_t stream);
 
 /* ---- a2/a3: Observer.__call__ rasterisation + depth->elevation
  *      (observer.py:252-260, 267-277; pybullet.getCameraImage) ----------------

@@ -86,30 +86,32 @@ def height(inputs, mask=None, **kwargs):
 def difference(inputs, mask=None, difference_exponent=2, weights_exponent=2,
                return_height=False, **kwargs):
   """Difference based heuristic: weighted residual between the rock's underside
-  and the wall at the drop height.  float64, bit-exact with the reference for
+  and the wall at the drop height (float32 or uint8 observations, the latter in
+  float64 throughout like numpy).  float64, bit-exact with the reference for
   ``difference_exponent`` in {1, 2} (numpy's float32 pow for other exponents is
   libm-defined and is refused rather than approximated)."""
   if difference_exponent not in (1, 2):
     raise ValueError('difference_exponent must be 1 or 2 for a bit-reproducible '
                      'result, got {}'.format(difference_exponent))
   walls, goals, rocks = _planes(inputs)
-  if walls.dtype != torch.float32:
-    raise TypeError('difference is wired for float32 observations')
+  if walls.dtype not in (torch.float32, torch.uint8):
+    raise TypeError('observations must be float32 or uint8, got {}'.format(walls.dtype))
+  u8 = walls.dtype == torch.uint8
   level = goals.amax(dim=(1, 2))
   if weights_exponent in (0, 2):
-    weights = capi.difference_weights(rocks, level, weights_exponent)
+    weights = capi.difference_weights(rocks, None if u8 else level, weights_exponent)
   else:
     # Any other exponent goes through numpy's own float64 pow on the host so the
     # weights keep the reference's bits (baselines.py:54-62).
-    n = (rocks[0, 0] / level[0]).cpu().numpy()
+    n = rocks[0, 0].cpu().numpy() if u8 else (rocks[0, 0] / level[0]).cpu().numpy()
     live = n > 0
     di = (np.arange(n.shape[0], dtype='float') - n.shape[0] / 2) ** 2
     dj = (np.arange(n.shape[1], dtype='float') - n.shape[1] / 2) ** 2
     w = np.where(live, (di[:, None] + dj[None, :]) ** (weights_exponent / 2), 0)
     w /= w.sum()
     weights = _upload(w[None, None])
-  f, top = capi.difference_f32(walls, rocks, level, weights, difference_exponent,
-                               want_top=return_height)
+  run = capi.difference_u8 if u8 else capi.difference_f32
+  f, top = run(walls, rocks, level, weights, difference_exponent, want_top=return_height)
   f = f[0, 0].cpu().numpy()
   if mask is not None:
     f = np.where(mask, f, 0.)
@@ -134,13 +136,17 @@ def correlate(inputs, **kwargs):
 
 # ---- baselines.py:79-114 ----------------------------------------------------- #
 def corrcoef(inputs, mask=None, localized=False, **kwargs):
-  """Correlation-coefficient heuristic (the reference's OpenCV
-  TM_CCOEFF_NORMED path, baselines.py:84-85).  float32, matched to ~1e-5
-  absolute.  ``localized=True`` (masked Python loop in the reference) is not
-  accelerated."""
-  if localized:
-    raise NotImplementedError('corrcoef(localized=True) has no GPU kernel')
+  """Correlation-coefficient heuristic.  Default: the reference's OpenCV
+  TM_CCOEFF_NORMED path (baselines.py:84-85), float32, matched to ~1e-5
+  absolute.  ``localized=True``: the masked variant (baselines.py:87-114),
+  float64 container, bit-exact (numpy's pairwise sums in the observation's
+  arithmetic type; float32 and uint8 observations)."""
   walls, goals, rocks = _planes(inputs)
+  if localized:
+    f = capi.corrcoef_localized(walls, rocks, goals.amax(dim=(1, 2)))[0, 0].cpu().numpy()
+    if mask is not None:
+      f = np.where(mask, f, 0.)
+    return f
   if walls.dtype != torch.float32:
     raise TypeError('corrcoef is wired for float32 observations')
   _, coef = capi.correlate_f32(walls, rocks, goals.amax(dim=(1, 2)), want_corr=False)

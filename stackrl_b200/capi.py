@@ -50,6 +50,10 @@ _SIGNATURES = {
   'srl_score_f32': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_difference_weights': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
   'srl_difference_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+  'srl_difference_weights_u8': (_I, [_P, _P, _I, _I, _I, _I, _P]),
+  'srl_difference_u8': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+  'srl_corrcoef_localized_f32': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+  'srl_corrcoef_localized_u8': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
   'srl_correlate_f32': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
   'srl_raster': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_reward_sums_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
@@ -195,9 +199,15 @@ def select(values, counts=None, minorder=1, overlap_threshold=0.75,
 
 
 def difference_weights(rocks, level=None, weights_exponent=2):
-  """rocks [E,R,h,h] float32 -> normalised radial weights [E,R,h,h] float64."""
+  """rocks [E,R,h,h] float32 or uint8 -> normalised radial weights [E,R,h,h] float64."""
   E, R, h, h2 = rocks.shape
   out = torch.empty((E, R, h, h), dtype=torch.float64, device=rocks.device)
+  if rocks.dtype == torch.uint8:
+    with torch.cuda.device(rocks.device):
+      _check(lib.srl_difference_weights_u8(_dev(rocks, torch.uint8, 'rocks'),
+                                           _dev(out, torch.float64, 'weights'),
+                                           E, R, h, int(weights_exponent), _stream()))
+    return out
   args = (_dev(rocks, torch.float32, 'rocks'), _opt(level, torch.float32, 'level'))
   with torch.cuda.device(rocks.device):
     _check(lib.srl_difference_weights(*args, _dev(out, torch.float64, 'weights'),
@@ -218,6 +228,37 @@ def difference_f32(walls, rocks, level, weights, difference_exponent=2, want_top
                                   _opt(top, torch.float32, 'top'), E, R, H, W, h,
                                   int(difference_exponent), _stream()))
   return out, top
+
+
+def difference_u8(walls, rocks, level, weights, difference_exponent=2, want_top=False):
+  """uint8 observations -> (f [E,R,Ph,Pw] float64, h0 [E,R,Ph,Pw] float64 | None)."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  args = (_dev(walls, torch.uint8, 'walls'), _dev(rocks, torch.uint8, 'rocks'),
+          _opt(level, torch.uint8, 'level'), _dev(weights, torch.float64, 'weights'))
+  shape = (E, R, H - h + 1, W - h + 1)
+  out = torch.empty(shape, dtype=torch.float64, device=walls.device)
+  top = torch.empty(shape, dtype=torch.float64, device=walls.device) if want_top else None
+  with torch.cuda.device(walls.device):
+    _check(lib.srl_difference_u8(*args, _dev(out, torch.float64, 'out'),
+                                 _opt(top, torch.float64, 'top'), E, R, H, W, h,
+                                 int(difference_exponent), _stream()))
+  return out, top
+
+
+def corrcoef_localized(walls, rocks, level=None):
+  """corrcoef(localized=True) for float32 or uint8 planes -> [E,R,Ph,Pw] float64."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  u8 = walls.dtype == torch.uint8
+  dt = torch.uint8 if u8 else torch.float32
+  cdt = torch.float64 if u8 else torch.float32
+  args = (_dev(walls, dt, 'walls'), _dev(rocks, dt, 'rocks'), _opt(level, dt, 'level'))
+  work = torch.empty((E * R * (h * h + 2),), dtype=cdt, device=walls.device)
+  out = torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.float64, device=walls.device)
+  fn = lib.srl_corrcoef_localized_u8 if u8 else lib.srl_corrcoef_localized_f32
+  with torch.cuda.device(walls.device):
+    _check(fn(*args, _dev(work, cdt, 'work'), _dev(out, torch.float64, 'out'),
+              E, R, H, W, h, _stream()))
+  return out
 
 
 # numpy mirrors of srl_raster_instance / srl_raster_job (include/stackrl_b200.h)

@@ -118,6 +118,33 @@ int srl_difference_f32(const float* walls, const float* rocks, const float* leve
                              difference_exponent, (cudaStream_t)stream);
 }
 
+int srl_difference_weights_u8(const uint8_t* rocks, double* weights, int E, int R, int h,
+                              int weights_exponent, srl_stream_t stream) {
+  return srl::difference_weights_u8(rocks, weights, E, R, h, weights_exponent,
+                                    (cudaStream_t)stream);
+}
+
+int srl_difference_u8(const uint8_t* walls, const uint8_t* rocks, const uint8_t* level,
+                      const double* weights, double* out, double* top, int E, int R, int H,
+                      int W, int h, int difference_exponent, srl_stream_t stream) {
+  return srl::difference_u8(walls, rocks, level, weights, out, top, E, R, H, W, h,
+                            difference_exponent, (cudaStream_t)stream);
+}
+
+int srl_corrcoef_localized_f32(const float* walls, const float* rocks, const float* level,
+                               void* work, double* out, int E, int R, int H, int W, int h,
+                               srl_stream_t stream) {
+  return srl::corrcoef_localized_f32(walls, rocks, level, work, out, E, R, H, W, h,
+                                     (cudaStream_t)stream);
+}
+
+int srl_corrcoef_localized_u8(const uint8_t* walls, const uint8_t* rocks,
+                              const uint8_t* level, void* work, double* out, int E, int R,
+                              int H, int W, int h, srl_stream_t stream) {
+  return srl::corrcoef_localized_u8(walls, rocks, level, work, out, E, R, H, W, h,
+                                    (cudaStream_t)stream);
+}
+
 int srl_raster(const float* verts, const int32_t* tris, const srl_raster_instance* insts,
                const srl_raster_job* jobs, float* out, int njobs, int rows, int cols,
                int mode, double far_plane, srl_stream_t stream) {

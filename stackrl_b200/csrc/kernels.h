@@ -51,6 +51,19 @@ int difference_f32(const float* walls, const float* rocks, const float* level,
                    const double* weights, double* out, float* top, int E, int R, int H,
                    int W, int h, int difference_exponent, cudaStream_t stream);
 
+int difference_weights_u8(const uint8_t* rocks, double* weights, int E, int R, int h,
+                          int weights_exponent, cudaStream_t stream);
+int difference_u8(const uint8_t* walls, const uint8_t* rocks, const uint8_t* level,
+                  const double* weights, double* out, double* top, int E, int R, int H,
+                  int W, int h, int difference_exponent, cudaStream_t stream);
+
+int corrcoef_localized_f32(const float* walls, const float* rocks, const float* level,
+                           void* work, double* out, int E, int R, int H, int W, int h,
+                           cudaStream_t stream);
+int corrcoef_localized_u8(const uint8_t* walls, const uint8_t* rocks, const uint8_t* level,
+                          void* work, double* out, int E, int R, int H, int W, int h,
+                          cudaStream_t stream);
+
 int raster(const float* verts, const int32_t* tris, const srl_raster_instance* insts,
            const srl_raster_job* jobs, float* out, int njobs, int rows, int cols, int mode,
            double far_plane, cudaStream_t stream);

@@ -79,6 +79,33 @@ def test_difference_bit_exact(B, scoring_golden, case):
                           scoring_golden[case + '/difference_d1'])
 
 
+@pytest.mark.parametrize('case', ['stackv0_u8', 'c5like_u8'])
+def test_difference_uint8_is_float64_exact(B, scoring_golden, case):
+  """uint8 observations: numpy runs baselines.py:64-69 in float64 throughout."""
+  obs = scoring_golden.obs(case)
+  d, h0 = B.difference(obs, return_height=True)
+  assert d.dtype == np.float64 and h0.dtype == np.float64
+  assert np.array_equal(h0, scoring_golden[case + '/difference_height'])
+  assert np.array_equal(d, scoring_golden[case + '/difference'])
+  if case + '/difference_w0' in scoring_golden:
+    assert np.array_equal(B.difference(obs, weights_exponent=0),
+                          scoring_golden[case + '/difference_w0'])
+    assert np.array_equal(B.difference(obs, difference_exponent=1),
+                          scoring_golden[case + '/difference_d1'])
+
+
+@pytest.mark.parametrize('case', ['c2like_f32', 'nonsquare_wall_f32', 'dense_rock_f32',
+                                  'ties_f32', 'flat_wall_f32', 'c4like_f32',
+                                  'full_rock_window_f32', 'stackv0_u8'])
+def test_corrcoef_localized_bit_exact(B, scoring_golden, case):
+  """The masked correlation coefficient (baselines.py:87-114): numpy pairwise
+  sums in float32 (float32 observations) or float64 (uint8 ones)."""
+  want = scoring_golden[case + '/corrcoef_localized']
+  got = B.corrcoef(scoring_golden.obs(case), localized=True)
+  assert got.dtype == want.dtype and got.shape == want.shape
+  assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize('side', [3, 5, 6, 10, 12, 20])
 def test_difference_pairwise_order_odd_sizes(B, side):
   """Rock sizes whose h*h is not a power of two exercise every branch of
