@@ -666,10 +666,18 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
     const V x = v[pos];
     vm = (!any || x > vm) ? x : vm;
     any = true;
-    take(bmask, x, pos);
-    if (M != 0) {
+    // Positions come in increasing order per lane, so only a strictly smaller
+    // value can replace a candidate: test that before the neighbourhood.
+    if (bmask.idx < 0 || x < bmask.v) {
+      bmask.v = x;
+      bmask.idx = pos;
+    }
+    if (M != 0 && (bmin.idx < 0 || x < bmin.v)) {
       const int i = kFixed ? pos / Pw : (int)__umulhi((uint32_t)pos, q.mulPw), j = pos - i * Pw;
-      if (local_min<V, M>(v, x, i, j, Ph, Pw, q.minorder)) take(bmin, x, pos);
+      if (local_min<V, M>(v, x, i, j, Ph, Pw, q.minorder)) {
+        bmin.v = x;
+        bmin.idx = pos;
+      }
     }
   }
   for (int o = R; o < 32; o <<= 1) {

@@ -159,3 +159,12 @@ def test_correlate_and_corrcoef_within_tolerance(B, scoring_golden, case):
   assert got.dtype == want.dtype and got.shape == want.shape
   np.testing.assert_allclose(got, want, rtol=0, atol=2e-5)
   assert set(B.methods) == {'random', 'correlate', 'height', 'difference', 'corrcoef'}
+
+
+def test_baseline_difference_uint8_actions(B, scoring_golden):
+  obs = scoring_golden.obs('stackv0_u8')
+  for goal, minorder in ((1, 0), (1, 1), (1, 2), (0, 1)):
+    key = 'stackv0_u8/select_difference_g{}_m{}'.format(goal, minorder)
+    a, v = B.Baseline(method='difference', goal=bool(goal), minorder=minorder, value=True)(obs)
+    assert a == int(scoring_golden[key + '/action'])
+    assert np.array_equal(v, scoring_golden[key + '/values'])
