@@ -305,7 +305,11 @@ def run_graft(args, rank, local_rank, world):
       best=torch.empty((E, 2), dtype=torch.int64, device=dev)))
   set_bytes = sum(t.numel() * t.element_size() for t in sets[0].values())
   lib, P_ = capi.lib, capi._P
-  stream = P_(torch.cuda.current_stream().cuda_stream)
+  main_stream = torch.cuda.current_stream()
+  stream = P_(main_stream.cuda_stream)
+  side_stream = torch.cuda.Stream(device=dev) if args.overlap else None
+  side = P_(side_stream.cuda_stream) if args.overlap else None
+  done_events = [torch.cuda.Event() for _ in range(NSETS)]
   mp_events = []
 
   fused = args.fused
@@ -326,12 +330,24 @@ def run_graft(args, rank, local_rank, world):
         b.record()
         mp_events.append((a, b))
       return
+    if args.overlap and k >= NSETS:
+      main_stream.wait_event(done_events[k % NSETS])   # set k's values are free again
     capi._check(lib.srl_maxplus_f32(
       P_(s['walls'].data_ptr()), P_(s['rocks'].data_ptr()), P_(s['level'].data_ptr()),
       P_(s['values'].data_ptr()), E, R, H, W, h, 0.0, stream))
     if timed:
       b.record()
       mp_events.append((a, b))
+    if masked and args.overlap:
+      ev = torch.cuda.Event()
+      ev.record(main_stream)
+      side_stream.wait_event(ev)
+      capi._check(lib.srl_mask_select_f32(
+        P_(s['values'].data_ptr()), P_(s['walls'].data_ptr()), P_(s['goals'].data_ptr()),
+        P_(s['rocks'].data_ptr()), P_(s['actions'].data_ptr()), P_(None),
+        P_(s['best'].data_ptr()), E, R, H, W, h, 1, 0.75, side))
+      done_events[k % NSETS].record(side_stream)
+      return
     if masked:
       capi._check(lib.srl_mask_select_f32(
         P_(s['values'].data_ptr()), P_(s['walls'].data_ptr()), P_(s['goals'].data_ptr()),
@@ -365,6 +381,8 @@ def run_graft(args, rank, local_rank, world):
   ev0.record()
   for k in range(args.steps):
     step(k, timed=True)
+  if side_stream is not None:
+    main_stream.wait_stream(side_stream)
   ev1.record()
   torch.cuda.synchronize()
   sampler.stop()
@@ -494,6 +512,9 @@ def main():
   ap.add_argument('--no-extra', action='store_true')
   ap.add_argument('--fused', action='store_true',
                   help='run the single fully fused kernel (srl_score_f32)')
+  ap.add_argument('--overlap', action='store_true',
+                  help='goal mask / arg-min kernel of step k on a second stream, '
+                       'concurrent with the max-plus kernel of step k+1')
   ap.add_argument('--separate', action='store_true',
                   help='run the three separate kernels instead of the fused one')
   args = ap.parse_args()

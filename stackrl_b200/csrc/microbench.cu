@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out
 
   float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const float magic = __int_as_float(never);
-  for (int it = 0; it < iters; ++it) {
+  for (int it = 0; it < (VARIANT >= 17 ? 0 : iters); ++it) {
 #pragma unroll
     for (int v = 0; v < kV; v += 2) {
 #pragma unroll
@@ -178,6 +178,28 @@ __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out
       }
     }
   }
+  // Variants 17/18: DPX fused integer add + max, 16x2 packed (two cells per
+  // instruction) and 32-bit (one cell per instruction).
+  if constexpr (VARIANT == 17 || VARIANT == 18) {
+    unsigned ia[kT], in_[kV];
+#pragma unroll
+    for (int t = 0; t < kT; ++t) ia[t] = __float_as_uint(acc[t]);
+#pragma unroll
+    for (int k = 0; k < kV; ++k) in_[k] = __float_as_uint(nv[k]) & 0x00ff00ffu;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int v = 0; v < kV; ++v) {
+#pragma unroll
+        for (int t = 0; t < kT; ++t) {
+          const int k1 = (t + 8) % kT;
+          if constexpr (VARIANT == 17) ia[t] = __viaddmax_s16x2(ia[k1], in_[v], ia[t]);
+          else ia[t] = (unsigned)__viaddmax_s32((int)ia[k1], (int)in_[v], (int)ia[t]);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < kT; ++t) acc[t] = __uint_as_float(ia[t]);
+  }
 done:
   float r = acc[0];
   if constexpr (VARIANT == 15 || VARIANT == 16) {
@@ -192,7 +214,7 @@ done:
 }  // namespace
 
 int microbench_addmax(int variant, int iters, double* host_cells_per_s) {
-  SRL_REQUIRE(host_cells_per_s != nullptr && iters > 0 && variant >= 0 && variant <= 16,
+  SRL_REQUIRE(host_cells_per_s != nullptr && iters > 0 && variant >= 0 && variant <= 18,
               SRL_E_INVALID, "microbench_addmax: bad arguments");
   const int sms = sm_count();
   SRL_REQUIRE(sms > 0, SRL_E_CUDA, "microbench_addmax: no device");
@@ -212,7 +234,7 @@ int microbench_addmax(int variant, int iters, double* host_cells_per_s) {
     switch (variant) {
 #define SRL_MB(V) case V: addmax_kernel<V><<<blocks, threads>>>(in, out, iters, 0x7fc12345); break;
       SRL_MB(0) SRL_MB(1) SRL_MB(2) SRL_MB(3) SRL_MB(4) SRL_MB(5) SRL_MB(6) SRL_MB(7)
-      SRL_MB(8) SRL_MB(9) SRL_MB(10) SRL_MB(11) SRL_MB(12) SRL_MB(13) SRL_MB(14) SRL_MB(15) SRL_MB(16)
+      SRL_MB(8) SRL_MB(9) SRL_MB(10) SRL_MB(11) SRL_MB(12) SRL_MB(13) SRL_MB(14) SRL_MB(15) SRL_MB(16) SRL_MB(17) SRL_MB(18)
 #undef SRL_MB
     }
     SRL_CUDA(cudaEventRecord(t1));
@@ -228,7 +250,8 @@ int microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   cudaFree(out);
   if (rc != SRL_OK) return rc;
   double cells = (double)blocks * threads * (double)iters * kT * kV;
-  if (variant == 6 || variant == 14) cells *= 0.5;   // one FADD2 per two (v, t) steps
+  if (variant == 6 || variant == 14) cells *= 0.5;
+  if (variant == 17) cells *= 2.0;   // two (add, max) cells per instruction   // one FADD2 per two (v, t) steps
   *host_cells_per_s = cells / (best_ms * 1e-3);
   return SRL_OK;
 }
