@@ -539,13 +539,24 @@ maxplus_direct_kernel(const MaxPlusParams p) {
 
   const int tid = threadIdx.x;
   const int nthreads = blockDim.x;
-  const int group = blockIdx.x / p.rchunks;
-  const int rchunk = blockIdx.x % p.rchunks;
+  // blockIdx = ((group * rchunks) + rchunk) * nbands + band.  Bands (p.nbands > 1
+  // only with one environment per CTA) cut the output rows so that a single
+  // observation still spreads over the chip.
+  const int bandi = blockIdx.x % p.nbands;
+  const int gc = blockIdx.x / p.nbands;
+  const int group = gc / p.rchunks;
+  const int rchunk = gc % p.rchunks;
+  const int i0 = bandi * p.band;                            // first output row
+  const int rows_out = min(p.band, p.Ph - i0);
+  const int Hb = rows_out + p.h - 1;                        // wall rows this CTA needs
   const int e0 = group * p.G;
   const int r0 = rchunk * p.RC;
   const int Gv = min(p.G, p.E - e0);
   const int RCv = min(p.RC, p.R - r0);
   const int H = p.H, W = p.W, h = p.h, hp = p.hp, Ws = p.Ws;
+  // Row r of environment el of the group: local row el * Hb + r, global row
+  // (e0 + el) * H + i0 + r.
+  const FastDiv dHb = {Hb == 1 ? 0u : (uint32_t)(((1ull << 32) + Hb - 1) / Hb), (uint32_t)Hb};
   const FastDiv dRCv = {RCv == 1 ? 0u : (uint32_t)(((1ull << 32) + RCv - 1) / RCv),
                         (uint32_t)RCv};
 
@@ -561,14 +572,18 @@ maxplus_direct_kernel(const MaxPlusParams p) {
   if (tid < 32 && any_tma) {
     if (tid == 0) {
       uint32_t bytes = 0;
-      if (p.tma_wall) bytes += (uint32_t)Gv * H * W * 4;
+      if (p.tma_wall) bytes += (uint32_t)Gv * Hb * W * 4;
       if (p.tma_rock) bytes += (uint32_t)Gv * RCv * h * h * 4;
       mbar_arrive_expect_tx(bar, bytes);
     }
     __syncwarp();
     if (p.tma_wall) {
-      for (int k = tid; k < Gv * H; k += 32)   // row k of the group: el*H + row
-        tma_load_1d(wall_s + k * Ws, p.walls + ((size_t)e0 * H + k) * W, W * 4, bar);
+      for (uint32_t k = tid; k < (uint32_t)(Gv * Hb); k += 32) {
+        uint32_t el, r;
+        fdivmod(k, dHb, el, r);
+        tma_load_1d(wall_s + (el * H + r) * Ws,
+                    p.walls + ((size_t)(e0 + el) * H + i0 + r) * W, W * 4, bar);
+      }
     }
     if (p.tma_rock) {
       for (uint32_t k = tid; k < (uint32_t)(Gv * RCv * h); k += 32) {
@@ -582,10 +597,12 @@ maxplus_direct_kernel(const MaxPlusParams p) {
     }
   }
   if (!p.tma_wall) {
-    for (uint32_t k = tid; k < (uint32_t)(Gv * H * W); k += nthreads) {
-      uint32_t row, c;
+    for (uint32_t k = tid; k < (uint32_t)(Gv * Hb * W); k += nthreads) {
+      uint32_t row, c, el, r;
       fdivmod(k, p.dW, row, c);
-      wall_s[row * Ws + c] = __ldg(p.walls + (size_t)e0 * H * W + k);
+      fdivmod(row, dHb, el, r);
+      wall_s[(el * H + r) * Ws + c] =
+          __ldg(p.walls + ((size_t)(e0 + el) * H + i0 + r) * W + c);
     }
   }
   if (!p.tma_rock) {
@@ -602,8 +619,10 @@ maxplus_direct_kernel(const MaxPlusParams p) {
   // shifted copy are written by the normalise pass below.)
   {
     const int padw = Ws - W;
-    for (int k = tid; k < Gv * H * padw; k += nthreads)
-      wall_s[(k / padw) * Ws + W + k % padw] = 0.f;
+    for (int k = tid; k < Gv * Hb * padw; k += nthreads) {
+      const int row = k / padw, el = row / Hb, r = row - el * Hb;
+      wall_s[(el * H + r) * Ws + W + k % padw] = 0.f;
+    }
   }
   if (any_tma) mbar_wait(bar, 0);
   __syncthreads();
@@ -611,11 +630,12 @@ maxplus_direct_kernel(const MaxPlusParams p) {
   // ---- normalise in place, fold the mask, build the shifted copy ------------- //
   const bool scaled = p.level != nullptr;
   if (scaled) {
-    for (uint32_t k = tid; k < (uint32_t)(Gv * H * W); k += nthreads) {
-      uint32_t row, c;
+    for (uint32_t k = tid; k < (uint32_t)(Gv * Hb * W); k += nthreads) {
+      uint32_t row, c, el, r;
       fdivmod(k, p.dW, row, c);
-      float* q = wall_s + row * Ws + c;
-      *q = div_level(*q, __ldg(p.level + e0 + fdiv(row, p.dH)));
+      fdivmod(row, dHb, el, r);
+      float* q = wall_s + (el * H + r) * Ws + c;
+      *q = div_level(*q, __ldg(p.level + e0 + el));
     }
   }
   for (uint32_t k = tid; k < (uint32_t)(Gv * RCv * h * hp); k += nthreads) {
@@ -643,10 +663,13 @@ maxplus_direct_kernel(const MaxPlusParams p) {
 
   // ---- sweep ------------------------------------------------------------------ //
   const int Ph = p.Ph, Pw = p.Pw;
-  const int items = Gv * RCv * p.strips * Ph;
+  // p.dPh divides by the band height (== Ph without banding); the last band may be
+  // shorter.
+  const int items = Gv * RCv * p.strips * p.band;
   for (int item = tid; item < items; item += nthreads) {
     uint32_t rest, i, strip, er, el, r;
     fdivmod((uint32_t)item, p.dPh, rest, i);
+    if ((int)i >= rows_out) continue;
     fdivmod(rest, p.dStrips, er, strip);
     fdivmod(er, dRCv, el, r);
     const int slot = el * p.RC + r;
@@ -656,7 +679,7 @@ maxplus_direct_kernel(const MaxPlusParams p) {
                               rock_sh + slot * p.rock_stride, h, hp, Ws);
     const bool floor0 = masked[slot] != 0;
     float* orow = p.out +
-                  (((size_t)(e0 + el) * p.R + r0 + r) * Ph + i) * (size_t)Pw +
+                  (((size_t)(e0 + el) * p.R + r0 + r) * Ph + i0 + i) * (size_t)Pw +
                   strip * S;
     // The last column of a strip is the first of the next one; only the last
     // strip stores it.
@@ -710,9 +733,21 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
   p.E = E; p.R = R; p.H = H; p.W = W; p.h = h;
   p.Ph = H - h + 1; p.Pw = W - h + 1;
   p.threshold = threshold;
+  p.band = p.Ph;
+  p.nbands = 1;
   const int P = p.Ph * p.Pw;
 
-  const Choice c = choose_tile(p.Pw, h);
+  const int sms = sm_count();
+  SRL_REQUIRE(sms > 0, SRL_E_CUDA, "maxplus_f32: no CUDA device");
+  Choice c = choose_tile(p.Pw, h);
+  // Latency-bound calls (one observation, a handful of maps): far fewer items
+  // than lanes on the chip, so take the narrowest tile -- more, shorter threads.
+  if ((long long)E * R * strips_for(p.Pw, c.T) * p.Ph < (long long)sms * 256) c.T = kTs[0];
+  if (const char* st = getenv("SRL_MP_T")) {   // test / tuning override
+    const int t = atoi(st);
+    for (int known : kTs)
+      if (t == known) c.T = t;
+  }
   const int T = c.T, VC = c.VC;
   const int paired = variant != 0;   // 0: FADD + FMNMX, 1: FADD2 + FMNMX3 (default)
   p.hp = round_up(h, VC);
@@ -727,8 +762,6 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
   p.tma_wall = (W % 4 == 0) && (((uintptr_t)walls) % 16 == 0);
   p.tma_rock = (h % 4 == 0) && (((uintptr_t)rocks) % 16 == 0);
 
-  const int sms = sm_count();
-  SRL_REQUIRE(sms > 0, SRL_E_CUDA, "maxplus_f32: no CUDA device");
   const size_t kBudget = 110 * 1024;     // per CTA, two CTAs per SM
   const size_t kMax = 220 * 1024;
   const size_t wall_bytes = (size_t)p.wall_stride * 4;
@@ -847,16 +880,25 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
     }
     p.stage_out = 0;
     smem = direct_smem(G, RC);
-    threads = pick_threads(G * items_per_env, kThreads);
     p.ngroups = (E + G - 1) / G;
     blocks = p.ngroups * ((R + RC - 1) / RC);
+    // Few CTAs (a single observation, a handful of maps): cut the output rows
+    // into bands so that the work spreads over the SMs.
+    if (G == 1 && blocks < 2 * sms && p.Ph > 1) {
+      int nb = (2 * sms + blocks - 1) / blocks;
+      if (nb > p.Ph) nb = p.Ph;
+      p.band = (p.Ph + nb - 1) / nb;
+      p.nbands = (p.Ph + p.band - 1) / p.band;
+    }
+    threads = pick_threads(G * RC * p.strips * p.band, kThreads);
+    blocks *= p.nbands;
   }
   if (const char* s = getenv("SRL_MP_THREADS")) {
     const int t = atoi(s);
     if (t >= 32 && t <= 288 && t % 32 == 0) threads = t;
   }
   p.G = G; p.RC = RC; p.rchunks = (R + RC - 1) / RC;
-  p.dPh = make_fastdiv(p.Ph); p.dStrips = make_fastdiv(p.strips);
+  p.dPh = make_fastdiv(staged ? p.Ph : p.band); p.dStrips = make_fastdiv(p.strips);
   p.dRC = make_fastdiv(RC); p.dW = make_fastdiv(W); p.dH = make_fastdiv(H);
   p.dh = make_fastdiv(h); p.dhp = make_fastdiv(p.hp);
   p.dW4 = make_fastdiv(W >= 4 ? W / 4 : 1); p.dh4 = make_fastdiv(h >= 4 ? h / 4 : 1);

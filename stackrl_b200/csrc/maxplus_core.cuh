@@ -49,6 +49,7 @@ struct MaxPlusParams {
   int tma_wall;     // wall rows can be bulk-copied (W % 4 == 0, 16-B aligned base)
   int tma_rock;     // rock rows can be bulk-copied (h % 4 == 0, 16-B aligned base)
   int stage_out;    // staged kernel: score maps leave by bulk TMA store
+  int band, nbands; // direct kernel: output rows per CTA / CTAs per (group, chunk)
   // stream kernel (maxplus_stream_kernel)
   int nslot;        // environments resident in the compute-layout ring
   int ipe;          // items (rotation, output row, strip) per environment

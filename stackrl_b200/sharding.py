@@ -8,9 +8,27 @@ collective.  The only communication is a final gather of per-shard statistics
 (timings, counts, checksums) with one all-gather -- NCCL over NVLink on GPUs,
 gloo in the CPU tests.
 """
+import contextlib
 import os
+import sys
 
 import torch
+
+
+@contextlib.contextmanager
+def _stdout_to_stderr():
+  """NCCL prints its version banner on file descriptor 1 when the first
+  communicator is created; callers that print machine-readable lines on stdout
+  (bench.py) want that on stderr."""
+  sys.stdout.flush()
+  saved = os.dup(1)
+  try:
+    os.dup2(2, 1)
+    yield
+  finally:
+    sys.stdout.flush()
+    os.dup2(saved, 1)
+    os.close(saved)
 
 
 def world():
@@ -42,7 +60,14 @@ def init(backend=None, device=None):
     kwargs = {}
     if backend == 'nccl' and device is not None:
       kwargs['device_id'] = device
-    dist.init_process_group(backend, **kwargs)
+    with _stdout_to_stderr():
+      dist.init_process_group(backend, **kwargs)
+      if backend == 'nccl':
+        # create the communicator now (its banner goes to stderr with the rest)
+        t = torch.zeros(1, device=device if device is not None else
+                        torch.device('cuda', torch.cuda.current_device()))
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
   return dist
 
 

@@ -147,7 +147,7 @@ def _numpy_maps(walls, rocks, level, threshold=0.):
   (301, 1, 32, 32, 16),    # 17 items per environment: a warp pass spans 2-3 environments
   (150, 3, 20, 20, 8),     # ring slots reused many times per CTA
   (1200, 8, 32, 32, 16),   # CTA ranges that start and end inside an environment
-  (97, 2, 64, 64, 16),     # two strips per output row
+  (400, 2, 64, 64, 16),    # two strips per output row
   (40, 8, 48, 48, 16),
 ])
 def test_stream_kernel_item_stream(capi, monkeypatch, shape):
@@ -180,3 +180,19 @@ def test_stream_kernel_negative_values(capi):
     got = capi.maxplus_f32(torch.from_numpy(walls).to(dev), torch.from_numpy(rocks).to(dev),
                            torch.from_numpy(level).to(dev), threshold=thr).cpu().numpy()
     assert np.array_equal(got, _numpy_maps(walls, rocks, level, thr))
+
+
+@pytest.mark.parametrize('tile', ['5', '9', '13', '17', '21', '25'])
+@pytest.mark.parametrize('mode', ['2', '1', '0'])
+def test_every_tile_width_and_kernel(capi, monkeypatch, tile, mode):
+  """All per-thread tile widths (T outputs per thread) of the three kernels --
+  stream (2), staged (1), direct (0) -- on shapes with one and several strips per
+  output row, including widths that do not divide the row."""
+  monkeypatch.setenv('SRL_MP_T', tile)
+  monkeypatch.setenv('SRL_MP_MODE', mode)
+  dev = torch.device('cuda')
+  for E, R, H, W, h in ((9, 3, 32, 32, 16), (5, 2, 48, 64, 16), (3, 1, 64, 40, 8)):
+    walls, rocks, level = synth.placement_batch(77, E, R, H, W, h)
+    got = capi.maxplus_f32(torch.from_numpy(walls).to(dev), torch.from_numpy(rocks).to(dev),
+                           torch.from_numpy(level).to(dev)).cpu().numpy()
+    assert np.array_equal(got, _numpy_maps(walls, rocks, level))
