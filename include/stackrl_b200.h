@@ -61,6 +61,19 @@ SRL_API int srl_maxplus_f32(const float* walls, const float* rocks, const float*
                     float* out, int E, int R, int H, int W, int h,
                     float threshold, srl_stream_t stream);
 
+/* Same maps, with a hint: the caller expects every wall and rock value to be a
+ * non-negative multiple of 2^quantum_log2 below 2^(quantum_log2 + 14) -- true for
+ * heightmaps that come from the reference's float32 depth->elevation formulas
+ * (observer.py:259-260, 274-275: multiples of ulp(1000) = 2^-14 m).  Environments
+ * for which that holds (checked value by value on the device) and whose level is a
+ * power of two are swept in exact 16-bit fixed point (VIADDMNMX.S16x2, two cells
+ * per instruction); all others take the float32 path.  Results are bit-identical
+ * to srl_maxplus_f32 either way.  SRL_NO_QUANTUM disables the hint. */
+#define SRL_NO_QUANTUM 0x7fffffff
+SRL_API int srl_maxplus_f32_q(const float* walls, const float* rocks, const float* level,
+                              float* out, int E, int R, int H, int W, int h,
+                              float threshold, int quantum_log2, srl_stream_t stream);
+
 /* Same for uint8 observations (registered Stack-v0/1/2 dtype): the reference
  * divides uint8 by uint8 -> float64, so this evaluates IEEE float64
  * a/g + b/g per cell.  level [E] u8 (goal.max()), out f64. */

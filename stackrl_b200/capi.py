@@ -38,6 +38,7 @@ _SIGNATURES = {
   'srl_last_error': (_c.c_char_p, []),
   'srl_device_sm_count': (_I, [_c.POINTER(_I)]),
   'srl_maxplus_f32': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_float, _P]),
+  'srl_maxplus_f32_q': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_float, _I, _P]),
   'srl_maxplus_u8': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
   'srl_drop_height_f32': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_float, _P]),
   'srl_goal_overlap_f32': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
@@ -103,8 +104,11 @@ def sm_count():
   return n.value
 
 
-def maxplus_f32(walls, rocks, level=None, threshold=0., out=None):
-  """walls [E,H,W], rocks [E,R,h,h], level [E] or None -> [E,R,H-h+1,W-h+1]."""
+def maxplus_f32(walls, rocks, level=None, threshold=0., out=None, quantum_log2=None):
+  """walls [E,H,W], rocks [E,R,h,h], level [E] or None -> [E,R,H-h+1,W-h+1].
+  ``quantum_log2``: hint that the values are non-negative multiples of
+  2**quantum_log2 (heightmaps from the rasteriser: -14); environments for which
+  it holds are swept in exact 16-bit fixed point, same bits either way."""
   E, H, W = walls.shape
   E2, R, h, h2 = rocks.shape
   if E2 != E or h != h2:
@@ -115,8 +119,13 @@ def maxplus_f32(walls, rocks, level=None, threshold=0., out=None):
     out = torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.float32,
                       device=walls.device)
   with torch.cuda.device(walls.device):
-    _check(lib.srl_maxplus_f32(*args, _dev(out, torch.float32, 'out'),
-                               E, R, H, W, h, float(threshold), _stream()))
+    if quantum_log2 is None:
+      _check(lib.srl_maxplus_f32(*args, _dev(out, torch.float32, 'out'),
+                                 E, R, H, W, h, float(threshold), _stream()))
+    else:
+      _check(lib.srl_maxplus_f32_q(*args, _dev(out, torch.float32, 'out'),
+                                   E, R, H, W, h, float(threshold), int(quantum_log2),
+                                   _stream()))
   return out
 
 

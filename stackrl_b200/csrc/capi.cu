@@ -60,7 +60,16 @@ int srl_maxplus_f32(const float* walls, const float* rocks, const float* level,
   int variant = 1;
   if (const char* s = getenv("SRL_MAXPLUS_VARIANT")) variant = atoi(s);
   return srl::maxplus_f32(walls, rocks, level, out, E, R, H, W, h, threshold,
-                          variant, (cudaStream_t)stream);
+                          variant, SRL_NO_QUANTUM, (cudaStream_t)stream);
+}
+
+int srl_maxplus_f32_q(const float* walls, const float* rocks, const float* level,
+                      float* out, int E, int R, int H, int W, int h, float threshold,
+                      int quantum_log2, srl_stream_t stream) {
+  int variant = 1;
+  if (const char* s = getenv("SRL_MAXPLUS_VARIANT")) variant = atoi(s);
+  return srl::maxplus_f32(walls, rocks, level, out, E, R, H, W, h, threshold,
+                          variant, quantum_log2, (cudaStream_t)stream);
 }
 
 int srl_maxplus_u8(const uint8_t* walls, const uint8_t* rocks, const uint8_t* level,

@@ -9,7 +9,7 @@ namespace srl {
 
 int maxplus_f32(const float* walls, const float* rocks, const float* level,
                 float* out, int E, int R, int H, int W, int h, float threshold,
-                int variant, cudaStream_t stream);
+                int variant, int quantum_log2, cudaStream_t stream);
 
 int goal_overlap_f32(const float* walls, const float* goals, const float* rocks,
                      int32_t* counts, int E, int R, int H, int W, int h,

@@ -303,6 +303,128 @@ __device__ __forceinline__ uint32_t convert_env(const MaxPlusParams& p, const fl
 constexpr int kStreamThreads = (kConsumers + kProducers) * 32;
 constexpr int kProducerThreads = kProducers * 32;
 
+// ---- 16-bit fixed-point layout (see maxplus_core.cuh, "16-bit fixed-point sweep") -- //
+struct Layout16 {
+  int wsw;        // wall row stride in words (two columns per word), wsw % 4 == 0, (wsw/4) odd
+  int rstride;    // words per rock: h * hp / 2 + 4
+  int words;      // words per environment: 2 * H * wsw + R * rstride
+};
+__host__ __device__ inline Layout16 layout16(int H, int R, int h, int hp, int need_words) {
+  Layout16 l;
+  l.wsw = round_up(need_words, 4);
+  if ((l.wsw / 4) % 2 == 0) l.wsw += 4;
+  l.rstride = h * hp / 2 + 4;
+  l.words = 2 * H * l.wsw + R * l.rstride;
+  return l;
+}
+
+// x * sc must be an integer count in [0, 2^14): t + 1.5 * 2^23 keeps an integer t
+// exactly in the low mantissa bits.
+__device__ __forceinline__ bool count16(float x, float sc, int& v) {
+  const float t = __fmul_rn(x, sc);
+  const float r = __fadd_rn(t, 12582912.f);
+  v = __float_as_int(r) - 0x4B400000;
+  return __fadd_rn(r, -12582912.f) == t && (unsigned)v < 16384u;
+}
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) {
+  return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
+}
+
+// Pad words of one slot for the 16-bit layout (written when a slot changes layout).
+__device__ __forceinline__ void init_pads16(uint32_t* slot, const Layout16 l, int H, int W,
+                                            int R, int h, int hp, int pt) {
+  const int padw = l.wsw - W / 2;
+  for (int k = pt; k < 2 * H * padw; k += kProducers * 32) {
+    const int row = k / padw, c = k - row * padw;
+    slot[row * l.wsw + W / 2 + c] = 0u;
+  }
+  uint32_t* rocks = slot + 2 * H * l.wsw;
+  const uint32_t m2 = pack16(kMask16, kMask16);
+  for (int k = pt; k < R * 4; k += kProducers * 32)
+    rocks[(k >> 2) * l.rstride + h * hp / 2 + (k & 3)] = m2;
+  const int padr = (hp - h) / 2;
+  for (int k = pt; k < R * h * padr; k += kProducers * 32) {
+    const int row = k / padr, c = k - row * padr;
+    const int r = row / h, u = row - r * h;
+    rocks[r * l.rstride + u * (hp / 2) + h / 2 + c] = m2;
+  }
+}
+// Pad floats of one slot for the float layout.
+__device__ __forceinline__ void init_padsf(float* slot, const MaxPlusParams& p, int pt) {
+  const int H = p.H, W = p.W, h = p.h, hp = p.hp, Ws = p.Ws, R = p.R;
+  const int padw = Ws - W, padr = hp - h;
+  for (int k = pt; k < H * padw; k += kProducers * 32) {
+    const int row = k / padw, c = k - row * padw;
+    slot[row * Ws + W + c] = 0.f;
+  }
+  for (int k = pt; k < 2 * R * 4; k += kProducers * 32)
+    slot[p.wall_stride + (k >> 2) * p.rock_stride + h * hp + (k & 3)] = kNegInf;
+  for (int k = pt; k < 2 * R * h * padr; k += kProducers * 32) {
+    const int row = k / padr, c = k - row * padr;
+    const int r = row / h, u = row - r * h;
+    slot[p.wall_stride + r * p.rock_stride + u * hp + h + c] = kNegInf;
+  }
+}
+
+// raw -> 16-bit layout.  Returns false as soon as a value is not a count in
+// [0, 2^14) (the caller then converts the environment to the float layout).
+// `scaled`: live test is (x * inv) > thr like the float path.
+__device__ __forceinline__ bool convert_env16(const MaxPlusParams& p, const float* raw,
+                                              uint32_t* slot, const Layout16 l, int* flags,
+                                              float inv, float sc, int pt) {
+  const int H = p.H, W = p.W, h = p.h, hp = p.hp, R = p.R;
+  const uint32_t W4 = W / 4, h4 = h / 4;
+  const int lane = pt & 31;
+  bool ok = true;
+  uint32_t* A = slot;
+  uint32_t* B = slot + H * l.wsw;
+  uint32_t* rocks = slot + 2 * H * l.wsw;
+  const uint32_t nw = (uint32_t)H * W4;
+  for (uint32_t q0 = pt - lane; q0 < nw; q0 += kProducers * 32) {
+    const uint32_t q = q0 + lane;
+    const bool in = q < nw;
+    const uint32_t qq = in ? q : nw - 1;
+    uint32_t row, c4;
+    fdivmod(qq, p.dW4, row, c4);
+    const float4 x = lds128(raw + 4 * qq);
+    int v0, v1, v2, v3;
+    ok = count16(x.x, sc, v0) & count16(x.y, sc, v1) & count16(x.z, sc, v2) &
+         count16(x.w, sc, v3) & ok;
+    int nx = __shfl_down_sync(0xffffffffu, v0, 1);
+    if (c4 == W4 - 1) {
+      nx = 0;                                    // w[W]: pad column
+    } else if (lane == 31) {
+      ok = count16(raw[4 * qq + 4], sc, nx) & ok;
+    }
+    if (in) {
+      *reinterpret_cast<uint2*>(A + row * l.wsw + 2 * c4) =
+          make_uint2(pack16(v0, v1), pack16(v2, v3));
+      *reinterpret_cast<uint2*>(B + row * l.wsw + 2 * c4) =
+          make_uint2(pack16(v1, v2), pack16(v3, nx));
+    }
+  }
+  const float thr = p.threshold;
+  const float* rraw = raw + H * W;
+  const uint32_t nr = (uint32_t)R * h * h4;
+  for (uint32_t q = pt; q < nr; q += kProducers * 32) {
+    uint32_t rrow, c4, slot_i, u;
+    fdivmod(q, p.dh4, rrow, c4);
+    fdivmod(rrow, p.dh, slot_i, u);
+    const float4 x = lds128(rraw + 4 * q);
+    const bool lx = __fmul_rn(x.x, inv) > thr, ly = __fmul_rn(x.y, inv) > thr,
+               lz = __fmul_rn(x.z, inv) > thr, lw = __fmul_rn(x.w, inv) > thr;
+    int v0, v1, v2, v3;
+    const bool o0 = count16(x.x, sc, v0), o1 = count16(x.y, sc, v1),
+               o2 = count16(x.z, sc, v2), o3 = count16(x.w, sc, v3);
+    ok = ok & (o0 | !lx) & (o1 | !ly) & (o2 | !lz) & (o3 | !lw);
+    if (!(lx && ly && lz && lw)) flags[slot_i] = 1;
+    *reinterpret_cast<uint2*>(rocks + slot_i * l.rstride + u * (hp / 2) + 2 * c4) =
+        make_uint2(pack16(lx ? v0 : kMask16, ly ? v1 : kMask16),
+                   pack16(lz ? v2 : kMask16, lw ? v3 : kMask16));
+  }
+  return ok;
+}
+
 template <int T, int VC>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 maxplus_stream_kernel(const MaxPlusParams p) {
@@ -317,8 +439,14 @@ maxplus_stream_kernel(const MaxPlusParams p) {
   uint64_t* rawbar = full + nslot;                                 // [kRawDepth]
   int* ready = reinterpret_cast<int*>(rawbar + kRawDepth);         // [nslot]
   int* negative = ready + nslot;                                   // [nslot]
-  int* masked = negative + nslot;                                  // [nslot][R]
-  const int head = round_up((2 * nslot + kRawDepth) * 8 + (2 * nslot + nslot * R) * 4, 16);
+  int* exact16 = negative + nslot;                                 // [nslot] 16-bit layout?
+  int* lay = exact16 + nslot;                                      // [nslot] producer's copy
+  float* scale_out = reinterpret_cast<float*>(lay + nslot);        // [nslot] count -> value
+  int* bad16 = reinterpret_cast<int*>(scale_out + nslot);          // [1]
+  int* masked = bad16 + 1;                                         // [nslot][R]
+  const int head =
+      round_up((2 * nslot + kRawDepth) * 8 + (5 * nslot + 1 + nslot * R) * 4, 16);
+  const Layout16 l16 = layout16(H, R, h, hp, p.need16);
   const int raw_floats = H * W + R * h * h;
   const int env_floats = p.wall_stride + 2 * R * p.rock_stride;
   float* raw = reinterpret_cast<float*>(smem_raw + head);          // [kRawDepth][raw]
@@ -344,7 +472,11 @@ maxplus_stream_kernel(const MaxPlusParams p) {
     for (int k = 0; k < kRawDepth; ++k) mbar_init(rawbar + k, 1);
     fence_barrier_init();
   }
-  for (int k = tid; k < nslot; k += kStreamThreads) ready[k] = 0;
+  for (int k = tid; k < nslot; k += kStreamThreads) {
+    ready[k] = 0;
+    lay[k] = 0;
+    exact16[k] = 0;
+  }
   // One-time fills of what the producers never rewrite: wall pad columns
   // [W, Ws) (finite) and, in both rock copies, the pad columns [h, hp) and the 4
   // floats behind each rock (-inf: never win, never count as masked).
@@ -400,26 +532,48 @@ maxplus_stream_kernel(const MaxPlusParams p) {
       const float inv = scaled ? pow2_inverse(lv) : 0.f;
       if (use > 0) mbar_wait_parked(empty + s, (use - 1) & 1);   // slot drained
       for (int r = pt; r < R; r += kProducerThreads) flags[r] = 0;
-      if (pt == 0) negative[s] = 0;
-      mbar_wait_parked(rawbar + (k % kRawDepth), (k / kRawDepth) & 1);   // raw data landed
-      named_bar_sync(1, kProducerThreads);
+      if (pt == 0) {
+        negative[s] = 0;
+        *bad16 = 0;
+      }
       // Scale mode is uniform per environment: 0 none, 1 exact multiply by the
       // inverse of a power-of-two level, 2 IEEE division.
       const int mode = !scaled ? 0 : (inv != 0.f ? 1 : 2);
-      uint32_t neg;
-      if (mode == 0)
-        neg = convert_env<0>(p, myraw, wall_s, rock_s, rock_sh, flags, lv, inv, pt);
-      else if (mode == 1)
-        neg = convert_env<1>(p, myraw, wall_s, rock_s, rock_sh, flags, lv, inv, pt);
-      else
-        neg = convert_env<2>(p, myraw, wall_s, rock_s, rock_sh, flags, lv, inv, pt);
-      if ((neg >> 31) != 0u) negative[s] = 1;
+      const bool want16 = p.qlog2 != kNoQuantum && mode != 2;
+      uint32_t* slot16 = reinterpret_cast<uint32_t*>(wall_s);
+      if (want16 && lay[s] != 1) init_pads16(slot16, l16, H, W, R, h, hp, pt);
+      if (!want16 && lay[s] != 0) init_padsf(wall_s, p, pt);
+      mbar_wait_parked(rawbar + (k % kRawDepth), (k / kRawDepth) & 1);   // raw data landed
+      named_bar_sync(1, kProducerThreads);
+      bool is16 = false;
+      if (want16) {
+        // Optimistic 16-bit fixed-point layout; any value that is not a count in
+        // [0, 2^14) sends the environment to the float layout below.
+        const float inv1 = mode == 1 ? inv : 1.f;
+        if (!convert_env16(p, myraw, slot16, l16, flags, inv1, p.qscale, pt)) *bad16 = 1;
+        named_bar_sync(1, kProducerThreads);
+        is16 = *bad16 == 0;
+        if (!is16) init_padsf(wall_s, p, pt);
+      }
+      if (!is16) {
+        uint32_t neg;
+        if (mode == 0)
+          neg = convert_env<0>(p, myraw, wall_s, rock_s, rock_sh, flags, lv, inv, pt);
+        else if (mode == 1)
+          neg = convert_env<1>(p, myraw, wall_s, rock_s, rock_sh, flags, lv, inv, pt);
+        else
+          neg = convert_env<2>(p, myraw, wall_s, rock_s, rock_sh, flags, lv, inv, pt);
+        if ((neg >> 31) != 0u) negative[s] = 1;
+      }
       named_bar_sync(1, kProducerThreads);   // slot written, raw buffer read
       if (pt == 0) {
         if (k + kRawDepth < nenv) {
           fence_proxy_async();        // generic reads of the raw buffer before its async rewrite
           issue(k + kRawDepth);
         }
+        lay[s] = is16 ? 1 : 0;
+        exact16[s] = is16 ? 1 : 0;
+        scale_out[s] = p.qunit * (inv != 0.f ? inv : 1.f);
         st_release_shared(ready + s, k + 1);
         mbar_arrive(full + s);
         // Items of a boundary environment that belong to a neighbouring CTA.
@@ -467,13 +621,34 @@ maxplus_stream_kernel(const MaxPlusParams p) {
     const float* rock_s = wall_s + p.wall_stride + slot_i * p.rock_stride;
     const float* rock_sh = rock_s + R * p.rock_stride;
     const bool any_neg = __any_sync(0xffffffffu, negative[s] != 0);
+    const bool is16 = exact16[s] != 0;
     float acc[T];
-    if (any_neg)
-      sweep_item<T, VC, 1, false>(acc, wall_s + i * Ws + strip * S, rock_s, rock_sh, h, hp,
-                                  Ws);
-    else
-      sweep_item<T, VC, 1, true>(acc, wall_s + i * Ws + strip * S, rock_s, rock_sh, h, hp,
-                                 Ws);
+    if constexpr ((T - 1) % 8 == 0 && VC % 8 == 0) {
+      if (is16) {
+        // 16-bit fixed-point environment: one VIADDMNMX.S16x2 per two cells.
+        const uint32_t* slot16 = reinterpret_cast<const uint32_t*>(wall_s);
+        const uint32_t* wa = slot16 + i * l16.wsw + strip * (S / 2);
+        uint32_t acc16[T];
+        sweep_item16<T, VC>(acc16, wa, wa + H * l16.wsw,
+                            slot16 + 2 * H * l16.wsw + slot_i * l16.rstride, h, hp, l16.wsw);
+        const float unit = scale_out[s];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int lo = (int)(short)(acc16[t] & 0xffffu), hi = (int)(short)(acc16[t] >> 16);
+          const int m = max(lo, hi);
+          acc[t] = m < 0 ? kNegInf : __fmul_rn((float)m, unit);
+        }
+      }
+    }
+    if (!is16) {
+      if (any_neg)
+        sweep_item<T, VC, 1, false>(acc, wall_s + i * Ws + strip * S, rock_s, rock_sh, h, hp,
+                                    Ws);
+      else
+        sweep_item<T, VC, 1, true>(acc, wall_s + i * Ws + strip * S, rock_s, rock_sh, h, hp,
+                                   Ws);
+    }
+    __syncwarp();
     // Decode the item again instead of keeping its indices live across the
     // sweep (the register file is the scarce resource there).
     {
@@ -720,7 +895,7 @@ int launch(const MaxPlusParams& p, bool staged, int blocks, int threads, size_t 
 
 int maxplus_f32(const float* walls, const float* rocks, const float* level,
                 float* out, int E, int R, int H, int W, int h, float threshold,
-                int variant, cudaStream_t stream) {
+                int variant, int quantum_log2, cudaStream_t stream) {
   SRL_REQUIRE(E >= 0 && R >= 1 && h >= 1 && H >= h && W >= h, SRL_E_INVALID,
               "maxplus_f32: bad shape E=%d R=%d H=%d W=%d h=%d", E, R, H, W, h);
   if (E == 0) return SRL_OK;
@@ -795,7 +970,7 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
     const size_t env_b = wall_bytes + (size_t)R * rock_bytes;
     const size_t stage_b = (size_t)kConsumers * 32 * T1 * 4;
     auto stream_smem = [&](int ns) {
-      return (size_t)round_up((2 * ns + kRawDepth) * 8 + (2 * ns + ns * R) * 4, 16) +
+      return (size_t)round_up((2 * ns + kRawDepth) * 8 + (5 * ns + 1 + ns * R) * 4, 16) +
              kRawDepth * raw_b + ns * env_b + stage_b;
     };
     const size_t kStreamMax = 227 * 1024;
@@ -815,6 +990,24 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
                     (size_t)H * W < 65536 && (size_t)R * h * p.hp < 65536 &&
                     p.items < (1ll << 40);
     if (ok) {
+      // 16-bit fixed-point sweep: needs the quantum hint, 16-byte aligned strips
+      // and a packed layout that fits the float layout's slot.
+      p.qlog2 = kNoQuantum;
+      p.need16 = 4;
+      if (quantum_log2 != kNoQuantum && quantum_log2 > -120 && quantum_log2 < 120 &&
+          (T - 1) % 8 == 0 && VC % 8 == 0) {
+        const int pv = VC / 2;
+        const int na4 = ((T + 1) / 2 + pv - 1 + 3) / 4, nb4 = ((T - 1) / 2 + pv - 1 + 3) / 4;
+        int need = ((p.strips - 1) * (T - 1) + (p.hp - VC)) / 2 + 4 * (na4 > nb4 ? na4 : nb4);
+        if (need < W / 2 + 1) need = W / 2 + 1;
+        const Layout16 l = layout16(H, R, h, p.hp, need);
+        if ((size_t)l.words * 4 <= env_b) {
+          p.qlog2 = quantum_log2;
+          p.need16 = need;
+          p.qscale = ldexpf(1.f, -quantum_log2);
+          p.qunit = ldexpf(1.f, quantum_log2);
+        }
+      }
       p.nslot = ns;
       p.G = 1; p.RC = R; p.rchunks = 1; p.stage_out = 1; p.ngroups = E;
       p.dPh = make_fastdiv(p.Ph); p.dStrips = make_fastdiv(p.strips);

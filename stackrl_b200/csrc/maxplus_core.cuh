@@ -29,6 +29,8 @@ __device__ __forceinline__ void fdivmod(uint32_t n, const FastDiv f, uint32_t& q
   r = n - q * f.d;
 }
 
+constexpr int kNoQuantum = 0x7fffffff;
+
 struct MaxPlusParams {
   const float* walls;
   const float* rocks;
@@ -50,6 +52,10 @@ struct MaxPlusParams {
   int tma_rock;     // rock rows can be bulk-copied (h % 4 == 0, 16-B aligned base)
   int stage_out;    // staged kernel: score maps leave by bulk TMA store
   int band, nbands; // direct kernel: output rows per CTA / CTAs per (group, chunk)
+  int qlog2;        // stream kernel: raw values are expected to be multiples of
+                    // 2^qlog2 (kNoQuantum: no hint, float sweep only)
+  float qscale, qunit;   // 2^-qlog2, 2^qlog2
+  int wsw16, need16;     // 16-bit layout: wall row stride (words), words a row read needs
   // stream kernel (maxplus_stream_kernel)
   int nslot;        // environments resident in the compute-layout ring
   int ipe;          // items (rotation, output row, strip) per environment
@@ -166,6 +172,80 @@ __device__ __forceinline__ void sweep_item(float (&acc)[T], const float* wbase,
     if (++j == cpr) {
       j = 0;
       wbase += wskip;
+    }
+  }
+}
+
+// ---- 16-bit fixed-point sweep (DPX) --------------------------------------------- //
+// When every wall and rock value of an environment is a non-negative multiple of
+// one power of two q and smaller than 2^14 q (heightmaps straight from the
+// rasteriser: the reference's float32 depth->elevation formulas leave multiples of
+// ulp(1000) = 2^-14 m, observer.py:259-260/274-275), the float32 sums are exact and
+// so is 16-bit integer arithmetic on the counts x / q.  The sweep then needs ONE
+// instruction per two cells, VIADDMNMX.S16x2 (acc = max(acc, wall + rock) on two
+// packed 16-bit lanes), instead of FADD2 + VIMNMX3.
+//
+// Packed layout: 32-bit words of two consecutive columns.  wall A[m] = (w[2m],
+// w[2m+1]), wall B[m] = (w[2m+1], w[2m+2]) (even / odd output columns), rock
+// N[m] = (n[2m], n[2m+1]); masked rock cells hold kMask16, so their sums stay
+// negative and never win.  acc[t] holds the running maxima over even (low half)
+// and odd (high half) rock columns of output t.
+constexpr int kMask16 = -20000;          // 16383 + kMask16 < 0, 2 * kMask16 > -32768... never added twice
+constexpr uint32_t kAccInit16 = 0x80008000u;
+
+__device__ __forceinline__ uint4 lds128u(const uint32_t* p) {
+  return *reinterpret_cast<const uint4*>(p);
+}
+
+// All cells of one item: T outputs of one output row against one rock.
+// wa/wb: the item's first word of the A / B wall copies (row stride wsw words),
+// rk: the rock's first word (rows are hp/2 words, contiguous).
+template <int T, int VC>
+__device__ __forceinline__ void sweep_item16(uint32_t (&acc)[T], const uint32_t* wa,
+                                             const uint32_t* wb, const uint32_t* rk, int h,
+                                             int hp, int wsw) {
+  static_assert((T - 1) % 8 == 0 && VC % 8 == 0, "16-bit sweep: 16-byte aligned strips");
+  constexpr int PV = VC / 2;                     // rock pair words per chunk
+  constexpr int NA = (T + 1) / 2 + PV - 1;       // A words: even t, pairs t/2 .. t/2+PV-1
+  constexpr int NB = (T - 1) / 2 + PV - 1;       // B words: odd t
+  constexpr int NA4 = (NA + 3) / 4, NB4 = (NB + 3) / 4;
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t] = kAccInit16;
+  const int cpr = hp / VC, nchunks = h * cpr, wskip = wsw - hp / 2;
+  int j = 0;
+#pragma unroll 2
+  for (int c = 0; c < nchunks; ++c) {
+    uint32_t a[4 * NA4], b[4 * NB4], n[PV];
+#pragma unroll
+    for (int k = 0; k < NA4; ++k) {
+      const uint4 x = lds128u(wa + 4 * k);
+      a[4 * k] = x.x; a[4 * k + 1] = x.y; a[4 * k + 2] = x.z; a[4 * k + 3] = x.w;
+    }
+#pragma unroll
+    for (int k = 0; k < NB4; ++k) {
+      const uint4 x = lds128u(wb + 4 * k);
+      b[4 * k] = x.x; b[4 * k + 1] = x.y; b[4 * k + 2] = x.z; b[4 * k + 3] = x.w;
+    }
+#pragma unroll
+    for (int k = 0; k < PV / 4; ++k) {
+      const uint4 x = lds128u(rk + 4 * k);
+      n[4 * k] = x.x; n[4 * k + 1] = x.y; n[4 * k + 2] = x.z; n[4 * k + 3] = x.w;
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+      for (int v = 0; v < PV; ++v) {
+        const uint32_t w = (t & 1) ? b[(t - 1) / 2 + v] : a[t / 2 + v];
+        acc[t] = __viaddmax_s16x2(w, n[v], acc[t]);
+      }
+    }
+    wa += PV;
+    wb += PV;
+    rk += PV;
+    if (++j == cpr) {
+      j = 0;
+      wa += wskip;
+      wb += wskip;
     }
   }
 }

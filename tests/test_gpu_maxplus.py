@@ -196,3 +196,51 @@ def test_every_tile_width_and_kernel(capi, monkeypatch, tile, mode):
     got = capi.maxplus_f32(torch.from_numpy(walls).to(dev), torch.from_numpy(rocks).to(dev),
                            torch.from_numpy(level).to(dev)).cpu().numpy()
     assert np.array_equal(got, _numpy_maps(walls, rocks, level))
+
+
+def _quantised_batch(seed, E, R, H, W, h, qlog2=-14, wall_top=0.3):
+  """Heightmaps as the rasteriser leaves them: non-negative multiples of 2^qlog2
+  (observer.py:259-260 evaluates the elevation at magnitude 1000 in float32)."""
+  walls, rocks, level = synth.placement_batch(seed, E, R, H, W, h)
+  q = np.float32(2.0 ** qlog2)
+  walls = (np.round(walls * (wall_top / 0.3) / q) * q).astype('float32')
+  rocks = (np.round(rocks / q) * q).astype('float32')
+  return walls, rocks, level
+
+
+@pytest.mark.parametrize('shape', [(64, 8, 32, 32, 16), (700, 8, 32, 32, 16), (150, 2, 64, 64, 16),
+                                   (33, 3, 48, 40, 8)])
+def test_fixed_point_sweep_is_bit_exact(capi, shape):
+  """srl_maxplus_f32_q: quantised heightmaps with a power-of-two level are swept
+  in 16-bit fixed point (VIADDMNMX.S16x2) -- same bits as numpy's float32."""
+  E, R, H, W, h = shape
+  walls, rocks, level = _quantised_batch(5, E, R, H, W, h)
+  dev = torch.device('cuda')
+  args = [torch.from_numpy(x).to(dev) for x in (walls, rocks, level)]
+  got = capi.maxplus_f32(*args, quantum_log2=-14)
+  assert torch.equal(got, capi.maxplus_f32(*args))           # float sweep, same bits
+  pick = np.random.default_rng(2).choice(E, min(E, 40), replace=False)
+  want = _numpy_maps(walls[pick], rocks[pick], level[pick])
+  assert np.array_equal(got[torch.from_numpy(pick).to(dev)].cpu().numpy(), want)
+
+
+def test_fixed_point_sweep_falls_back_per_environment(capi):
+  """The hint is only a hint: environments that are not quantised, too tall for
+  14 bits, negative, or normalised by a level that is not a power of two take the
+  float sweep; a batch can mix all of them."""
+  E, R, H, W, h = 96, 8, 32, 32, 16
+  walls, rocks, level = _quantised_batch(6, E, R, H, W, h)
+  fw, fr, _ = synth.placement_batch(7, E, R, H, W, h)
+  walls[1::6] = fw[1::6]                       # arbitrary float32 walls
+  rocks[2::6] = fr[2::6]                       # arbitrary float32 rocks
+  walls[3::6] += np.float32(1.5)               # counts above 2^14
+  walls[4::6, 0, 0] = np.float32(-2.0 ** -14)  # one negative cell
+  level = level.copy()
+  level[5::6] = np.float32(0.3)                # not a power of two
+  dev = torch.device('cuda')
+  args = [torch.from_numpy(x).to(dev) for x in (walls, rocks, level)]
+  got = capi.maxplus_f32(*args, quantum_log2=-14).cpu().numpy()
+  assert np.array_equal(got, _numpy_maps(walls, rocks, level))
+  # no level at all, pose threshold
+  got = capi.maxplus_f32(args[0], args[1], None, threshold=1e-4, quantum_log2=-14)
+  assert torch.equal(got, capi.maxplus_f32(args[0], args[1], None, threshold=1e-4))
