@@ -218,7 +218,22 @@ maxplus_staged_kernel(const MaxPlusParams p) {
 #ifndef SRL_CONSUMERS
 #define SRL_CONSUMERS 16
 #endif
-constexpr int kConsumers = SRL_CONSUMERS, kProducers = 4, kRawDepth = 2;
+#ifndef SRL_PRODUCERS
+#define SRL_PRODUCERS 8
+#endif
+// Register split of the warp-specialised kernel (setmaxnreg): 24 warps start at
+// the launch-bound cap of 80 registers; the two producer warpgroups give
+// registers back to the CTA pool, the four consumer warpgroups take them.  The
+// pool only holds what was released, so 8 * (80 - P) >= 16 * (C - 80) must hold
+// (P = 64, C = 88 is the measured optimum: the 32/16 geometry is producer-bound,
+// the 64/16 one consumer-bound).
+#ifndef SRL_PRODUCER_REGS
+#define SRL_PRODUCER_REGS 64
+#endif
+#ifndef SRL_CONSUMER_REGS
+#define SRL_CONSUMER_REGS 88
+#endif
+constexpr int kConsumers = SRL_CONSUMERS, kProducers = SRL_PRODUCERS, kRawDepth = 2;
 
 // Producer-side conversion of one environment, raw -> compute layout, by the
 // kProducerThreads threads of the producer group (thread index pt).  Returns the
@@ -302,6 +317,9 @@ __device__ __forceinline__ uint32_t convert_env(const MaxPlusParams& p, const fl
 
 constexpr int kStreamThreads = (kConsumers + kProducers) * 32;
 constexpr int kProducerThreads = kProducers * 32;
+static_assert(SRL_PRODUCER_REGS == 0 ||
+                  kProducers * (80 - SRL_PRODUCER_REGS) >= kConsumers * (SRL_CONSUMER_REGS - 80),
+              "setmaxnreg: the consumers cannot take more registers than the producers release");
 
 // ---- 16-bit fixed-point layout (see maxplus_core.cuh, "16-bit fixed-point sweep") -- //
 struct Layout16 {
@@ -506,6 +524,8 @@ maxplus_stream_kernel(const MaxPlusParams p) {
 
   if (warp >= kConsumers) {
     // ============================ producer group ============================ //
+    if constexpr (kConsumers % 4 == 0 && kProducers % 4 == 0 && SRL_PRODUCER_REGS > 0)
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SRL_PRODUCER_REGS));
     const int pt = tid - kConsumers * 32;          // 0 .. kProducerThreads-1
     const uint32_t wb = (uint32_t)H * W * 4, rb = (uint32_t)R * h * h * 4;
     auto issue = [&](int k) {
@@ -587,6 +607,8 @@ maxplus_stream_kernel(const MaxPlusParams p) {
   }
 
   // ============================= consumer warp ================================ //
+  if constexpr (kConsumers % 4 == 0 && kProducers % 4 == 0 && SRL_CONSUMER_REGS > 0)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SRL_CONSUMER_REGS));
   const int cw = warp;                            // consumer index
   float* mystage = stage + cw * (32 * T);
   const bool out_aligned = (((uintptr_t)p.out) & 15) == 0;
