@@ -243,6 +243,30 @@ def extra_metrics(torch, dev):
                  'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                  'frac': n * bytes_per_rock / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
                  'bytes_per_rock': bytes_per_rock}}
+  # -- config 2 on heightmaps as the rasteriser leaves them (multiples of 2^-14 m):
+  #    the exact 16-bit fixed-point sweep behind srl_maxplus_f32_q ---------------- #
+  from stackrl_b200 import baselines, synth
+  E, R, H, W, h = (CFG[k] for k in ('envs', 'rotations', 'H', 'W', 'h'))
+  walls_h, rocks_h, _ = synth.placement_batch(0, E, R, H, W, h)
+  q = np.float32(2.0 ** -14)
+  wq = torch.from_numpy((np.round(walls_h / q) * q).astype('float32')).to(dev)
+  rq = torch.from_numpy((np.round(rocks_h / q) * q).astype('float32')).to(dev)
+  gq = torch.from_numpy(synth.goals(7, E, H, W)).to(dev)
+  lq = gq.amax(dim=(1, 2))
+  vq = torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.float32, device=dev)
+  same = torch.equal(capi.maxplus_f32(wq, rq, lq), capi.maxplus_f32(wq, rq, lq, quantum_log2=-14))
+  ms_q = _time_loop(torch, lambda _: capi.maxplus_f32(wq, rq, lq, out=vq, quantum_log2=-14), 50)
+  ms_f = _time_loop(torch, lambda _: capi.maxplus_f32(wq, rq, lq, out=vq), 50)
+  scorer_q = baselines.PlacementScorer('height', quantum_log2=-14)
+  ms_s = _time_loop(torch, lambda _: scorer_q(wq, gq, rq), 50)
+  evals = evals_per_step()
+  out['quantised_heightmaps'] = {
+    'workload': 'C2 shapes, walls/rocks rounded to multiples of 2^-14 m (what the '
+                'float32 depth->elevation formulas of observer.py:259-260 produce), '
+                'level 0.25; L2-warm single set',
+    'maxplus_fixed_point_ms': ms_q, 'maxplus_fixed_point_evals_per_s': evals / (ms_q * 1e-3),
+    'maxplus_float_ms': ms_f, 'bit_identical_to_float_sweep': bool(same),
+    'scorer_ms': ms_s, 'scorer_evals_per_s': evals / (ms_s * 1e-3)}
   # -- config 4 slice: env observations, 64x64 wall, 16x16 rock ----------------- #
   E = 4096
   bank2 = meshes.MeshBank()

@@ -55,11 +55,12 @@ def _planes(inputs):
   return _upload(wall[None]), _upload(goal[None]), _upload(rock[None, None])
 
 
-def _height_device(walls, goals, rocks):
-  """[E,R,Ph,Pw] drop map in the reference's arithmetic for the obs dtype."""
+def _height_device(walls, goals, rocks, quantum_log2=None):
+  """[E,R,Ph,Pw] drop map in the reference's arithmetic for the obs dtype.
+  ``quantum_log2``: see capi.maxplus_f32 (a hint, never changes the result)."""
   if walls.dtype == torch.float32:
     level = goals.amax(dim=(1, 2))          # get_inputs: goal.max() (baselines.py:23)
-    return capi.maxplus_f32(walls, rocks, level)
+    return capi.maxplus_f32(walls, rocks, level, quantum_log2=quantum_log2)
   if walls.dtype == torch.uint8:
     # uint8/uint8 is float64 in numpy: IEEE float64 a/g + b/g per cell.
     return capi.maxplus_u8(walls, rocks, goals.amax(dim=(1, 2)))
@@ -186,15 +187,20 @@ class PlacementScorer(object):
   All tensors stay on the GPU; nothing synchronises.  ``walls``/``goals``
   [E,H,W], ``rocks`` [E,R,h,h] (float32, planar)."""
 
-  def __init__(self, method='height', goal=True, minorder=1, threshold=0.75):
+  def __init__(self, method='height', goal=True, minorder=1, threshold=0.75,
+               quantum_log2=None):
+    """``quantum_log2``: the heightmaps are expected to be multiples of
+    2**quantum_log2 (maps straight from the rasteriser: camera.HEIGHT_QUANTUM_LOG2);
+    such environments are swept in exact 16-bit fixed point.  Same results."""
     if method != 'height':
       raise ValueError('PlacementScorer scores with the max-plus height map')
     self.goal = goal
     self.minorder = minorder
     self.threshold = threshold
+    self.quantum_log2 = quantum_log2
 
   def values(self, walls, goals, rocks):
-    return _height_device(walls, goals, rocks)
+    return _height_device(walls, goals, rocks, self.quantum_log2)
 
   def __call__(self, walls, goals, rocks, want_shown=False, fused='mask'):
     """-> dict(values [E,R,Ph,Pw], actions [E,R], best [E,2] = (view, flat index),

@@ -11,6 +11,9 @@ import math
 import numpy as np
 
 FAR = 10 ** 3          # Observer.far (observer.py:6)
+# The float32 elevation formulas (observer.py:259-260, 274-275) subtract two numbers
+# of magnitude ~FAR, so every height is a multiple of ulp(FAR) = 2^-14 m.
+HEIGHT_QUANTUM_LOG2 = -14
 
 
 def view_matrix(eye, target, up):

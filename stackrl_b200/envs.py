@@ -22,6 +22,7 @@ import torch
 
 from stackrl_b200 import capi
 from stackrl_b200.baselines import PlacementScorer
+from stackrl_b200.camera import HEIGHT_QUANTUM_LOG2
 from stackrl_b200.observer import BatchedObserver
 
 
@@ -285,7 +286,9 @@ class HeightPolicy(object):
   BatchedStackEnv: returns the action tensor(s) ``step`` expects."""
 
   def __init__(self, goal=True, minorder=1, threshold=0.75):
-    self._scorer = PlacementScorer('height', goal, minorder, threshold)
+    # float32 maps come straight from the rasteriser: multiples of 2^-14 m
+    self._scorer = PlacementScorer('height', goal, minorder, threshold,
+                                   quantum_log2=HEIGHT_QUANTUM_LOG2)
 
   def __call__(self, env):
     walls, goals, rocks = env.planes()

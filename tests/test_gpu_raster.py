@@ -292,3 +292,32 @@ def test_batched_env_random_rollout_and_settle_hook(mods, observe_golden):
     env.step(policy(env))                      # finished environments must be reset
   a = env.sample()
   assert a.shape == (E,) and int(a.max()) < 97 * 97
+
+
+def test_rasterised_maps_take_the_fixed_point_sweep_unchanged():
+  """Heightmaps from raster_kernel are multiples of 2^-14 m (observer.py:259-260
+  in float32): the quantum hint HeightPolicy passes must not change a bit."""
+  from stackrl_b200 import baselines, envs, meshes
+  from stackrl_b200.camera import HEIGHT_QUANTUM_LOG2
+  dev = torch.device('cuda')
+  bank = meshes.MeshBank()
+  v, t = meshes.synthetic_rocks(5, 16, 1, max_dimension=0.12)
+  for k in range(16):
+    bank.add(v[k], t)
+  env = envs.BatchedStackEnv(bank, 64, episode_length=6, observable_size_ratio=2,
+                             resolution_factor=4, dtype='float32', seed=3,
+                             orientation_freedom=3, device=dev)
+  policy = envs.HeightPolicy()
+  env.reset()
+  for _ in range(3):
+    env.step(policy(env))
+  walls, goals, rocks = env.planes()
+  q = 2.0 ** HEIGHT_QUANTUM_LOG2
+  assert bool(((walls / q) == torch.round(walls / q)).all())
+  assert bool(((rocks / q) == torch.round(rocks / q)).all())
+  plain = baselines.PlacementScorer('height')(walls, goals, rocks)
+  hinted = baselines.PlacementScorer('height', quantum_log2=HEIGHT_QUANTUM_LOG2)(
+    walls, goals, rocks)
+  assert torch.equal(plain['values'], hinted['values'])
+  assert torch.equal(plain['actions'], hinted['actions'])
+  assert torch.equal(plain['best'], hinted['best'])
