@@ -168,3 +168,32 @@ def test_baseline_difference_uint8_actions(B, scoring_golden):
     a, v = B.Baseline(method='difference', goal=bool(goal), minorder=minorder, value=True)(obs)
     assert a == int(scoring_golden[key + '/action'])
     assert np.array_equal(v, scoring_golden[key + '/values'])
+
+
+@pytest.mark.parametrize('shape', [(40, 8, 32, 32, 16), (6, 2, 128, 128, 32), (9, 3, 40, 36, 8),
+                                   (5, 1, 30, 27, 7)])
+def test_uint8_integer_key_kernel_equals_float64_kernel(monkeypatch, shape):
+  """maxplus_u8: the VIADDMNMX integer-key sweep (default) against the float64
+  DADD kernel, for goal levels whose quotients round in every possible way."""
+  from stackrl_b200 import capi
+  E, R, H, W, h = shape
+  rng = np.random.default_rng(17)
+  walls = rng.integers(0, 256, (E, H, W), dtype=np.uint8)
+  rocks = rng.integers(0, 256, (E, R, h, h), dtype=np.uint8)
+  rocks[rng.random(rocks.shape) < 0.3] = 0
+  rocks[0] = 0                                      # an all-masked environment
+  rocks[1] = np.maximum(rocks[1], 1)                # no masked cell at all
+  levels = np.array([1, 2, 3, 7, 85, 170, 255, 254, 129, 128], dtype=np.uint8)
+  level = levels[np.arange(E) % len(levels)]
+  dev = torch.device('cuda')
+  args = [torch.from_numpy(x).to(dev) for x in (walls, rocks, level)]
+  monkeypatch.setenv('SRL_U8_MODE', '0')
+  want = capi.maxplus_u8(*args)
+  monkeypatch.setenv('SRL_U8_MODE', '1')
+  got = capi.maxplus_u8(*args)
+  assert torch.equal(got, want)
+  # and the float64 kernel itself against the oracle on one environment per level
+  for e in range(min(E, len(levels))):
+    goal = np.full((H, W), level[e], dtype=np.uint8)
+    ref = S.height((np.stack([walls[e], goal], -1), rocks[e, 0][..., None]))
+    assert np.array_equal(got[e, 0].cpu().numpy(), ref)
