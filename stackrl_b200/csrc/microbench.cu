@@ -51,9 +51,12 @@ __device__ __forceinline__ float vimax(float a, float b) {
   return __int_as_float(d);
 }
 
-// VARIANT: 0 FADD+FMNMX | 1 2xFADD+FMNMX3 | 2 FADD2+FMNMX3 (kernel's mix)
+// VARIANT: 0 FADD+FMNMX | 1 2xFADD+FMNMX3 | 2 FADD2+FMNMX3 (float sweep, any sign)
 //          3 FADD only | 4 FMNMX only | 5 FMNMX3 only | 6 FADD2 only
-//          7 FADD2+VIMNMX3(s32) | 8 VIMNMX3 only | 9 FADD+VIMNMX(s32)
+//          7 FADD2+VIMNMX3(s32) (float sweep, non-negative tiles) | 8 VIMNMX3 only
+//          9 FADD+VIMNMX(s32) | 14 warp-specialised FADD2 / VIMNMX3 | 15 basic-block
+//          separated groups | 17 VIADDMNMX.S16x2 (fixed-point sweep) | 18 VIADDMNMX.S32
+//          (uint8 integer-key sweep)
 // Every op takes a loop-carried accumulator as an operand, so ptxas can neither
 // hoist it out of the loop nor fold it.  Dependency distance is >= 8 ops.
 // "cells" are counted as if each variant did the full (add, max) pair work of
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out
 #pragma unroll
     for (int v = 0; v < kV; v += 2) {
 #pragma unroll
-      for (int t = 0; t < (VARIANT >= 10 ? 0 : kT); ++t) {
+      for (int t = 0; t < (VARIANT >= 14 ? 0 : kT); ++t) {
         const int k = ((t + 8) % kT) & ~1;     // even-aligned register pair
         const int k1 = (t + 8) % kT, k2 = (t + 9) % kT;
         if constexpr (VARIANT == 0) {
@@ -114,28 +117,6 @@ __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out
           acc[t] = vimax(acc[t], vadd(acc[k2], nv[v + 1]));
         }
       }
-      // Variants 10-13: the FADD2 + 3-input max mix issued in groups of G adds
-      // that share the rock pair (operand-reuse cache) followed by G maxes.
-      if constexpr (VARIANT >= 10 && VARIANT <= 13) {
-        constexpr int G = (VARIANT == 12) ? 4 : (VARIANT == 13) ? 16 : 8;
-#pragma unroll
-        for (int t0 = 0; t0 < kT; t0 += G) {
-          float s0[G], s1[G];
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            const int k = ((t0 + g + 8) % kT) & ~1;
-            // even/odd t share the wall pair; add it to the pair of the next
-            // rock column for odd t so that no two adds are identical
-            if ((t0 + g) & 1) vadd2(s0[g], s1[g], acc[k], acc[k + 1], nv[(v + 2) % kV], nv[(v + 3) % kV]);
-            else vadd2(s0[g], s1[g], acc[k], acc[k + 1], nv[v], nv[v + 1]);
-          }
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            if constexpr (VARIANT == 11) acc[t0 + g] = vmax3(acc[t0 + g], s0[g], s1[g]);
-            else acc[t0 + g] = vimax3(acc[t0 + g], s0[g], s1[g]);
-          }
-        }
-      }
       // Variant 14: warp-specialised -- even warps issue only FADD2 (rock pair
       // reused), odd warps only VIMNMX3: do the two pipes overlap when the
       // instructions come from different warps?
@@ -155,9 +136,10 @@ __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out
           }
         }
       }
-      // Variants 15/16: groups of 8 adds and 8 maxes kept apart by never-taken
-      // loop exits (basic-block boundaries ptxas cannot schedule across).
-      if constexpr (VARIANT == 15 || VARIANT == 16) {
+      // Variant 15: groups of 8 adds and 8 maxes kept apart by never-taken
+      // data-dependent branches (basic-block boundaries ptxas cannot schedule
+      // across), so that the shared rock pair is served by the operand-reuse cache.
+      if constexpr (VARIANT == 15) {
         constexpr int G = 8;
 #pragma unroll
         for (int t0 = 0; t0 < kT; t0 += G) {
@@ -170,8 +152,7 @@ __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out
           if (s1[G - 1] == magic) goto done;      // never true; ends the add block
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            if constexpr (VARIANT == 16) acc[t0 + g] = vmax3(acc[t0 + g], s0[g], s1[g]);
-            else acc[t0 + g] = vimax3(acc[t0 + g], s0[g], s1[g]);
+            acc[t0 + g] = vimax3(acc[t0 + g], s0[g], s1[g]);
           }
           if (acc[t0 + G - 1] == magic) goto done;  // ends the max block
         }
@@ -202,7 +183,7 @@ __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out
   }
 done:
   float r = acc[0];
-  if constexpr (VARIANT == 15 || VARIANT == 16) {
+  if constexpr (VARIANT == 15) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) r = fmaxf(r, fmaxf(s0[g], s1[g]));
   }
@@ -214,7 +195,8 @@ done:
 }  // namespace
 
 int microbench_addmax(int variant, int iters, double* host_cells_per_s) {
-  SRL_REQUIRE(host_cells_per_s != nullptr && iters > 0 && variant >= 0 && variant <= 18,
+  SRL_REQUIRE(host_cells_per_s != nullptr && iters > 0 && (variant <= 9 || variant == 14 || variant == 15 || variant == 17 || variant == 18) &&
+                  variant >= 0,
               SRL_E_INVALID, "microbench_addmax: bad arguments");
   const int sms = sm_count();
   SRL_REQUIRE(sms > 0, SRL_E_CUDA, "microbench_addmax: no device");
@@ -234,7 +216,7 @@ int microbench_addmax(int variant, int iters, double* host_cells_per_s) {
     switch (variant) {
 #define SRL_MB(V) case V: addmax_kernel<V><<<blocks, threads>>>(in, out, iters, 0x7fc12345); break;
       SRL_MB(0) SRL_MB(1) SRL_MB(2) SRL_MB(3) SRL_MB(4) SRL_MB(5) SRL_MB(6) SRL_MB(7)
-      SRL_MB(8) SRL_MB(9) SRL_MB(10) SRL_MB(11) SRL_MB(12) SRL_MB(13) SRL_MB(14) SRL_MB(15) SRL_MB(16) SRL_MB(17) SRL_MB(18)
+      SRL_MB(8) SRL_MB(9) SRL_MB(14) SRL_MB(15) SRL_MB(17) SRL_MB(18)
 #undef SRL_MB
     }
     SRL_CUDA(cudaEventRecord(t1));

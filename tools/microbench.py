@@ -3,10 +3,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sys
 from stackrl_b200 import capi
 names = {0: 'FADD+FMNMX', 1: '2FADD+FMNMX3', 2: 'FADD2+FMNMX3', 3: 'FADD', 4: 'FMNMX(fused)',
-         5: 'FMNMX3', 6: 'FADD2', 7: 'FADD2+VIMNMX3', 8: 'VIMNMX3', 9: '2FADD+VIMNMX3', 10: 'grp8 FADD2+VIMNMX3', 11: 'grp8 FADD2+FMNMX3', 12: 'grp4', 13: 'grp16',
-         14: 'warp-specialised FADD2 | VIMNMX3', 15: 'BB-split grp8 FADD2 / VIMNMX3', 16: 'BB-split grp8 FADD2 / FMNMX3', 17: 'VIADDMNMX.S16x2 (2 cells/inst)', 18: 'VIADDMNMX.S32 (1 cell/inst)'}
+         5: 'FMNMX3', 6: 'FADD2', 7: 'FADD2+VIMNMX3', 8: 'VIMNMX3', 9: '2FADD+VIMNMX3', 14: 'warp-specialised FADD2 | VIMNMX3', 15: 'BB-split grp8 FADD2 / VIMNMX3', 17: 'VIADDMNMX.S16x2 (2 cells/inst)', 18: 'VIADDMNMX.S32 (1 cell/inst)'}
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-variants = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else range(19)
+variants = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else sorted(names)
 for v in variants:
   c = capi.microbench_addmax(v, iters)
   print('variant %d %-16s %.4e cells/s  %.1f cells/clk/SM @1965MHz' % (v, names[v], c, c / 148 / 1.965e9))
