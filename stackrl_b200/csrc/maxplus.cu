@@ -550,7 +550,13 @@ maxplus_stream_kernel(const MaxPlusParams p) {
       int* flags = masked + s * R;
       const float lv = scaled ? __ldg(p.level + env_first + k) : 1.f;
       const float inv = scaled ? pow2_inverse(lv) : 0.f;
-      if (use > 0) mbar_wait_parked(empty + s, (use - 1) & 1);   // slot drained
+      // One warp waits on the mbarriers (slot drained, raw data landed); the others
+      // block in the named barrier, which costs no issue slots.
+      if (pt < 32) {
+        if (use > 0) mbar_wait_parked(empty + s, (use - 1) & 1);
+        mbar_wait_parked(rawbar + (k % kRawDepth), (k / kRawDepth) & 1);
+      }
+      named_bar_sync(1, kProducerThreads);
       for (int r = pt; r < R; r += kProducerThreads) flags[r] = 0;
       if (pt == 0) {
         negative[s] = 0;
@@ -563,7 +569,6 @@ maxplus_stream_kernel(const MaxPlusParams p) {
       uint32_t* slot16 = reinterpret_cast<uint32_t*>(wall_s);
       if (want16 && lay[s] != 1) init_pads16(slot16, l16, H, W, R, h, hp, pt);
       if (!want16 && lay[s] != 0) init_padsf(wall_s, p, pt);
-      mbar_wait_parked(rawbar + (k % kRawDepth), (k / kRawDepth) & 1);   // raw data landed
       named_bar_sync(1, kProducerThreads);
       bool is16 = false;
       if (want16) {
