@@ -14,7 +14,7 @@ CONFIGS = [
   ('C2 32x32/16 R8', 4096, 8, 32, 32, 16),
   ('C4 64x64/16 R1', 8192, 1, 64, 64, 16),
   ('C4 64x64/16 R8', 2048, 8, 64, 64, 16),
-  ('C5 128x128/32 R36', 128, 36, 128, 128, 32),
+  ('C5 128x128/32 R36', 592, 36, 128, 128, 32),   # 4736 CTAs = 16 whole waves
   ('C1 128x128/32 R1', 1024, 1, 128, 128, 32),
   ('C1 single obs', 1, 1, 128, 128, 32),
   ('odd 40x56/12 R3', 1024, 3, 40, 56, 12),
