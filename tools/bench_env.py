@@ -1,0 +1,44 @@
+"""Device time of one environment observation (C4 slice geometry): wall raster, rock
+raster, reward terms, packed observation.  python tools/bench_env.py [E]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from stackrl_b200 import envs, meshes
+
+E = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+dev = torch.device('cuda')
+bank = meshes.MeshBank()
+v, t = meshes.synthetic_rocks(5, 64, 1, max_dimension=0.12)
+for k in range(64):
+  bank.add(v[k], t)
+env = envs.BatchedStackEnv(bank, E, episode_length=12, observable_size_ratio=4,
+                           resolution_factor=4, dtype='float32', rewarder='iou', seed=5,
+                           device=dev)
+policy = envs.HeightPolicy()
+env.reset()
+for _ in range(6):
+  env.step(policy(env))
+torch.cuda.synchronize()
+
+
+def timeit(fn, reps=20):
+  for _ in range(2):
+    fn()
+  torch.cuda.synchronize()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(reps):
+    fn()
+  b.record()
+  torch.cuda.synchronize()
+  return a.elapsed_time(b) / reps
+
+
+print('walls  %.3f ms' % timeit(env.obs.observe_walls))
+print('rocks  %.3f ms' % timeit(lambda: env.obs.observe_rocks(env._current)))
+print('reward %.3f ms' % timeit(env.reward_terms))
+print('pack   %.3f ms' % timeit(lambda: env.observation))
+print('policy %.3f ms' % timeit(lambda: policy(env)))

@@ -8,7 +8,7 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.log 
 python bench.py --steps 200 --warmup 10 > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err || exit 1
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/final_bench_ref.json 2> gpurun_out/final_bench_ref.err
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv \
   --log-file gpurun_out/final_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline \
   > gpurun_out/final_ncu_launches.log 2>&1
 python tools/run_step.py 5 > gpurun_out/final_step.log 2>&1 && \
