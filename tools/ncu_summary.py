@@ -38,7 +38,7 @@ def main():
       for k in KEYS:
         if k in d:
           entry[k] = d[k] + (' ' + u[k] if u.get(k) else '')
-      out[name] = entry
+      out[name if name not in out else name + ' [' + entry['report'] + ']'] = entry
   with open(sys.argv[1], 'w') as f:
     json.dump(out, f, indent=1)
   print(json.dumps(out, indent=1))
