@@ -55,11 +55,13 @@ def _planes(inputs):
   return _upload(wall[None]), _upload(goal[None]), _upload(rock[None, None])
 
 
-def _height_device(walls, goals, rocks, quantum_log2=None):
+def _height_device(walls, goals, rocks, quantum_log2=None, level=None):
   """[E,R,Ph,Pw] drop map in the reference's arithmetic for the obs dtype.
-  ``quantum_log2``: see capi.maxplus_f32 (a hint, never changes the result)."""
+  ``quantum_log2``: see capi.maxplus_f32 (a hint, never changes the result).
+  ``level``: goal.max() per environment when the caller already has it."""
   if walls.dtype == torch.float32:
-    level = goals.amax(dim=(1, 2))          # get_inputs: goal.max() (baselines.py:23)
+    if level is None:
+      level = goals.amax(dim=(1, 2))        # get_inputs: goal.max() (baselines.py:23)
     return capi.maxplus_f32(walls, rocks, level, quantum_log2=quantum_log2)
   if walls.dtype == torch.uint8:
     # uint8/uint8 is float64 in numpy: IEEE float64 a/g + b/g per cell.
@@ -199,10 +201,10 @@ class PlacementScorer(object):
     self.threshold = threshold
     self.quantum_log2 = quantum_log2
 
-  def values(self, walls, goals, rocks):
-    return _height_device(walls, goals, rocks, self.quantum_log2)
+  def values(self, walls, goals, rocks, level=None):
+    return _height_device(walls, goals, rocks, self.quantum_log2, level)
 
-  def __call__(self, walls, goals, rocks, want_shown=False, fused='mask'):
+  def __call__(self, walls, goals, rocks, want_shown=False, fused='mask', level=None):
     """-> dict(values [E,R,Ph,Pw], actions [E,R], best [E,2] = (view, flat index),
     shown [E,R,Ph,Pw] float64 if requested, counts [E,R,Ph,Pw] when computed).
 
@@ -210,7 +212,8 @@ class PlacementScorer(object):
     and batch-wise pick (overlap counts stay in shared memory);
     fused='full': everything in one launch (srl_score_f32; float32 batches of
     supported shapes, falls back otherwise); fused=False: the three separate
-    kernels (also returns the counts)."""
+    kernels (also returns the counts).  ``level`` [E]: goal.max() per environment if
+    the caller has it (float32 planes only; saves one reduction kernel)."""
     if fused == 'full' and not want_shown and walls.dtype == torch.float32:
       try:
         values, actions, best = capi.score_f32(
@@ -223,7 +226,7 @@ class PlacementScorer(object):
       except capi.SrlError as err:
         if err.code != capi.SRL_E_UNSUPPORTED:
           raise
-    values = self.values(walls, goals, rocks)
+    values = self.values(walls, goals, rocks, level)
     counts = None
     if self.goal and fused:
       try:

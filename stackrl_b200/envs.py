@@ -303,5 +303,7 @@ class HeightPolicy(object):
       rocks = rock[..., 0].contiguous()
       if env.R == 1:
         rocks = rocks[:, None].contiguous()
-    best = self._scorer(walls, goals, rocks)['best']
+    # a goal rectangle is never empty, so goal.max() is the goal height
+    level = env._goal_z_d if walls.dtype == torch.float32 else None
+    best = self._scorer(walls, goals, rocks, level=level)['best']
     return (best[:, 0], best[:, 1]) if env.R > 1 else best[:, 1]
