@@ -920,9 +920,10 @@ int launch(const MaxPlusParams& p, bool staged, int blocks, int threads, size_t 
 
 }  // namespace
 
-int maxplus_f32(const float* walls, const float* rocks, const float* level,
-                float* out, int E, int R, int H, int W, int h, float threshold,
-                int variant, int quantum_log2, cudaStream_t stream) {
+static int maxplus_f32_impl(const float* walls, const float* rocks, const float* level,
+                            float* out, int E, int R, int H, int W, int h, float threshold,
+                            int variant, int quantum_log2, int forced_T,
+                            cudaStream_t stream) {
   SRL_REQUIRE(E >= 0 && R >= 1 && h >= 1 && H >= h && W >= h, SRL_E_INVALID,
               "maxplus_f32: bad shape E=%d R=%d H=%d W=%d h=%d", E, R, H, W, h);
   if (E == 0) return SRL_OK;
@@ -945,10 +946,15 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
   // Latency-bound calls (one observation, a handful of maps): far fewer items
   // than lanes on the chip, so take the narrowest tile -- more, shorter threads.
   if ((long long)E * R * strips_for(p.Pw, c.T) * p.Ph < (long long)sms * 256) c.T = kTs[0];
+  bool tile_fixed = forced_T != 0;
+  if (forced_T) c.T = forced_T;
   if (const char* st = getenv("SRL_MP_T")) {   // test / tuning override
     const int t = atoi(st);
     for (int known : kTs)
-      if (t == known) c.T = t;
+      if (t == known) {
+        c.T = t;
+        tile_fixed = true;
+      }
   }
   const int T = c.T, VC = c.VC;
   const int paired = variant != 0;   // 0: FADD + FMNMX, 1: FADD2 + FMNMX3 (default)
@@ -1091,6 +1097,34 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
     SRL_REQUIRE(direct_smem(1, RC) <= kMax, SRL_E_UNSUPPORTED,
                 "maxplus_f32: one wall (%dx%d) + one rock (%d) exceed shared memory",
                 H, W, h);
+    // One CTA sweeps its items in whole passes of its threads: with few items per
+    // CTA (one rotation of a 97-row map is 582 items at T = 17) the tile width that
+    // fills the passes best wins over the one with the fewest wasted columns.
+    if (!tile_fixed && (long long)E * R * p.strips * p.Ph >= (long long)sms * 256) {
+      auto cost_of = [&](int TT) {
+        const int st = strips_for(p.Pw, TT);
+        const int items = RC * st * p.Ph;
+        const int th = pick_threads(items, kThreads);
+        const int passes = (items + th - 1) / th;
+        const double util = (double)items / ((double)passes * th);
+        const double waste = (double)st * TT / p.Pw;
+        const double loads = ((TT + VC + 2) / 4 + VC / 2) / (double)(TT * VC);
+        return waste * (1.03 + loads) / util;
+      };
+      int best_T = T;
+      double best_cost = cost_of(T) * 0.97;       // switch only for a clear gain
+      for (int TT : kTs) {
+        if (VC == 16 && TT > 21) continue;
+        const double cst = cost_of(TT);
+        if (cst < best_cost) {
+          best_cost = cst;
+          best_T = TT;
+        }
+      }
+      if (best_T != T)
+        return maxplus_f32_impl(walls, rocks, level, out, E, R, H, W, h, threshold, variant,
+                                quantum_log2, best_T, stream);
+    }
     const int items_per_env = RC * p.strips * p.Ph;
     if (RC == R) {
       while (G < 32 && G < E && direct_smem(G + 1, RC) <= kBudget &&
@@ -1135,6 +1169,13 @@ int maxplus_f32(const float* walls, const float* rocks, const float* level,
 #undef SRL_MP_ROW
 #undef SRL_MP_CASE
   return fail(SRL_E_UNSUPPORTED, "maxplus_f32: no kernel for T=%d VC=%d", T, VC);
+}
+
+int maxplus_f32(const float* walls, const float* rocks, const float* level,
+                float* out, int E, int R, int H, int W, int h, float threshold,
+                int variant, int quantum_log2, cudaStream_t stream) {
+  return maxplus_f32_impl(walls, rocks, level, out, E, R, H, W, h, threshold, variant,
+                          quantum_log2, 0, stream);
 }
 
 }  // namespace srl
