@@ -212,6 +212,7 @@ struct MaskSelectParams {
   double overlap_threshold;
   uint32_t mulPw;              // ceil(2^32 / Pw) for k / Pw (k * Pw < 2^32)
   int vec4;                    // packed kernel: bit images straight from 4-wide global loads
+  int stage_values;            // packed kernel: score maps staged in shared memory (small maps)
   uint32_t mulW4, mulh4, mulhh4;   // ceil(2^32 / d) for d = W/4, h/4, h*h/4
 };
 
@@ -554,8 +555,9 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
     // Every thread turns 4 consecutive pixels into 4 bits and ORs them into the
     // packed word; only the score maps are staged in shared memory.
     for (int k = tid; k < H * g_nW + R * g_ng; k += kSelThreads) below[k] = 0u;
-    stage_bytes(vals, values + (size_t)e * R * P, (size_t)R * P * sizeof(V), tid,
-                kSelThreads);
+    if (q.stage_values)
+      stage_bytes(vals, values + (size_t)e * R * P, (size_t)R * P * sizeof(V), tid,
+                  kSelThreads);
     if (tid < 32) s_cmax[tid] = 0;
     __syncthreads();
     const In* wsrc = walls + (size_t)e * H * W;
@@ -638,7 +640,10 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
     for (int g = 0; g < NG; ++g) f[g] = foot[r * NG + g];
   }
   uint16_t* mine = cnt + (size_t)r * P;
-  const V* v = vals + (size_t)r * P;
+  // Big maps are not staged (they would leave one CTA per SM): the score map of
+  // the lane's view is read from global memory / L1 instead.
+  const V* v = (kFixed || q.vec4) && !q.stage_values ? values + ((size_t)e * R + r) * P
+                                                     : vals + (size_t)r * P;
   int cm = 0;
   for (int pos = warp * ppw + qpos; pos < P; pos += step) {
     const uint32_t* wp = win + pos;
@@ -785,10 +790,14 @@ int launch_mask_select(const V* values, const In* walls, const In* goals, const 
            ((uintptr_t)goals % al) == 0 && ((uintptr_t)rocks % al) == 0 &&
            (size_t)R * h * h * (h * h / 4) < (1ull << 32);
   q.mulW4 = mulc(W / 4); q.mulh4 = mulc(h / 4); q.mulhh4 = mulc(h * h / 4);
+  const size_t packed_base =
+      4 * ((size_t)H * q.nW + (size_t)R * q.ng + (size_t)H * q.Pw) + 2 * (size_t)R * P;
+  // stage the score maps while that keeps >= 4 CTAs per SM
+  q.stage_values = !q.vec4 || packed_base + 16 + pad16((size_t)R * P * sizeof(V)) <= 52 * 1024;
   const size_t packed_smem =
-      4 * ((size_t)H * q.nW + (size_t)R * q.ng + (size_t)H * q.Pw) + 2 * (size_t)R * P +
-      (q.vec4 ? 16 + pad16((size_t)R * P * sizeof(V)) : staged);
-  if (pow2 && packed_smem <= 110 * 1024 && minorder <= 1) {     // >= 2 CTAs per SM
+      packed_base + (!q.vec4 ? staged
+                             : (q.stage_values ? 16 + pad16((size_t)R * P * sizeof(V)) : 32));
+  if (pow2 && packed_smem <= 200 * 1024 && minorder <= 1) {     // one CTA per SM at worst
 #define SRL_MSP_LAUNCH(MM, NGG)                                                            \
   do {                                                                                     \
     auto k = mask_select_packed_kernel<V, In, MM, NGG>;                                    \
