@@ -16,6 +16,7 @@ namespace srl {
 namespace {
 
 constexpr int kSelThreads = 256;
+constexpr int kMaxViews = 64;      // views per environment the packed kernel keeps results for
 
 struct Best {          // arg-min candidate: smaller value wins, then smaller index
   double v;
@@ -213,6 +214,7 @@ struct MaskSelectParams {
   uint32_t mulPw;              // ceil(2^32 / Pw) for k / Pw (k * Pw < 2^32)
   int vec4;                    // packed kernel: bit images straight from 4-wide global loads
   int stage_values;            // packed kernel: score maps staged in shared memory (small maps)
+  int rch;                     // packed kernel: views per chunk (power of two dividing R, <= 32)
   uint32_t mulW4, mulh4, mulhh4;   // ceil(2^32 / d) for d = W/4, h/4, h*h/4
 };
 
@@ -519,8 +521,8 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
   __shared__ Cand<V> s_bmin[NW][32], s_bmask[NW][32];
   __shared__ V s_vm[NW][32];
   __shared__ bool s_any[NW][32];
-  __shared__ V s_pick[32];
-  __shared__ int s_pick_i[32];
+  __shared__ V s_pick[kMaxViews];
+  __shared__ int s_pick_i[kMaxViews];
   __shared__ double s_fill[32];
   constexpr bool kFixed = GEO != 0;
   const int R = kFixed ? (int)(GEO & 63) : q.R, H = kFixed ? (int)(GEO >> 26) : q.H;
@@ -534,8 +536,9 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
   uint32_t* below = reinterpret_cast<uint32_t*>(sel_smem);          // [H][nW]
   uint32_t* foot = below + H * g_nW;                                // [R][ng] row-packed
   uint32_t* win = foot + R * g_ng;                                  // [H][Pw] row-packed
-  uint16_t* cnt = reinterpret_cast<uint16_t*>(win + H * Pw);        // [R][P]
-  unsigned char* at = reinterpret_cast<unsigned char*>(cnt + (size_t)R * P);
+  uint16_t* cnt = reinterpret_cast<uint16_t*>(win + H * Pw);        // [views per chunk][P]
+  unsigned char* at =
+      reinterpret_cast<unsigned char*>(cnt + (size_t)(kFixed ? R : q.rch) * P);
   at += (16 - (reinterpret_cast<uintptr_t>(at) & 15)) & 15;
   V* vals = reinterpret_cast<V*>(at);
   at += ((size_t)R * P * sizeof(V) + 15) & ~(size_t)15;
@@ -628,103 +631,119 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
   }
   __syncthreads();
 
-  // ---- lanes = (view r, position slot): counts ------------------------------------ //
-  const int r = lane & (R - 1);
-  const int ppw = 32 / R;                       // positions per warp iteration
-  const int qpos = lane / R;
+  // ---- lanes = (view, position slot), RCH views at a time -------------------------- //
+  // RCH is the largest power of two (<= 32) that divides R: 8 rotations go in one
+  // chunk, 36 in nine chunks of 4, an odd count one view at a time.
+  const int RCH = kFixed ? R : q.rch;
+  const int rl = lane & (RCH - 1);
+  const int ppw = 32 / RCH;                     // positions per warp iteration
+  const int qpos = lane / RCH;
   const int step = NW * ppw;
   const int gstride = g_pf * Pw;
-  uint32_t f[NG > 0 ? NG : 1];
-  if (NG > 0) {
-#pragma unroll
-    for (int g = 0; g < NG; ++g) f[g] = foot[r * NG + g];
-  }
-  uint16_t* mine = cnt + (size_t)r * P;
-  // Big maps are not staged (they would leave one CTA per SM): the score map of
-  // the lane's view is read from global memory / L1 instead.
-  const V* v = (kFixed || q.vec4) && !q.stage_values ? values + ((size_t)e * R + r) * P
-                                                     : vals + (size_t)r * P;
-  int cm = 0;
-  for (int pos = warp * ppw + qpos; pos < P; pos += step) {
-    const uint32_t* wp = win + pos;
-    int c = 0;
+  uint16_t* mine = cnt + (size_t)rl * P;
+  for (int rc0 = 0; rc0 < R; rc0 += RCH) {
+    const int r = rc0 + rl;
+    uint32_t f[NG > 0 ? NG : 1];
     if (NG > 0) {
 #pragma unroll
-      for (int g = 0; g < NG; ++g) c += __popc(wp[g * gstride] & f[g]);
-    } else {
-      for (int g = 0; g < g_ng; ++g) c += __popc(wp[g * gstride] & foot[r * g_ng + g]);
+      for (int g = 0; g < NG; ++g) f[g] = foot[r * NG + g];
     }
-    mine[pos] = (uint16_t)c;
-    cm = max(cm, c);
-  }
-  for (int o = R; o < 32; o <<= 1) cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, o));
-  if (qpos == 0) atomicMax(s_cmax + r, cm);
-  __syncthreads();
+    // Big maps are not staged (they would leave one CTA per SM): the score map of
+    // the lane's view is read from global memory / L1 instead.
+    const V* v = (kFixed || q.vec4) && !q.stage_values ? values + ((size_t)e * R + r) * P
+                                                       : vals + (size_t)r * P;
+    int cm = 0;
+    for (int pos = warp * ppw + qpos; pos < P; pos += step) {
+      const uint32_t* wp = win + pos;
+      int c = 0;
+      if (NG > 0) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) c += __popc(wp[g * gstride] & f[g]);
+      } else {
+        for (int g = 0; g < g_ng; ++g) c += __popc(wp[g * gstride] & foot[r * g_ng + g]);
+      }
+      mine[pos] = (uint16_t)c;
+      cm = max(cm, c);
+    }
+    for (int o = RCH; o < 32; o <<= 1) cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+    if (qpos == 0) atomicMax(s_cmax + rl, cm);
+    __syncthreads();
 
-  // ---- mask cut, masked maximum, arg-min candidates --------------------------------- //
-  const int cmin = (int)ceil(q.overlap_threshold * (double)s_cmax[r]);
-  Cand<V> bmin = {V(0), -1}, bmask = {V(0), -1};
-  V vm = V(0);
-  bool any = false;
-  for (int pos = warp * ppw + qpos; pos < P; pos += step) {
-    if ((int)mine[pos] < cmin) continue;
-    const V x = v[pos];
-    vm = (!any || x > vm) ? x : vm;
-    any = true;
-    // Positions come in increasing order per lane, so only a strictly smaller
-    // value can replace a candidate: test that before the neighbourhood.
-    if (bmask.idx < 0 || x < bmask.v) {
-      bmask.v = x;
-      bmask.idx = pos;
-    }
-    if (M != 0 && (bmin.idx < 0 || x < bmin.v)) {
-      const int i = kFixed ? pos / Pw : (int)__umulhi((uint32_t)pos, q.mulPw), j = pos - i * Pw;
-      if (local_min<V, M>(v, x, i, j, Ph, Pw, q.minorder)) {
-        bmin.v = x;
-        bmin.idx = pos;
-      }
-    }
-  }
-  for (int o = R; o < 32; o <<= 1) {
-    const V xv = __shfl_xor_sync(0xffffffffu, bmin.v, o);
-    const int xi = __shfl_xor_sync(0xffffffffu, bmin.idx, o);
-    if (xi >= 0) take(bmin, xv, xi);
-    const V yv = __shfl_xor_sync(0xffffffffu, bmask.v, o);
-    const int yi = __shfl_xor_sync(0xffffffffu, bmask.idx, o);
-    if (yi >= 0) take(bmask, yv, yi);
-    const V zv = __shfl_xor_sync(0xffffffffu, vm, o);
-    const bool za = __shfl_xor_sync(0xffffffffu, (int)any, o) != 0;
-    if (za) {
-      vm = (!any || zv > vm) ? zv : vm;
+    // ---- mask cut, masked maximum, arg-min candidates ------------------------------- //
+    const int cmin = (int)ceil(q.overlap_threshold * (double)s_cmax[rl]);
+    Cand<V> bmin = {V(0), -1}, bmask = {V(0), -1};
+    V vm = V(0);
+    bool any = false;
+    for (int pos = warp * ppw + qpos; pos < P; pos += step) {
+      if ((int)mine[pos] < cmin) continue;
+      const V x = v[pos];
+      vm = (!any || x > vm) ? x : vm;
       any = true;
-    }
-  }
-  if (qpos == 0) {
-    s_bmin[warp][r] = bmin;
-    s_bmask[warp][r] = bmask;
-    s_vm[warp][r] = vm;
-    s_any[warp][r] = any;
-  }
-  __syncthreads();
-  if (tid < R) {
-    Cand<V> a = {V(0), -1}, b = {V(0), -1};
-    V m2 = V(0);
-    bool have = false;
-    for (int w = 0; w < NW; ++w) {
-      if (s_bmin[w][tid].idx >= 0) take(a, s_bmin[w][tid].v, s_bmin[w][tid].idx);
-      if (s_bmask[w][tid].idx >= 0) take(b, s_bmask[w][tid].v, s_bmask[w][tid].idx);
-      if (s_any[w][tid]) {
-        m2 = (!have || s_vm[w][tid] > m2) ? s_vm[w][tid] : m2;
-        have = true;
+      // Positions come in increasing order per lane, so only a strictly smaller
+      // value can replace a candidate: test that before the neighbourhood.
+      if (bmask.idx < 0 || x < bmask.v) {
+        bmask.v = x;
+        bmask.idx = pos;
+      }
+      if (M != 0 && (bmin.idx < 0 || x < bmin.v)) {
+        const int i = kFixed ? pos / Pw : (int)__umulhi((uint32_t)pos, q.mulPw),
+                  j = pos - i * Pw;
+        if (local_min<V, M>(v, x, i, j, Ph, Pw, q.minorder)) {
+          bmin.v = x;
+          bmin.idx = pos;
+        }
       }
     }
-    const Cand<V> pick = a.idx >= 0 ? a : b;
-    actions[(size_t)e * R + tid] = pick.idx;
-    s_pick[tid] = pick.v;
-    s_pick_i[tid] = pick.idx;
-    s_fill[tid] = (double)m2 + 0.001;
+    for (int o = RCH; o < 32; o <<= 1) {
+      const V xv = __shfl_xor_sync(0xffffffffu, bmin.v, o);
+      const int xi = __shfl_xor_sync(0xffffffffu, bmin.idx, o);
+      if (xi >= 0) take(bmin, xv, xi);
+      const V yv = __shfl_xor_sync(0xffffffffu, bmask.v, o);
+      const int yi = __shfl_xor_sync(0xffffffffu, bmask.idx, o);
+      if (yi >= 0) take(bmask, yv, yi);
+      const V zv = __shfl_xor_sync(0xffffffffu, vm, o);
+      const bool za = __shfl_xor_sync(0xffffffffu, (int)any, o) != 0;
+      if (za) {
+        vm = (!any || zv > vm) ? zv : vm;
+        any = true;
+      }
+    }
+    if (qpos == 0) {
+      s_bmin[warp][rl] = bmin;
+      s_bmask[warp][rl] = bmask;
+      s_vm[warp][rl] = vm;
+      s_any[warp][rl] = any;
+    }
+    __syncthreads();
+    if (tid < RCH) {
+      Cand<V> a = {V(0), -1}, b = {V(0), -1};
+      V m2 = V(0);
+      bool have = false;
+      for (int w = 0; w < NW; ++w) {
+        if (s_bmin[w][tid].idx >= 0) take(a, s_bmin[w][tid].v, s_bmin[w][tid].idx);
+        if (s_bmask[w][tid].idx >= 0) take(b, s_bmask[w][tid].v, s_bmask[w][tid].idx);
+        if (s_any[w][tid]) {
+          m2 = (!have || s_vm[w][tid] > m2) ? s_vm[w][tid] : m2;
+          have = true;
+        }
+      }
+      const Cand<V> pick = a.idx >= 0 ? a : b;
+      actions[(size_t)e * R + rc0 + tid] = pick.idx;
+      s_pick[rc0 + tid] = pick.v;
+      s_pick_i[rc0 + tid] = pick.idx;
+      s_fill[tid] = (double)m2 + 0.001;
+      s_cmax[tid] = 0;                            // for the next chunk of views
+    }
+    __syncthreads();
+    if (shown) {
+      const double fill = s_fill[rl];
+      double* sh = shown + ((size_t)e * R + r) * P;
+      for (int pos = warp * ppw + qpos; pos < P; pos += step)
+        sh[pos] = -((int)mine[pos] >= cmin ? (double)v[pos] : fill);
+    }
+    // the next chunk overwrites the counts and the per-warp partials
+    if (rc0 + RCH < R) __syncthreads();
   }
-  __syncthreads();
   if (best && tid == 0) {
     // PyGreedy batchwise: first argmax over views of -value (policies.py:78-80)
     int bv = 0;
@@ -732,12 +751,6 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
       if (s_pick[k] < s_pick[bv]) bv = k;
     best[2 * (size_t)e] = bv;
     best[2 * (size_t)e + 1] = s_pick_i[bv];
-  }
-  if (shown) {
-    const double fill = s_fill[r];
-    double* sh = shown + ((size_t)e * R + r) * P;
-    for (int pos = warp * ppw + qpos; pos < P; pos += step)
-      sh[pos] = -((int)mine[pos] >= cmin ? (double)v[pos] : fill);
   }
 }
 
@@ -783,7 +796,10 @@ int launch_mask_select(const V* values, const In* walls, const In* goals, const 
     k<<<E, kSelThreads, smem, stream>>>(values, walls, goals, rocks, actions, shown, best, \
                                         q);                                                \
   } while (0)
-  const bool pow2 = R <= 32 && (R & (R - 1)) == 0;
+  int rch = 1;
+  while (rch < 32 && R % (rch * 2) == 0) rch *= 2;
+  q.rch = rch;
+  const bool pow2 = R <= kMaxViews;      // (any view count: rch views at a time)
   auto mulc = [](uint32_t d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); };
   const size_t al = sizeof(In) * 4;
   q.vec4 = W % 4 == 0 && h % 4 == 0 && ((uintptr_t)walls % al) == 0 &&
@@ -791,7 +807,7 @@ int launch_mask_select(const V* values, const In* walls, const In* goals, const 
            (size_t)R * h * h * (h * h / 4) < (1ull << 32);
   q.mulW4 = mulc(W / 4); q.mulh4 = mulc(h / 4); q.mulhh4 = mulc(h * h / 4);
   const size_t packed_base =
-      4 * ((size_t)H * q.nW + (size_t)R * q.ng + (size_t)H * q.Pw) + 2 * (size_t)R * P;
+      4 * ((size_t)H * q.nW + (size_t)R * q.ng + (size_t)H * q.Pw) + 2 * (size_t)rch * P;
   // stage the score maps while that keeps >= 4 CTAs per SM
   q.stage_values = !q.vec4 || packed_base + 16 + pad16((size_t)R * P * sizeof(V)) <= 52 * 1024;
   const size_t packed_smem =

@@ -83,7 +83,8 @@ def test_unbatched_return_conventions(B, scoring_golden):
     B.Baseline(method=3)
 
 
-@pytest.mark.parametrize('shape', [(6, 8, 32, 32, 16), (3, 4, 64, 64, 16), (2, 3, 40, 56, 8)])
+@pytest.mark.parametrize('shape', [(6, 8, 32, 32, 16), (3, 4, 64, 64, 16), (2, 3, 40, 56, 8),
+                                   (2, 6, 32, 32, 16), (1, 12, 24, 24, 8), (1, 36, 48, 48, 16)])
 @pytest.mark.parametrize('goal,minorder', [(True, 1), (True, 0), (True, 2), (False, 1)])
 def test_placement_scorer_batched(B, shape, goal, minorder):
   """Device-resident batch: actions / batch-wise picks equal to looping the
