@@ -190,18 +190,32 @@ class PlacementScorer(object):
   [E,H,W], ``rocks`` [E,R,h,h] (float32, planar)."""
 
   def __init__(self, method='height', goal=True, minorder=1, threshold=0.75,
-               quantum_log2=None):
-    """``quantum_log2``: the heightmaps are expected to be multiples of
+               quantum_log2=None, difference_exponent=2, weights_exponent=2):
+    """``method``: 'height' (max-plus drop map) or 'difference' (baselines.py:45-77,
+    float64 maps).  ``quantum_log2``: the heightmaps are expected to be multiples of
     2**quantum_log2 (maps straight from the rasteriser: camera.HEIGHT_QUANTUM_LOG2);
     such environments are swept in exact 16-bit fixed point.  Same results."""
-    if method != 'height':
-      raise ValueError('PlacementScorer scores with the max-plus height map')
+    if method not in ('height', 'difference'):
+      raise ValueError("PlacementScorer scores with 'height' or 'difference'")
+    if method == 'difference' and (difference_exponent not in (1, 2) or
+                                   weights_exponent not in (0, 2)):
+      raise ValueError('difference on device batches: exponents (1|2, 0|2) only')
+    self.method = method
+    self.difference_exponent = difference_exponent
+    self.weights_exponent = weights_exponent
     self.goal = goal
     self.minorder = minorder
     self.threshold = threshold
     self.quantum_log2 = quantum_log2
 
   def values(self, walls, goals, rocks, level=None):
+    if self.method == 'difference':
+      if level is None:
+        level = goals.amax(dim=(1, 2))
+      u8 = walls.dtype == torch.uint8
+      weights = capi.difference_weights(rocks, None if u8 else level, self.weights_exponent)
+      run = capi.difference_u8 if u8 else capi.difference_f32
+      return run(walls, rocks, level, weights, self.difference_exponent)[0]
     return _height_device(walls, goals, rocks, self.quantum_log2, level)
 
   def __call__(self, walls, goals, rocks, want_shown=False, fused='mask', level=None):
@@ -214,7 +228,8 @@ class PlacementScorer(object):
     supported shapes, falls back otherwise); fused=False: the three separate
     kernels (also returns the counts).  ``level`` [E]: goal.max() per environment if
     the caller has it (float32 planes only; saves one reduction kernel)."""
-    if fused == 'full' and not want_shown and walls.dtype == torch.float32:
+    if fused == 'full' and not want_shown and walls.dtype == torch.float32 and \
+        self.method == 'height':
       try:
         values, actions, best = capi.score_f32(
           walls, goals if self.goal else None, rocks,

@@ -222,3 +222,25 @@ def test_fused_scoring_rejects_unsupported_shapes():
     capi.score_f32(torch.zeros((1, 17, 17), device=dev), torch.zeros((1, 17, 17), device=dev),
                    torch.zeros((1, 1, 5, 5), device=dev))
   assert err.value.code == capi.SRL_E_UNSUPPORTED
+
+
+@pytest.mark.parametrize('dtype', ['float32', 'uint8'])
+def test_placement_scorer_difference_batched(B, dtype):
+  """PlacementScorer('difference') on a device batch == looping the oracle's
+  Baseline(method='difference') over environments and views (float64 maps)."""
+  E, R, H, W, h = 3, 4, 32, 32, 8
+  dev = torch.device('cuda')
+  obs = [synth.batched_observation(60 + e, H, W, h, R, dtype=dtype) for e in range(E)]
+  walls = np.stack([o[0][0, ..., 0] for o in obs])
+  goals = np.stack([o[0][0, ..., 1] for o in obs])
+  rocks = np.stack([o[1][..., 0] for o in obs])
+  out = B.PlacementScorer('difference')(torch.from_numpy(walls).to(dev),
+                                        torch.from_numpy(goals).to(dev),
+                                        torch.from_numpy(rocks).to(dev), want_shown=True)
+  assert out['values'].dtype == torch.float64
+  for e in range(E):
+    (k, idx), v = S.greedy(
+      obs[e], lambda o: S.baseline_call(o, method='difference'), value=True, batched=True,
+      batchwise=True)
+    assert tuple(out['best'][e].cpu().numpy()) == (k, idx)
+    assert np.array_equal(out['shown'][e].cpu().numpy().reshape(R, -1), v)
