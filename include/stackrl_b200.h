@@ -160,7 +160,9 @@ SRL_API int srl_score_f32(const float* walls, const float* goals, const float* r
  * f = sum_{u,v} w[u,v] * |h0 - (o+n)|^p  in numpy's order: float32 lift and
  * residual, float64 weights/product, pairwise summation over the contiguous
  * [h,h] block.  p in {1, 2}.  weights [E,R,h,h] f64 come from
- * srl_difference_weights.  out [E,R,P] f64; top (h0) [E,R,P] f32 or NULL. */
+ * srl_difference_weights.  out [E,R,P] f64; top (h0) [E,R,P] f32 or NULL (when
+ * given, h0 comes from the max-plus kernel -- same bits, much faster than the
+ * in-kernel scalar pass used otherwise). */
 SRL_API int srl_difference_weights(const float* rocks, const float* level,
                            double* weights, int E, int R, int h,
                            int weights_exponent, srl_stream_t stream);

@@ -231,12 +231,14 @@ def difference_f32(walls, rocks, level, weights, difference_exponent=2, want_top
           _opt(level, torch.float32, 'level'), _dev(weights, torch.float64, 'weights'))
   shape = (E, R, H - h + 1, W - h + 1)
   out = torch.empty(shape, dtype=torch.float64, device=walls.device)
-  top = torch.empty(shape, dtype=torch.float32, device=walls.device) if want_top else None
+  # always hand over a `top` buffer: the library then takes h0 from its max-plus
+  # kernel instead of a scalar pass per position
+  top = torch.empty(shape, dtype=torch.float32, device=walls.device)
   with torch.cuda.device(walls.device):
     _check(lib.srl_difference_f32(*args, _dev(out, torch.float64, 'out'),
                                   _opt(top, torch.float32, 'top'), E, R, H, W, h,
                                   int(difference_exponent), _stream()))
-  return out, top
+  return out, (top if want_top else None)
 
 
 def difference_u8(walls, rocks, level, weights, difference_exponent=2, want_top=False):
@@ -246,12 +248,12 @@ def difference_u8(walls, rocks, level, weights, difference_exponent=2, want_top=
           _opt(level, torch.uint8, 'level'), _dev(weights, torch.float64, 'weights'))
   shape = (E, R, H - h + 1, W - h + 1)
   out = torch.empty(shape, dtype=torch.float64, device=walls.device)
-  top = torch.empty(shape, dtype=torch.float64, device=walls.device) if want_top else None
+  top = torch.empty(shape, dtype=torch.float64, device=walls.device)
   with torch.cuda.device(walls.device):
     _check(lib.srl_difference_u8(*args, _dev(out, torch.float64, 'out'),
                                  _opt(top, torch.float64, 'top'), E, R, H, W, h,
                                  int(difference_exponent), _stream()))
-  return out, top
+  return out, (top if want_top else None)
 
 
 def corrcoef_localized(walls, rocks, level=None):

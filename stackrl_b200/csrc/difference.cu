@@ -20,6 +20,8 @@
 #include "kernels.h"
 #include "pairwise.cuh"
 
+namespace srl { constexpr int kNoQuantumHint = SRL_NO_QUANTUM; }
+
 namespace srl {
 
 namespace {
@@ -58,7 +60,7 @@ difference_weights_kernel(const In* __restrict__ rocks, const In* __restrict__ l
   for (int k = 0; k < h * h; ++k) w[k] = __ddiv_rn(w[k], total);
 }
 
-template <typename In>
+template <typename In, bool HAVE_TOP>
 __global__ void __launch_bounds__(128)
 difference_kernel(const In* __restrict__ walls, const In* __restrict__ rocks,
                   const In* __restrict__ level, const double* __restrict__ weights,
@@ -106,17 +108,24 @@ difference_kernel(const In* __restrict__ walls, const In* __restrict__ rocks,
   for (int item = tid; item < rows_out * Pw; item += blockDim.x) {
     const int i = item / Pw, j = item % Pw;
     const C* win = wall_s + i * W + j;
-    // pass 1: h0, the max-plus value (baselines.py:68).
-    C h0 = C(kNegInf);
-    for (int u = 0; u < h; ++u)
-      for (int v = 0; v < h; ++v) {
-        const C n = rock_s[u * h + v];
-        if (n > C(0)) {
-          const C lifted = A::add(win[u * W + v], n);
-          h0 = lifted > h0 ? lifted : h0;
+    // pass 1: h0, the max-plus value (baselines.py:68) -- already in `top` when the
+    // max-plus kernel produced it (same arithmetic, bit for bit).
+    const size_t o = (((size_t)e * R + r) * Ph + i0 + i) * Pw + j;
+    C h0;
+    if constexpr (HAVE_TOP) {
+      h0 = top[o];
+    } else {
+      h0 = C(kNegInf);
+      for (int u = 0; u < h; ++u)
+        for (int v = 0; v < h; ++v) {
+          const C n = rock_s[u * h + v];
+          if (n > C(0)) {
+            const C lifted = A::add(win[u * W + v], n);
+            h0 = lifted > h0 ? lifted : h0;
+          }
         }
-      }
-    if (floor0 && !(h0 > C(0))) h0 = C(0);
+      if (floor0 && !(h0 > C(0))) h0 = C(0);
+    }
     // pass 2: weighted residual, numpy's pairwise order (baselines.py:69).
     int u = 0, v = 0;
     auto term = [&]() {
@@ -129,13 +138,20 @@ difference_kernel(const In* __restrict__ walls, const In* __restrict__ rocks,
       return x;
     };
     const double f = pairwise_sum(prog, term);
-    const size_t o = (((size_t)e * R + r) * Ph + i0 + i) * Pw + j;
     out[o] = f;
-    if (top) top[o] = h0;
   }
 }
 
 }  // namespace
+
+static int maxplus_into(const float* walls, const float* rocks, const float* level,
+                        float* top, int E, int R, int H, int W, int h, cudaStream_t stream) {
+  return maxplus_f32(walls, rocks, level, top, E, R, H, W, h, 0.f, 1, kNoQuantumHint, stream);
+}
+static int maxplus_into(const uint8_t* walls, const uint8_t* rocks, const uint8_t* level,
+                        double* top, int E, int R, int H, int W, int h, cudaStream_t stream) {
+  return maxplus_u8(walls, rocks, level, top, E, R, H, W, h, stream);
+}
 
 template <typename In>
 static int difference_weights_t(const In* rocks, const In* level, double* weights, int E,
@@ -188,11 +204,23 @@ static int difference_t(const In* walls, const In* rocks, const In* level,
   prog.n_ops = 0;
   build_prog(0, h * h, prog);
   const size_t smem = smem_for(band);
-  SRL_CUDA(cudaFuncSetAttribute(difference_kernel<In>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  difference_kernel<In><<<E * R * nbands, 128, smem, stream>>>(
-      walls, rocks, level, weights, out, top, R, H, W, h, band, nbands,
-      difference_exponent, prog);
+  if (top != nullptr) {
+    // h0 is the height() map: the max-plus kernels compute it much faster than a
+    // per-thread scalar pass (and with the same bits).
+    int rc = maxplus_into(walls, rocks, level, top, E, R, H, W, h, stream);
+    if (rc != SRL_OK) return rc;
+    SRL_CUDA(cudaFuncSetAttribute(difference_kernel<In, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    difference_kernel<In, true><<<E * R * nbands, 128, smem, stream>>>(
+        walls, rocks, level, weights, out, top, R, H, W, h, band, nbands,
+        difference_exponent, prog);
+  } else {
+    SRL_CUDA(cudaFuncSetAttribute(difference_kernel<In, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    difference_kernel<In, false><<<E * R * nbands, 128, smem, stream>>>(
+        walls, rocks, level, weights, out, top, R, H, W, h, band, nbands,
+        difference_exponent, prog);
+  }
   return check_launch("difference_kernel");
 }
 
