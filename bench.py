@@ -198,6 +198,8 @@ def run_reference(args, rank, world):
 def _time_loop(torch, fn, steps):
   ev0 = torch.cuda.Event(enable_timing=True)
   ev1 = torch.cuda.Event(enable_timing=True)
+  for k in range(3):                  # warm-up: lazy module loads, allocator
+    fn(k)
   torch.cuda.synchronize()
   ev0.record()
   for k in range(steps):
