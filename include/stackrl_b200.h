@@ -188,6 +188,20 @@ SRL_API int srl_correlate_f32(const float* walls, const float* rocks, const floa
                               float* corr, float* coef, int E, int R, int H, int W, int h,
                               srl_stream_t stream);
 
+/* ---- the Siamese correlation layer of the DQN ------------------
+ * Replaces stackrl.nets.correlation (nets/layers.py:21-38; called from
+ * nets/models.py:89 and :182), i.e. per sample
+ *   tf.nn.conv2d(x[b][None], w[b][..., None], strides=1, padding='VALID'):
+ *   out[b,i,j] = sum_{u,v,c} x[b,i+u,j+v,c] * w[b,u,v,c]
+ * x [B,H,W,C], w [B,h,wd,C] float32 channels-last (the reference's tensor layout),
+ * out [B,H-h+1,W-wd+1] (the reference's trailing unit channel is a view).  float32
+ * products and accumulation (float64 across input rows); inputs must be finite.
+ * Matched to a tolerance (1e-5 of the largest output): TensorFlow's own summation
+ * order is outside the reference tree. */
+SRL_API int srl_siam_correlation_f32(const float* x, const float* w, float* out, int B,
+                                     int H, int W, int C, int h, int wd,
+                                     srl_stream_t stream);
+
 /* corrcoef(localized=True) (baselines.py:87-114): the masked variant, every sum in
  * numpy's pairwise order and in the observation's arithmetic type (float32, or
  * float64 for uint8): bit-exact.  work: caller-owned scratch of

@@ -18,6 +18,8 @@ Contents
                    (rewarder.py:162-179, 297-307).
   raster_np.py     software z-buffer standing in for pybullet's TinyRenderer
                    (NOT in the reference tree: raster parity is UNPINNED).
+  nets_np.py       numpy restatement of the Siamese correlation layer
+                   (nets/layers.py:21-38; PARITY UNPINNED against TensorFlow).
   fake_pybullet.py duck-typed pybullet camera API + static bodies around it.
   csrc/            plain-C restatement of the same arithmetic for sizes the
                    numpy versions are too slow for (built to oracle/_build/).

@@ -56,6 +56,7 @@ _SIGNATURES = {
   'srl_corrcoef_localized_f32': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
   'srl_corrcoef_localized_u8': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
   'srl_correlate_f32': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+  'srl_siam_correlation_f32': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
   'srl_raster': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_reward_sums_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
   'srl_pack_obs': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_float, _I, _P]),
@@ -395,6 +396,26 @@ def score_f32(walls, goals, rocks, level=None, level_mode=2, minorder=1,
                              int(level_mode), int(minorder), float(overlap_threshold),
                              _stream()))
   return values, actions, best
+
+
+def siam_correlation_f32(x, w, out=None):
+  """Siamese correlation layer (nets/layers.py:21-38): x [B,H,W,C], w [B,h,wd,C]
+  float32 channels-last -> [B,H-h+1,W-wd+1,1] float32 (per-sample VALID cross-
+  correlation summed over the channels)."""
+  if x.dim() != 4 or w.dim() != 4 or x.shape[0] != w.shape[0] or x.shape[3] != w.shape[3]:
+    raise ValueError('correlation expects [B,H,W,C] and [B,h,w,C], got {} and {}'.format(
+      tuple(x.shape), tuple(w.shape)))
+  B, H, W, C = x.shape
+  h, wd = w.shape[1], w.shape[2]
+  if h > H or wd > W:
+    raise ValueError('the second input must not be larger than the first')
+  args = (_dev(x, torch.float32, 'x'), _dev(w, torch.float32, 'w'))
+  if out is None:
+    out = torch.empty((B, H - h + 1, W - wd + 1, 1), dtype=torch.float32, device=x.device)
+  with torch.cuda.device(x.device):
+    _check(lib.srl_siam_correlation_f32(*args, _dev(out, torch.float32, 'out'),
+                                        B, H, W, C, h, wd, _stream()))
+  return out
 
 
 def correlate_f32(walls, rocks, level=None, want_corr=True, want_coef=True):

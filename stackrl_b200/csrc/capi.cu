@@ -214,6 +214,11 @@ int srl_correlate_f32(const float* walls, const float* rocks, const float* level
                             (cudaStream_t)stream);
 }
 
+int srl_siam_correlation_f32(const float* x, const float* w, float* out, int B, int H, int W,
+                             int C, int h, int wd, srl_stream_t stream) {
+  return srl::siam_correlation_f32(x, w, out, B, H, W, C, h, wd, (cudaStream_t)stream);
+}
+
 int srl_microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   return srl::microbench_addmax(variant, iters, host_cells_per_s);
 }

@@ -82,6 +82,9 @@ int score_f32(const float* walls, const float* goals, const float* rocks, const 
 int correlate_f32(const float* walls, const float* rocks, const float* level, float* corr,
                   float* coef, int E, int R, int H, int W, int h, cudaStream_t stream);
 
+int siam_correlation_f32(const float* x, const float* w, float* out, int B, int H, int W,
+                         int C, int h, int wd, cudaStream_t stream);
+
 int microbench_addmax(int variant, int iters, double* host_cells_per_s);
 
 }  // namespace srl

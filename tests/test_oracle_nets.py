@@ -1,0 +1,32 @@
+"""Oracle of the Siamese correlation layer (stackrl/nets/layers.py:21-38) against the
+definition of tf.nn.conv2d(VALID) written as loops and against scipy's correlate2d
+(CPU; TensorFlow itself is not installable here: parity unpinned, see oracle/nets_np.py)."""
+import numpy as np
+import pytest
+from scipy import signal
+
+from oracle import nets_np
+
+
+@pytest.mark.parametrize('shape', [(2, 9, 11, 3, 4, 5), (1, 8, 8, 1, 8, 8), (3, 12, 7, 5, 1, 1)])
+def test_einsum_form_equals_loops_and_scipy(shape):
+  B, H, W, C, h, w = shape
+  rng = np.random.default_rng(11)
+  x = rng.standard_normal((B, H, W, C)).astype('float32')
+  f = rng.standard_normal((B, h, w, C)).astype('float32')
+  got = nets_np.correlation(x, f)
+  assert got.shape == (B, H - h + 1, W - w + 1, 1)
+  np.testing.assert_allclose(got, nets_np.correlation_loops(x, f), rtol=0, atol=1e-12)
+  for b in range(B):
+    ref = sum(signal.correlate2d(x[b, :, :, c].astype('float64'), f[b, :, :, c].astype('float64'),
+                                 mode='valid') for c in range(C))
+    np.testing.assert_allclose(got[b, :, :, 0], ref, rtol=0, atol=1e-12)
+
+
+def test_known_answer():
+  # one channel, 3x3 ramp with a 2x2 filter of ones = 2x2 box sums; no kernel flip
+  x = np.arange(9, dtype='float32').reshape(1, 3, 3, 1)
+  f = np.ones((1, 2, 2, 1), dtype='float32')
+  np.testing.assert_array_equal(nets_np.correlation(x, f)[0, :, :, 0], [[8, 12], [20, 24]])
+  f[0, 0, 0, 0] = 0                      # drops the top-left pixel of every window
+  np.testing.assert_array_equal(nets_np.correlation(x, f)[0, :, :, 0], [[8, 11], [17, 20]])
