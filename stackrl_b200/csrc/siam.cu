@@ -26,6 +26,10 @@
 // Inputs must be finite: the zero filter rows / zero-padded filter columns multiply
 // pixels one step outside the window (0 * inf would give NaN where the reference
 // gives a finite value).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -35,7 +39,7 @@ namespace {
 
 constexpr int kSiamTI = 2;      // output rows per thread
 constexpr int kSiamTJ = 8;      // output columns per thread
-constexpr int kSiamMaxThreads = 256;
+constexpr int kSiamMaxThreads = 384;
 
 struct SiamParams {
   const float* x;     // [B, H, W, C]
@@ -212,27 +216,51 @@ int siam_correlation_f32(const float* x, const float* w, float* out, int B, int 
   p.H = H; p.W = W; p.C = C; p.h = h; p.wd = wd;
   p.Ph = H - h + 1; p.Pw = W - wd + 1;
   p.wdp = (wd + 7) & ~7;
-  const int max_bj = 13 * kSiamTJ;                  // 104 columns: 13 column groups
-  p.nbj = (p.Pw + max_bj - 1) / max_bj;
-  p.BJ = (((p.Pw + p.nbj - 1) / p.nbj) + kSiamTJ - 1) / kSiamTJ * kSiamTJ;
+  // Tile search: a CTA covers ceil(Ph/nbi) rows x ceil(Pw/nbj) columns (rounded to the
+  // thread tile) with one thread per 2x8 outputs.  Every thread does the same work, so
+  // a launch costs (waves of CTAs) x (warps per SM sub-partition); ties go to the
+  // smaller halo.  The patch of the tile must fit shared memory.
+  const size_t filt = (size_t)(h + 2) * p.wdp * 16;
+  auto band = [&](int n, int parts, int unit) { return (((n + parts - 1) / parts) + unit - 1) / unit * unit; };
+  int force_bi = 0, force_bj = 0;
+  if (const char* t = getenv("SRL_SIAM_TILE")) sscanf(t, "%d,%d", &force_bi, &force_bj);   // tuning override
+  double best = 1e300;
+  int best_nbi = 0, best_nbj = 0;
+  for (int nbj = 1; nbj <= (p.Pw + kSiamTJ - 1) / kSiamTJ; ++nbj) {
+    const int BJ = band(p.Pw, nbj, kSiamTJ), ncg = BJ / kSiamTJ;
+    if ((p.Pw + BJ - 1) / BJ != nbj || ncg > kSiamMaxThreads) continue;
+    const int cols_in = BJ + p.wdp - 1, xpitch = cols_in + (cols_in >> 3) + 1;
+    for (int nbi = 1; nbi <= (p.Ph + kSiamTI - 1) / kSiamTI; ++nbi) {
+      const int BI = band(p.Ph, nbi, kSiamTI);
+      if ((p.Ph + BI - 1) / BI != nbi) continue;
+      const int threads = (BI / kSiamTI) * ncg;
+      const size_t smem = (size_t)(BI + h - 1) * xpitch * 16 + filt;
+      if (threads > kSiamMaxThreads || smem > 220 * 1024) continue;
+      const int warps = (threads + 31) / 32;
+      const size_t ctas = (size_t)B * nbi * nbj;
+      const int per_sm = (int)std::min<size_t>((220 * 1024) / smem, (size_t)(kSiamMaxThreads / (warps * 32)));
+      const double waves = (double)((ctas + (size_t)sms * per_sm - 1) / ((size_t)sms * per_sm));
+      const double rounds = (double)((warps * per_sm + 3) / 4);
+      const double halo = (double)(BI + h - 1) * cols_in / ((double)BI * BJ);
+      double cost = waves * rounds * (1. + 0.02 * halo);
+      if (force_bi) cost = (nbi == force_bi && nbj == force_bj) ? 0. : 1e299;
+      if (cost < best) {
+        best = cost;
+        best_nbi = nbi;
+        best_nbj = nbj;
+      }
+    }
+  }
+  SRL_REQUIRE(best_nbi > 0, SRL_E_UNSUPPORTED,
+              "siam_correlation: a %dx%d filter on %d-column rows exceeds shared memory", h, wd,
+              W);
+  p.nbi = best_nbi; p.nbj = best_nbj;
+  p.BJ = band(p.Pw, p.nbj, kSiamTJ);
   p.ncg = p.BJ / kSiamTJ;
   p.cols_in = p.BJ + p.wdp - 1;
   p.xpitch = p.cols_in + (p.cols_in >> 3) + 1;
-  const size_t filt = (size_t)(h + 2) * p.wdp * 16;
+  p.BI = band(p.Ph, p.nbi, kSiamTI);
   auto smem_for = [&](int bi) { return (size_t)(bi + h - 1) * p.xpitch * 16 + filt; };
-  int bi_max = kSiamTI * (kSiamMaxThreads / p.ncg);
-  while (bi_max > kSiamTI && smem_for(bi_max) > 220 * 1024) bi_max -= kSiamTI;
-  SRL_REQUIRE(smem_for(bi_max) <= 220 * 1024, SRL_E_UNSUPPORTED,
-              "siam_correlation: a %dx%d filter on %d-column rows exceeds shared memory", h, wd,
-              W);
-  p.nbi = (p.Ph + bi_max - 1) / bi_max;
-  auto band = [&](int nbi) { return (((p.Ph + nbi - 1) / nbi) + kSiamTI - 1) / kSiamTI * kSiamTI; };
-  // small batches: more, shorter bands as long as the grid stays within one wave of
-  // CTAs (the tiles are one CTA per SM; the halo rows are re-staged per band, so not
-  // below 8 rows)
-  while ((size_t)B * (p.nbi + 1) * p.nbj <= (size_t)sms && band(p.nbi + 1) >= 8) ++p.nbi;
-  p.BI = band(p.nbi);
-  p.nbi = (p.Ph + p.BI - 1) / p.BI;
   p.rows_in = p.BI + h - 1;
   const size_t smem = smem_for(p.BI);
   int threads = (p.BI / kSiamTI) * p.ncg;
