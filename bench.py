@@ -269,6 +269,25 @@ def extra_metrics(torch, dev):
     'maxplus_fixed_point_ms': ms_q, 'maxplus_fixed_point_evals_per_s': evals / (ms_q * 1e-3),
     'maxplus_float_ms': ms_f, 'bit_identical_to_float_sweep': bool(same),
     'scorer_ms': ms_s, 'scorer_evals_per_s': evals / (ms_s * 1e-3)}
+  # -- the DQN's Siamese correlation layer (nets/layers.py:21-38) -- #
+  Bs, Cs, Hs, hs = 148, 16, 128, 32        # config.gin:55 geometry; 148 samples = whole waves
+  gen = torch.Generator(device=dev).manual_seed(0)
+  xs = torch.randn((Bs, Hs, Hs, Cs), device=dev, generator=gen)
+  fs = torch.randn((Bs, hs, hs, Cs), device=dev, generator=gen)
+  os_ = torch.empty((Bs, Hs - hs + 1, Hs - hs + 1, 1), device=dev)
+  ms_c = _time_loop(torch, lambda _: capi.siam_correlation_f32(xs, fs, out=os_), 10)
+  flops = 2.0 * Bs * (Hs - hs + 1) ** 2 * hs * hs * Cs
+  fma_peak = 2 * max(capi.microbench_fma(v, 400) for v in (0, 1, 2)) / 1e12
+  out['siam_correlation'] = {
+    'workload': '{} samples, {}x{}x{} wall features * {}x{}x{} rock features, float32 '
+                '(stackrl.nets.correlation, config.gin geometry)'.format(Bs, Hs, Hs, Cs, hs, hs, Cs),
+    'ms': ms_c, 'samples_per_s': Bs / (ms_c * 1e-3),
+    'roofline': {'bound': 'fp32-fma', 'achieved': flops / (ms_c * 1e-3) / 1e12,
+                 'peak': fma_peak, 'unit': 'TFLOP/s',
+                 'frac': flops / (ms_c * 1e-3) / 1e12 / fma_peak,
+                 'peak_source': 'srl_microbench_fma, best of FFMA / FFMA2 measured in this run '
+                                '(nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4)'}}
+  del xs, fs, os_
   # -- config 4 slice: env observations, 64x64 wall, 16x16 rock ----------------- #
   E = 4096
   bank2 = meshes.MeshBank()

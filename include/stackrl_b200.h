@@ -274,6 +274,9 @@ SRL_API int srl_pack_obs(const float* walls, const float* goals, const float* ro
  * full-chip grid and reports cells/s.  variant 0: FADD+FMNMX, 1: FADD+FMNMX3,
  * 2: FADD2+FMNMX3 (the kernel's mix).  Synchronises the device. */
 SRL_API int srl_microbench_addmax(int variant, int iters, double* host_cells_per_s);
+/* FP32 FMA issue rate (0 FFMA, 1 FFMA2 with a shared multiplicand like the
+ * correlation kernel, 2 FFMA2 with distinct operands): FMAs per second. */
+SRL_API int srl_microbench_fma(int variant, int iters, double* host_fma_per_s);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,7 @@ _SIGNATURES = {
   'srl_reward_sums_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
   'srl_pack_obs': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_float, _I, _P]),
   'srl_microbench_addmax': (_I, [_I, _I, _c.POINTER(_c.c_double)]),
+  'srl_microbench_fma': (_I, [_I, _I, _c.POINTER(_c.c_double)]),
 }
 
 for _name, (_res, _args) in _SIGNATURES.items():
@@ -437,4 +438,12 @@ def microbench_addmax(variant, iters=2000):
   """(add, max) cells per second of the issue-rate micro-benchmark."""
   v = _c.c_double(0.)
   _check(lib.srl_microbench_addmax(int(variant), int(iters), ctypes.byref(v)))
+  return v.value
+
+
+def microbench_fma(variant, iters=2000):
+  """FP32 FMAs per second of the FMA micro-benchmark (0 FFMA, 1 FFMA2 with a shared
+  multiplicand, 2 FFMA2 with distinct operands)."""
+  v = ctypes.c_double(0.)
+  _check(lib.srl_microbench_fma(int(variant), int(iters), ctypes.byref(v)))
   return v.value

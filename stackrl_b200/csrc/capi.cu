@@ -223,4 +223,8 @@ int srl_microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   return srl::microbench_addmax(variant, iters, host_cells_per_s);
 }
 
+int srl_microbench_fma(int variant, int iters, double* host_fma_per_s) {
+  return srl::microbench_fma(variant, iters, host_fma_per_s);
+}
+
 }  // extern "C"

@@ -87,4 +87,6 @@ int siam_correlation_f32(const float* x, const float* w, float* out, int B, int 
 
 int microbench_addmax(int variant, int iters, double* host_cells_per_s);
 
+int microbench_fma(int variant, int iters, double* host_fma_per_s);
+
 }  // namespace srl

@@ -192,6 +192,75 @@ done:
   out[tid] = r;
 }
 
+
+// ---- FP32 FMA issue rate (roofline denominator of siam_correlation_kernel) ----- //
+// VARIANT 0: FFMA, three 32-bit register operands | 1: FFMA2 (fma.rn.f32x2) in the
+// kernel's pattern: 8 consecutive instructions share one multiplicand pair
+// (operand-reuse cache) | 2: FFMA2 with three distinct register pairs.
+__device__ __forceinline__ unsigned long long vfma2(unsigned long long a, unsigned long long b,
+                                                    unsigned long long c) {
+  unsigned long long d;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float vfma(float a, float b, float c) {
+  float d;
+  asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256) fma_kernel(const float* in, float* out, int iters) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long acc[16], x[8], w[2];
+  float accf[32], xf[8], wf[4];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) acc[t] = pack2(in[(tid + t) & 1023], in[(tid + 2 * t + 1) & 1023]);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) x[t] = pack2(in[(tid * 3 + t) & 1023], in[(tid * 5 + t) & 1023]);
+  w[0] = pack2(in[tid & 1023] * 1e-3f, in[(tid + 7) & 1023] * 1e-3f);
+  w[1] = pack2(in[(tid + 9) & 1023] * 1e-3f, in[(tid + 11) & 1023] * 1e-3f);
+#pragma unroll
+  for (int t = 0; t < 32; ++t) accf[t] = in[(tid + t) & 1023];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) xf[t] = in[(tid * 3 + t) & 1023];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) wf[t] = in[(tid + 13 * t) & 1023] * 1e-3f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if constexpr (VARIANT == 0) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) accf[t] = vfma(xf[t & 7], wf[(t >> 3) & 3], accf[t]);
+      } else if constexpr (VARIANT == 1) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc[t] = vfma2(x[t & 7], w[t >> 3], acc[t]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc[t] = vfma2(x[t & 7], acc[(t + 8) & 15], acc[t]);
+      }
+    }
+  }
+  float r = 0.f;
+  if constexpr (VARIANT == 0) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) r += accf[t];
+  } else {
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      float lo, hi;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[t]));
+      r += lo + hi;
+    }
+  }
+  out[tid] = r;
+}
+
 }  // namespace
 
 int microbench_addmax(int variant, int iters, double* host_cells_per_s) {
@@ -235,6 +304,43 @@ int microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   if (variant == 6 || variant == 14) cells *= 0.5;
   if (variant == 17) cells *= 2.0;   // two (add, max) cells per instruction   // one FADD2 per two (v, t) steps
   *host_cells_per_s = cells / (best_ms * 1e-3);
+  return SRL_OK;
+}
+
+int microbench_fma(int variant, int iters, double* host_fma_per_s) {
+  SRL_REQUIRE(host_fma_per_s != nullptr && iters > 0 && variant >= 0 && variant <= 2,
+              SRL_E_INVALID, "microbench_fma: bad arguments");
+  const int sms = sm_count();
+  SRL_REQUIRE(sms > 0, SRL_E_CUDA, "microbench_fma: no device");
+  const int threads = 256, blocks = sms * 4;
+  float *in = nullptr, *out = nullptr;
+  SRL_CUDA(cudaMalloc(&in, 1024 * sizeof(float)));
+  SRL_CUDA(cudaMalloc(&out, (size_t)blocks * threads * sizeof(float)));
+  float host_in[1024];
+  for (int k = 0; k < 1024; ++k) host_in[k] = (float)((k * 37) % 101) * 0.01f;
+  SRL_CUDA(cudaMemcpy(in, host_in, sizeof(host_in), cudaMemcpyHostToDevice));
+  cudaEvent_t t0, t1;
+  SRL_CUDA(cudaEventCreate(&t0));
+  SRL_CUDA(cudaEventCreate(&t1));
+  float best_ms = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {   // rep 0 is the warm-up
+    SRL_CUDA(cudaEventRecord(t0));
+    if (variant == 0) fma_kernel<0><<<blocks, threads>>>(in, out, iters);
+    else if (variant == 1) fma_kernel<1><<<blocks, threads>>>(in, out, iters);
+    else fma_kernel<2><<<blocks, threads>>>(in, out, iters);
+    SRL_CUDA(cudaEventRecord(t1));
+    SRL_CUDA(cudaEventSynchronize(t1));
+    float ms = 0;
+    SRL_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+    if (rep > 0 && ms < best_ms) best_ms = ms;
+  }
+  int rc = check_launch("fma_kernel");
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaFree(in);
+  cudaFree(out);
+  if (rc != SRL_OK) return rc;
+  *host_fma_per_s = (double)blocks * threads * (double)iters * 4 * 32 / (best_ms * 1e-3);
   return SRL_OK;
 }
 
