@@ -269,6 +269,25 @@ def extra_metrics(torch, dev):
     'maxplus_fixed_point_ms': ms_q, 'maxplus_fixed_point_evals_per_s': evals / (ms_q * 1e-3),
     'maxplus_float_ms': ms_f, 'bit_identical_to_float_sweep': bool(same),
     'scorer_ms': ms_s, 'scorer_evals_per_s': evals / (ms_s * 1e-3)}
+  # -- config 2 shapes as uint8 observations (the dtype of the registered Stack-v0/1/2
+  #    environments, env.py:171-178): device-resident and end to end from host memory -- #
+  w8 = torch.from_numpy(synth.to_dtype(walls_h, 'uint8')).to(dev)
+  r8 = torch.from_numpy(synth.to_dtype(rocks_h, 'uint8')).to(dev)
+  g8 = torch.from_numpy(synth.to_dtype(synth.goals(7, E, H, W), 'uint8')).to(dev)
+  scorer8 = baselines.PlacementScorer('height')
+  ms_8 = _time_loop(torch, lambda _: scorer8(w8, g8, r8), 30)
+  pipe8 = baselines.HostPipeline(scorer8, E, R, H, W, h, chunks=4, device=dev, dtype=torch.uint8)
+  pipe8.stage(w8.cpu().numpy(), g8.cpu().numpy(), r8.cpu().numpy())
+  ms_8e = _time_loop(torch, lambda _: pipe8.run(), 20)
+  same8 = bool(np.array_equal(pipe8.run()[0], scorer8(w8, g8, r8)['actions'].cpu().numpy()))
+  out['uint8_observations'] = {
+    'workload': 'C2 shapes cast like StackEnv._return (uint8, goal level 170): float64 '
+                'max-plus values through the integer-key sweep + goal mask + arg-min',
+    'scorer_ms': ms_8, 'scorer_evals_per_s': evals / (ms_8 * 1e-3),
+    'e2e_ms': ms_8e, 'e2e_evals_per_s': evals / (ms_8e * 1e-3),
+    'h2d_bytes_per_step': pipe8.h2d_bytes, 'd2h_bytes_per_step': pipe8.d2h_bytes,
+    'host_pipeline_matches_device': same8}
+  del w8, r8, g8, pipe8
   # -- the DQN's Siamese correlation layer (nets/layers.py:21-38) -- #
   Bs, Cs, Hs, hs = 148, 16, 128, 32        # config.gin:55 geometry; 148 samples = whole waves
   gen = torch.Generator(device=dev).manual_seed(0)

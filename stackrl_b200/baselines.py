@@ -270,24 +270,28 @@ class HostPipeline(object):
   only the actions / batch-wise picks travel back.  This is the end-to-end call
   bench.py times (``e2e``): numpy in, numpy out."""
 
-  def __init__(self, scorer, envs, rotations, H, W, h, chunks=4, device=None):
+  def __init__(self, scorer, envs, rotations, H, W, h, chunks=4, device=None,
+               dtype=torch.float32):
+    """``dtype``: observation dtype, float32 or uint8 (the dtype of the registered
+    Stack-v0/1/2 environments, env.py:171-178: a quarter of the bytes per step)."""
+    if dtype not in (torch.float32, torch.uint8):
+      raise TypeError('observations must be float32 or uint8, got {}'.format(dtype))
     self.scorer = scorer
     self.dev = device if device is not None else _device()
     self.E, self.R = int(envs), int(rotations)
     self.bounds = [(k * self.E // chunks, (k + 1) * self.E // chunks) for k in range(chunks)]
     self.bounds = [b for b in self.bounds if b[1] > b[0]]
-    f32 = torch.float32
     self.pin = {
-      'walls': torch.empty((self.E, H, W), dtype=f32).pin_memory(),
-      'goals': torch.empty((self.E, H, W), dtype=f32).pin_memory(),
-      'rocks': torch.empty((self.E, self.R, h, h), dtype=f32).pin_memory(),
+      'walls': torch.empty((self.E, H, W), dtype=dtype).pin_memory(),
+      'goals': torch.empty((self.E, H, W), dtype=dtype).pin_memory(),
+      'rocks': torch.empty((self.E, self.R, h, h), dtype=dtype).pin_memory(),
     }
-    self.dev_in = {k: torch.empty(v.shape, dtype=f32, device=self.dev)
+    self.dev_in = {k: torch.empty(v.shape, dtype=dtype, device=self.dev)
                    for k, v in self.pin.items()}
     self.actions = torch.empty((self.E, self.R), dtype=torch.int64).pin_memory()
     self.best = torch.empty((self.E, 2), dtype=torch.int64).pin_memory()
     self.copy_stream = torch.cuda.Stream(device=self.dev)
-    self.h2d_bytes = sum(v.numel() * 4 for v in self.pin.values())
+    self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.pin.values())
     self.d2h_bytes = (self.actions.numel() + self.best.numel()) * 8
 
   def stage(self, walls, goals, rocks):

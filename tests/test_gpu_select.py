@@ -244,3 +244,30 @@ def test_placement_scorer_difference_batched(B, dtype):
       batchwise=True)
     assert tuple(out['best'][e].cpu().numpy()) == (k, idx)
     assert np.array_equal(out['shown'][e].cpu().numpy().reshape(R, -1), v)
+
+
+@pytest.mark.parametrize('dtype', ['float32', 'uint8'])
+@pytest.mark.parametrize('envs,chunks', [(10, 4), (3, 4), (1, 1)])
+def test_host_pipeline_equals_oracle(B, dtype, envs, chunks):
+  """numpy observations in, numpy actions out (the call bench.py times as `e2e`):
+  chunked copies overlapping the kernels give the oracle's picks, for float32 and
+  for the uint8 observations of the registered environments; ragged chunking
+  (fewer environments than chunks) included."""
+  E, R, H, W, h = envs, 8, 32, 32, 16
+  walls, rocks, _ = synth.placement_batch(41, E, R, H, W, h)
+  goals = synth.goals(42, E, H, W)
+  walls, goals, rocks = (synth.to_dtype(x, dtype) for x in (walls, goals, rocks))
+  pipe = B.HostPipeline(B.PlacementScorer(), E, R, H, W, h, chunks=chunks,
+                        dtype=getattr(torch, dtype))
+  assert pipe.h2d_bytes == (walls.nbytes + goals.nbytes + rocks.nbytes)
+  for _ in range(2):                       # staging buffers are reused
+    actions, best = pipe(walls, goals, rocks)
+    for e in range(E):
+      wg = np.stack([walls[e], goals[e]], -1)
+      obs = (np.stack([wg] * R), rocks[e][..., None])
+      k, idx = S.greedy(obs, lambda o: S.baseline_call(o, method='height'),
+                        batched=True, batchwise=True)
+      assert (best[e, 0], best[e, 1]) == (k, idx)
+      assert actions[e, k] == idx
+  with pytest.raises(TypeError):
+    B.HostPipeline(B.PlacementScorer(), E, R, H, W, h, dtype=torch.float64)
