@@ -337,6 +337,29 @@ def extra_metrics(torch, dev):
                 'float32 obs + IoU terms'.format(E, len(t2)),
     'obs_per_s': E / (ms * 1e-3), 'ms': ms,
     'full_step_ms_with_host_glue': step_ms, 'full_steps_per_s': E / (step_ms * 1e-3)}
+  # -- last (a failed capture must not disturb anything above): the host pipeline
+  #    replayed as ONE CUDA graph per step, float32 and uint8 ------------------------ #
+  try:
+    E, R, H, W, h = (CFG[k] for k in ('envs', 'rotations', 'H', 'W', 'h'))
+    walls_h, rocks_h, _ = synth.placement_batch(0, E, R, H, W, h)
+    goals_h = synth.goals(7, E, H, W)
+    res = {}
+    for name, dt in (('float32', torch.float32), ('uint8', torch.uint8)):
+      obs = [synth.to_dtype(x, name) for x in (walls_h, goals_h, rocks_h)]
+      pipe = baselines.HostPipeline(baselines.PlacementScorer('height'), E, R, H, W, h,
+                                    chunks=4, device=dev, dtype=dt)
+      pipe.stage(*obs)
+      eager = pipe.run()[0].copy()
+      ms_e = _time_loop(torch, lambda _: pipe.run(), 20)
+      pipe.capture()
+      ms_g = _time_loop(torch, lambda _: pipe.run(), 20)
+      res[name] = {'eager_ms': ms_e, 'graph_ms': ms_g,
+                   'graph_evals_per_s': evals_per_step() / (ms_g * 1e-3),
+                   'same_actions': bool(np.array_equal(eager, pipe.run()[0]))}
+      del pipe
+    out['host_pipeline_cuda_graph'] = res
+  except Exception as exc:
+    out['host_pipeline_cuda_graph'] = {'error': repr(exc)}
   return out
 
 

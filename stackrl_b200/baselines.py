@@ -291,6 +291,7 @@ class HostPipeline(object):
     self.actions = torch.empty((self.E, self.R), dtype=torch.int64).pin_memory()
     self.best = torch.empty((self.E, 2), dtype=torch.int64).pin_memory()
     self.copy_stream = torch.cuda.Stream(device=self.dev)
+    self.graph = None
     self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.pin.values())
     self.d2h_bytes = (self.actions.numel() + self.best.numel()) * 8
 
@@ -300,11 +301,9 @@ class HostPipeline(object):
     self.pin['goals'].numpy()[...] = goals
     self.pin['rocks'].numpy()[...] = rocks
 
-  def run(self):
-    """Score the staged batch: H2D per chunk -> max-plus, goal overlap, select
-    -> D2H of actions.  Returns (actions [E,R], best [E,2]) numpy views after a
-    full synchronise."""
-    main = torch.cuda.current_stream(self.dev)
+  def _enqueue(self, main):
+    """One step's copies and kernels on ``main`` (+ the copy stream, forked from
+    and joined back into ``main``)."""
     self.copy_stream.wait_stream(main)
     ready = []
     with torch.cuda.stream(self.copy_stream):
@@ -320,6 +319,32 @@ class HostPipeline(object):
                         self.dev_in['rocks'][lo:hi])
       self.actions[lo:hi].copy_(out['actions'], non_blocking=True)
       self.best[lo:hi].copy_(out['best'], non_blocking=True)
+
+  def capture(self):
+    """Record one step (every copy and kernel of ``run``) into a CUDA graph; later
+    ``run`` calls replay it with ONE launch instead of ~10 per chunk, which is what
+    bounds small or uint8 batches (the staging buffers are fixed, so the graph's
+    addresses stay valid).  Call after at least one eager ``run`` (kernel attributes
+    and lazy module loads must not happen inside a capture).  Returns self."""
+    stream = torch.cuda.Stream(device=self.dev)
+    stream.wait_stream(torch.cuda.current_stream(self.dev))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+      with torch.cuda.graph(graph, stream=stream):
+        self._enqueue(stream)
+    torch.cuda.current_stream(self.dev).wait_stream(stream)
+    self.graph = graph
+    return self
+
+  def run(self):
+    """Score the staged batch: H2D per chunk -> max-plus, goal overlap, select
+    -> D2H of actions.  Returns (actions [E,R], best [E,2]) numpy views after a
+    full synchronise."""
+    main = torch.cuda.current_stream(self.dev)
+    if self.graph is not None:
+      self.graph.replay()
+    else:
+      self._enqueue(main)
     main.synchronize()
     return self.actions.numpy(), self.best.numpy()
 

@@ -271,3 +271,22 @@ def test_host_pipeline_equals_oracle(B, dtype, envs, chunks):
       assert actions[e, k] == idx
   with pytest.raises(TypeError):
     B.HostPipeline(B.PlacementScorer(), E, R, H, W, h, dtype=torch.float64)
+
+
+@pytest.mark.parametrize('dtype', ['float32', 'uint8'])
+def test_host_pipeline_cuda_graph_replay(B, dtype):
+  """The captured step (one graph launch) gives the eager step's actions, also
+  after the staged observations change (the graph reads the same pinned buffers)."""
+  E, R, H, W, h = 12, 8, 32, 32, 16
+  pipe = B.HostPipeline(B.PlacementScorer(), E, R, H, W, h, chunks=3,
+                        dtype=getattr(torch, dtype))
+  batches = []
+  for seed in (51, 52, 53):
+    walls, rocks, _ = synth.placement_batch(seed, E, R, H, W, h)
+    goals = synth.goals(seed + 100, E, H, W)
+    batches.append([synth.to_dtype(x, dtype) for x in (walls, goals, rocks)])
+  eager = [tuple(a.copy() for a in pipe(*b)) for b in batches]
+  pipe.capture()
+  for b, (actions, best) in zip(batches, eager):
+    got_actions, got_best = pipe(*b)
+    assert np.array_equal(got_actions, actions) and np.array_equal(got_best, best)
