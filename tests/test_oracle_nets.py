@@ -30,3 +30,22 @@ def test_known_answer():
   np.testing.assert_array_equal(nets_np.correlation(x, f)[0, :, :, 0], [[8, 12], [20, 24]])
   f[0, 0, 0, 0] = 0                      # drops the top-left pixel of every window
   np.testing.assert_array_equal(nets_np.correlation(x, f)[0, :, :, 0], [[8, 11], [17, 20]])
+
+
+def test_mirror_has_no_cpu_path():
+  """stackrl_b200.nets.correlation keeps the reference's name and arguments
+  (nets/layers.py:21) and refuses anything that is not a float32 CUDA tensor
+  instead of computing on the host."""
+  import inspect
+  import torch
+  from stackrl_b200 import nets
+  assert list(inspect.signature(nets.correlation).parameters) == [
+    'in0', 'in1', 'parallel_iterations']
+  x = np.zeros((1, 8, 8, 4), dtype='float32')
+  f = np.zeros((1, 3, 3, 4), dtype='float32')
+  with pytest.raises(TypeError):
+    nets.correlation(x, f)
+  with pytest.raises(TypeError):
+    nets.correlation(torch.from_numpy(x), torch.from_numpy(f))
+  with pytest.raises(TypeError):
+    nets.correlation(torch.from_numpy(x).double(), torch.from_numpy(f).double())
