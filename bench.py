@@ -493,7 +493,7 @@ def run_graft(args, rank, local_rank, world):
 
   # ---- end to end: host buffers in, host actions out ------------------------------ #
   scorer = baselines.PlacementScorer('height')
-  pipe = baselines.HostPipeline(scorer, E, R, H, W, h, chunks=4, device=dev)
+  pipe = baselines.HostPipeline(scorer, E, R, H, W, h, chunks=8, device=dev)
   pipe.stage(walls_h, goals_h, rocks_h)
   e2e_steps = max(3, min(args.steps, 30))
   for _ in range(3):
