@@ -217,8 +217,8 @@ def extra_metrics(torch, dev):
   from stackrl_b200.camera import ObserverGeometry
   out = {}
   # -- config 3: 4096 synthetic rocks, 32x32 px at 0.005 m/px ------------------- #
-  n, sub = 4096, 3
-  verts, tris = meshes.synthetic_rocks(4, n, sub, max_dimension=0.16)
+  n = 4096
+  verts, tris = meshes.synthetic_rocks(4, n, max_dimension=0.16, frequency=10)   # ~2k tris
   bank = meshes.MeshBank()
   for k in range(n):
     bank.add(verts[k], tris)

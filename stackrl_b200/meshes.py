@@ -88,13 +88,44 @@ def icosphere(subdivisions):
   return np.asarray(verts, dtype='float64'), np.asarray(faces, dtype='int32')
 
 
-def synthetic_rocks(seed, count, subdivisions=3, max_dimension=0.16, smooth=0.6):
+def geodesic_icosphere(frequency):
+  """Unit class-I geodesic sphere: every icosahedron face cut into frequency^2
+  triangles (20 f^2 triangles, 10 f^2 + 2 vertices; f = 10 gives the 2 000
+  triangles / 1 002 vertices of BASELINE config 3)."""
+  base, faces = icosphere(0)
+  f = int(frequency)
+  index, verts, tris = {}, [], []
+
+  def vertex(a, b, c, i, j):
+    # barycentric grid point of face (a, b, c); the key is the same for both faces
+    # that share an edge or a corner
+    w = sorted(((a, f - i - j), (b, i), (c, j)))
+    key = tuple((n, k) for n, k in w if k)
+    if key not in index:
+      p = ((f - i - j) * base[a] + i * base[b] + j * base[c]) / f
+      verts.append(p / np.linalg.norm(p))
+      index[key] = len(verts) - 1
+    return index[key]
+  for a, b, c in faces:
+    for i in range(f):
+      for j in range(f - i):
+        tris.append((vertex(a, b, c, i, j), vertex(a, b, c, i + 1, j), vertex(a, b, c, i, j + 1)))
+        if i + j < f - 1:
+          tris.append((vertex(a, b, c, i + 1, j), vertex(a, b, c, i + 1, j + 1),
+                       vertex(a, b, c, i, j + 1)))
+  return np.asarray(verts, dtype='float64'), np.asarray(tris, dtype='int32')
+
+
+def synthetic_rocks(seed, count, subdivisions=3, max_dimension=0.16, smooth=0.6,
+                    frequency=None):
   """``count`` star-convex rocks: an icosphere whose
   vertices are pushed radially by a seeded triangular(0.1, 0.4, 1.0) factor
   blended with a per-rock ellipsoid, scaled to fit a ball of ``max_dimension``.
-  subdivisions=3 gives 1280 triangles / 642 vertices, 4 gives 5120 / 2562.
+  subdivisions=3 gives 1280 triangles / 642 vertices, 4 gives 5120 / 2562;
+  ``frequency`` (overrides ``subdivisions``) uses the geodesic sphere instead:
+  frequency=10 gives config 3's 2 000 triangles / 1 002 vertices.
   Returns (verts [count, V, 3] float32, tris [T, 3] int32 shared by all)."""
-  base, tris = icosphere(subdivisions)
+  base, tris = geodesic_icosphere(frequency) if frequency else icosphere(subdivisions)
   rng = np.random.default_rng(seed)
   axes = rng.uniform(0.55, 1.0, (count, 1, 3))
   radial = rng.triangular(0.1, 0.4, 1.0, (count, base.shape[0], 1))

@@ -77,6 +77,24 @@ def test_rock_images_all_orientations(mods, seed):
     assert (got == 0).sum() > 20 and got.max() > geo.object_z / 2   # exact-zero background
 
 
+def test_config3_rock_2000_triangles(mods):
+  """BASELINE config 3's mesh size: a 2 000-triangle / 1 002-vertex synthetic rock on a
+  32x32 image at 0.005 m/px (vertex cache and index staging both nearly full), plus a
+  5 120-triangle one that exceeds the vertex cache (corners projected per triangle)."""
+  geo = mods['camera'].ObserverGeometry(128, 32, 0.005, 0.375)
+  spawn = ((0., 0., 0.375 + 0.16), (0., 0., 0., 1.))
+  for kwargs in (dict(frequency=10), dict(subdivisions=4)):
+    verts, tris = mods['meshes'].synthetic_rocks(4, 2, max_dimension=0.16, **kwargs)
+    for k in range(2):
+      bodies = [(verts[k], tris, np.identity(3), np.array(spawn[0]))]
+      view = geo.object_view(spawn, 0)
+      want_d = R.render_depth(view, geo.object_projection, 32, 32, bodies)
+      got = _gpu_render(mods, bodies, view, geo.object_projection, 32, 32,
+                        mods['capi'].RASTER_ROCK, geo.object_z)
+      assert np.array_equal(got, O.rock_elevation(want_d, geo.object_z))
+      assert (got > 0).sum() > 100
+
+
 def test_box_known_answer(mods, observe_golden):
   """The reference's perfect box 0_0.obj (half extents 0.0536 x 0.0268 x
   0.0179 m) resting on the ground: flat top at 2*hz, footprint 2hx x 2hy."""

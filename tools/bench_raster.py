@@ -1,4 +1,5 @@
-"""Rasterisation throughput (BASELINE config 3 geometry). python tools/bench_raster.py [n] [subdiv]"""
+"""Rasterisation throughput (BASELINE config 3 geometry). python tools/bench_raster.py [n] [subdiv] [reps]
+(subdiv >= 5 is read as a geodesic frequency: 10 = 2000 triangles / 1002 vertices)"""
 import os
 import sys
 
@@ -15,7 +16,8 @@ def main():
   sub = int(sys.argv[2]) if len(sys.argv) > 2 else 3
   reps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
   dev = torch.device('cuda')
-  verts, tris = meshes.synthetic_rocks(4, n, sub, max_dimension=0.16)
+  verts, tris = meshes.synthetic_rocks(4, n, sub, max_dimension=0.16) if sub < 5 else \
+    meshes.synthetic_rocks(4, n, max_dimension=0.16, frequency=sub)
   bank = meshes.MeshBank()
   for k in range(n):
     bank.add(verts[k], tris)
