@@ -209,7 +209,7 @@ def _time_loop(torch, fn, steps):
   return ev0.elapsed_time(ev1) / steps
 
 
-def extra_metrics(torch, dev):
+def extra_metrics(torch, dev, cpu_baseline=True):
   """Short measurements of the other two BASELINE metrics on this GPU: mesh
   rasterisation (config 3 geometry) and full env observations (config 4
   geometry, static settle).  Reported under `extra`; not the headline."""
@@ -245,6 +245,23 @@ def extra_metrics(torch, dev):
                  'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                  'frac': n * bytes_per_rock / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
                  'bytes_per_rock': bytes_per_rock}}
+  if cpu_baseline:
+    # CPU baseline of the raster: the oracle's C z-buffer (gcc -O2, one core) on a
+    # sample of the same rocks and camera -- the RESTATEMENT, not pybullet's
+    # TinyRenderer (absent here).
+    from oracle import raster_np
+    spawn = ((0., 0., 0.375 + 0.16), (0., 0., 0., 1.))
+    view = g.object_view(spawn, 0)
+    sample = n                       # every rock of the batch once (~1 s)
+    t0 = time.perf_counter()
+    for k in range(sample):
+      raster_np.render_depth(view, g.object_projection, g.object_h, g.object_w,
+                             [(verts[k], tris, np.identity(3), np.array(spawn[0]))])
+    dt = time.perf_counter() - t0
+    out['raster']['cpu_baseline'] = {
+      'value': sample / dt, 'unit': 'rocks/s', 'cores': 1, 'kind': 'port',
+      'sample': '{} of the same rocks, depth image only, oracle/csrc/oracle.c z-buffer '
+                'through ctypes in {:.2f} s'.format(sample, dt)}
   # -- config 2 on heightmaps as the rasteriser leaves them (multiples of 2^-14 m):
   #    the exact 16-bit fixed-point sweep behind srl_maxplus_f32_q ---------------- #
   from stackrl_b200 import baselines, synth
@@ -574,7 +591,7 @@ def run_graft(args, rank, local_rank, world):
   }
   if world == 1 and not args.no_extra:
     try:
-      line['extra'] = extra_metrics(torch, dev)
+      line['extra'] = extra_metrics(torch, dev, cpu_baseline=not args.no_cpu_baseline)
     except Exception as exc:   # the headline must survive a failure of the extras
       line['extra'] = {'error': repr(exc)}
   if world == 1 and not args.no_cpu_baseline:
