@@ -131,12 +131,16 @@ siam_correlation_kernel(const SiamParams p) {
   for (int cq = 0; cq < nquads; ++cq) {
     const int c0 = cq * 4;
     __syncthreads();                               // previous quad's sweep is done
-    for (int k = tid; k < p.rows_in * p.cols_in; k += nthr) {
-      const int rr = k / p.cols_in, q = k - rr * p.cols_in;
-      const int gr = i0 + rr, gq = j0 + q;
-      float4 val = zero4;
-      if (gr < p.H && gq < p.W) val = load_quad(xb + ((size_t)gr * p.W + gq) * p.C, c0, p.C, vec);
-      xs[(size_t)rr * p.xpitch + q + (q >> 3)] = val;
+    // patch rows by warp, pixels by lane (no index division; a warp's loads of one
+    // row are one contiguous run of the image)
+    for (int rr = tid >> 5; rr < p.rows_in; rr += nthr >> 5) {
+      const int gr = i0 + rr;
+      const float* src = xb + ((size_t)gr * p.W + j0) * p.C;
+      float4* dst = xs + (size_t)rr * p.xpitch;
+      const int live = gr < p.H ? min(p.cols_in, p.W - j0) : 0;   // pixels inside the image
+#pragma unroll 4
+      for (int q = tid & 31; q < p.cols_in; q += 32)
+        dst[q + (q >> 3)] = q < live ? load_quad(src + (size_t)q * p.C, c0, p.C, vec) : zero4;
     }
     for (int k = tid; k < p.h * p.wdp; k += nthr) {
       const int u = k / p.wdp, v = k - u * p.wdp;
