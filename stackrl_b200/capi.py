@@ -413,6 +413,8 @@ def siam_correlation_f32(x, w, out=None):
   args = (_dev(x, torch.float32, 'x'), _dev(w, torch.float32, 'w'))
   if out is None:
     out = torch.empty((B, H - h + 1, W - wd + 1, 1), dtype=torch.float32, device=x.device)
+  elif out.numel() != B * (H - h + 1) * (W - wd + 1):
+    raise ValueError('out must hold [B, H-h+1, W-w+1, 1] values, got {}'.format(tuple(out.shape)))
   with torch.cuda.device(x.device):
     _check(lib.srl_siam_correlation_f32(*args, _dev(out, torch.float32, 'out'),
                                         B, H, W, C, h, wd, _stream()))
