@@ -14,8 +14,8 @@
 //    and the filter of that channel quad are staged in shared memory;
 //  * a thread owns 2 output rows x 8 output columns.  For every INPUT row it slides
 //    an 8-slot register window along the filter columns (one new LDS.128 per step)
-//    and feeds the row to both of its output rows (filter rows u and u-1; the
-//    filter has a zero row above and below, so the first/last step need no branch):
+//    and feeds the row to both of its output rows (filter rows u and u-1; the first
+//    and the last input row of the window meet one filter row only):
 //    32 FFMA2 (fma.rn.f32x2: the even and the odd channels of a quad in one
 //    instruction, accumulator pairs) per 3 LDS.128, two of them warp-wide broadcasts;
 //  * the patch rows carry one spare slot after every 8 pixels, so the 8 lanes of a
@@ -23,9 +23,9 @@
 //  * the accumulator pairs are folded into per-output totals after every input row
 //    (512 products per pair), a two-level sum that stays within ~2e-6 of the exact
 //    result for the 16k-product windows of the reference geometry.
-// Inputs must be finite: the zero filter rows / zero-padded filter columns multiply
-// pixels one step outside the window (0 * inf would give NaN where the reference
-// gives a finite value).
+// Inputs must be finite when the filter width is not a multiple of 8: its zero-padded
+// columns multiply pixels just outside the window (0 * inf would give NaN where the
+// reference gives a finite value).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -83,6 +83,47 @@ __device__ __forceinline__ float pair_sum(f32x2 v) {
   return __fadd_rn(e, o);
 }
 
+// One input row of the thread's strip against filter row(s): ROWS = 3 feeds output
+// row 0 with `wrow0` and output row 1 with `wrow1`; ROWS = 1 / 2 only the first /
+// second (the first and the last input row of a thread's window meet one filter row).
+template <int ROWS>
+__device__ __forceinline__ void sweep_row(const float4* __restrict__ xrow,
+                                          const float4* __restrict__ wrow0,
+                                          const float4* __restrict__ wrow1, int wdp,
+                                          float (&tot)[2][8]) {
+  f32x2 acc[2][8];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[a][c] = 0ull;
+  Quad xw[8];
+#pragma unroll
+  for (int t = 0; t < 7; ++t) xw[t] = lds_quad(xrow + t);
+  for (int vc = 0; vc < wdp; vc += 8) {
+    const float4* xc = xrow + (vc >> 3) * 9;
+#pragma unroll
+    for (int vv = 0; vv < 8; ++vv) {
+      // column (vc + vv + 7) of the thread's strip: skewed slot 7 for vv = 0,
+      // 8 + vv after the spare slot otherwise
+      xw[(7 + vv) & 7] = lds_quad(xc + (vv == 0 ? 7 : 8 + vv));
+      Quad w0, w1;
+      if constexpr (ROWS & 1) w0 = lds_quad(wrow0 + vc + vv);
+      if constexpr (ROWS & 2) w1 = lds_quad(wrow1 + vc + vv);
+#pragma unroll
+      for (int tj = 0; tj < 8; ++tj) {
+        const Quad xv = xw[(tj + vv) & 7];
+        if constexpr (ROWS & 1) acc[0][tj] = dot4(acc[0][tj], xv, w0);
+        if constexpr (ROWS & 2) acc[1][tj] = dot4(acc[1][tj], xv, w1);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if constexpr (ROWS & 1) tot[0][c] = __fadd_rn(tot[0][c], pair_sum(acc[0][c]));
+    if constexpr (ROWS & 2) tot[1][c] = __fadd_rn(tot[1][c], pair_sum(acc[1][c]));
+  }
+}
+
 // Channels [c0, c0+4) of one pixel (zero beyond C).
 __device__ __forceinline__ float4 load_quad(const float* __restrict__ px, int c0, int C,
                                             bool vec) {
@@ -99,7 +140,7 @@ __global__ void __launch_bounds__(kSiamMaxThreads)
 siam_correlation_kernel(const SiamParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* xs = reinterpret_cast<float4*>(smem_raw);               // [rows_in][xpitch]
-  float4* ws = xs + (size_t)p.rows_in * p.xpitch;                 // [h + 2][wdp]
+  float4* ws = xs + (size_t)p.rows_in * p.xpitch;                 // [h][wdp]
 
   int blk = blockIdx.x;
   const int bj = blk % p.nbj; blk /= p.nbj;
@@ -121,12 +162,6 @@ siam_correlation_kernel(const SiamParams p) {
 #pragma unroll
     for (int c = 0; c < kSiamTJ; ++c) tot[a][c] = 0.f;
 
-  // zero rows above and below the filter (written once; never overwritten)
-  for (int k = tid; k < p.wdp; k += nthr) {
-    ws[k] = zero4;
-    ws[(size_t)(p.h + 1) * p.wdp + k] = zero4;
-  }
-
   const int nquads = (p.C + 3) >> 2;
   for (int cq = 0; cq < nquads; ++cq) {
     const int c0 = cq * 4;
@@ -146,48 +181,19 @@ siam_correlation_kernel(const SiamParams p) {
       const int u = k / p.wdp, v = k - u * p.wdp;
       float4 val = zero4;
       if (v < p.wd) val = load_quad(wb + ((size_t)u * p.wd + v) * p.C, c0, p.C, vec);
-      ws[(size_t)(u + 1) * p.wdp + v] = val;
+      ws[(size_t)u * p.wdp + v] = val;
     }
     __syncthreads();
     if (!active) continue;
 
+    // input row (rg*2 + rr) feeds output row 0 with filter row rr and output row 1
+    // with filter row rr-1
     const float4* xbase = xs + (size_t)(rg * kSiamTI) * p.xpitch + cg * 9;
-    for (int rr = 0; rr <= p.h; ++rr) {
-      // input row (rg*2 + rr) feeds output row 0 with filter row rr and output
-      // row 1 with filter row rr-1 (ws rows are shifted by the zero row).
-      const float4* xrow = xbase + (size_t)rr * p.xpitch;
-      const float4* wrow0 = ws + (size_t)(rr + 1) * p.wdp;
-      const float4* wrow1 = ws + (size_t)rr * p.wdp;
-      f32x2 acc[kSiamTI][kSiamTJ];
-#pragma unroll
-      for (int a = 0; a < kSiamTI; ++a)
-#pragma unroll
-        for (int c = 0; c < kSiamTJ; ++c) acc[a][c] = 0ull;
-      Quad xw[kSiamTJ];
-#pragma unroll
-      for (int t = 0; t < kSiamTJ - 1; ++t) xw[t] = lds_quad(xrow + t);
-      for (int vc = 0; vc < p.wdp; vc += 8) {
-        const float4* xc = xrow + (vc >> 3) * 9;
-#pragma unroll
-        for (int vv = 0; vv < 8; ++vv) {
-          // column (vc + vv + 7) of the thread's strip: skewed slot 7 for vv = 0,
-          // 8 + vv after the spare slot otherwise
-          xw[(7 + vv) & 7] = lds_quad(xc + (vv == 0 ? 7 : 8 + vv));
-          const Quad w0 = lds_quad(wrow0 + vc + vv);
-          const Quad w1 = lds_quad(wrow1 + vc + vv);
-#pragma unroll
-          for (int tj = 0; tj < kSiamTJ; ++tj) {
-            const Quad xv = xw[(tj + vv) & 7];
-            acc[0][tj] = dot4(acc[0][tj], xv, w0);
-            acc[1][tj] = dot4(acc[1][tj], xv, w1);
-          }
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < kSiamTI; ++a)
-#pragma unroll
-        for (int c = 0; c < kSiamTJ; ++c) tot[a][c] = __fadd_rn(tot[a][c], pair_sum(acc[a][c]));
-    }
+    sweep_row<1>(xbase, ws, ws, p.wdp, tot);
+    for (int rr = 1; rr < p.h; ++rr)
+      sweep_row<3>(xbase + (size_t)rr * p.xpitch, ws + (size_t)rr * p.wdp,
+                   ws + (size_t)(rr - 1) * p.wdp, p.wdp, tot);
+    sweep_row<2>(xbase + (size_t)p.h * p.xpitch, ws, ws + (size_t)(p.h - 1) * p.wdp, p.wdp, tot);
   }
 
   if (!active) return;
@@ -224,7 +230,7 @@ int siam_correlation_f32(const float* x, const float* w, float* out, int B, int 
   // thread tile) with one thread per 2x8 outputs.  Every thread does the same work, so
   // a launch costs (waves of CTAs) x (warps per SM sub-partition); ties go to the
   // smaller halo.  The patch of the tile must fit shared memory.
-  const size_t filt = (size_t)(h + 2) * p.wdp * 16;
+  const size_t filt = (size_t)h * p.wdp * 16;
   auto band = [&](int n, int parts, int unit) { return (((n + parts - 1) / parts) + unit - 1) / unit * unit; };
   int force_bi = 0, force_bj = 0;
   if (const char* t = getenv("SRL_SIAM_TILE")) sscanf(t, "%d,%d", &force_bi, &force_bj);   // tuning override
