@@ -248,6 +248,17 @@ SRL_API int srl_raster(const float* verts, const int32_t* tris,
                        const srl_raster_instance* insts, const srl_raster_job* jobs,
                        float* out, int njobs, int rows, int cols, int mode,
                        double far_plane, srl_stream_t stream);
+/* Same, for scenes that live on the device: inst_counts [njobs] i32 (or NULL)
+ * overrides jobs[k].inst_count -- the number of placed rocks of each environment
+ * changes every step while the job table stays put -- and max_cached_verts (0:
+ * default 2048) sizes the per-image screen-space vertex cache in shared memory: the
+ * vertex count of the largest mesh (rock images) or of one image's instances (wall
+ * images); anything larger still renders, its corners projected per triangle. */
+SRL_API int srl_raster_ex(const float* verts, const int32_t* tris,
+                          const srl_raster_instance* insts, const srl_raster_job* jobs,
+                          const int32_t* inst_counts, float* out, int njobs, int rows,
+                          int cols, int mode, double far_plane, int max_cached_verts,
+                          srl_stream_t stream);
 
 /* ---- a11: Rewarder._intersection/_union (rewarder.py:297-307) ---------------
  * inter[e] = sum(min(walls[e][goal != 0], goal_z[e])), uni[e] = sum(max(walls[e],
@@ -267,6 +278,106 @@ SRL_API int srl_pack_obs(const float* walls, const float* goals, const float* ro
                  void* wall_goal, void* rock, int E, int R, int H, int W, int h,
                  int dtype_code, float scale, int repeat_wall,
                  srl_stream_t stream);
+
+/* ---- a4 for a batch: Observer.pose (observer.py:392-421) ------------------------
+ * For every environment: (row, col) = divmod(flat[e], W-h+1) (env.py:240-241),
+ * z = max((walls[e, row:row+h, col:col+h] + rocks[e, r])[rocks[e, r] > threshold])
+ * in float32 with r = views[e] (0 when views == NULL), and
+ *   poses[e] = (row*pixel_h + object_x/2, col*pixel_w + object_y/2,
+ *               z - object_z/2 [float32], orientations[r][0..3])      float64 [E,7]
+ * views/flat are int64 device arrays with `action_stride` elements between
+ * consecutive environments (1 for plain [E] arrays; 2 when they are the two columns
+ * of the `best` [E,2] table the selection kernels write); orientations [R,4] float64
+ * (Observer._object_orientations).
+ * The reference asserts action_space.contains(action) (env.py:237): an action out
+ * of range reads nothing, yields a NaN pose and status[e] = 1 (status [E] i32,
+ * may be NULL; 0 = valid). */
+SRL_API int srl_place_poses_f32(const float* walls, const float* rocks, const int64_t* views,
+                                const int64_t* flat, const double* orientations,
+                                double* poses, int32_t* status, int E, int R, int H, int W,
+                                int h, int action_stride, double pixel_h, double pixel_w,
+                                double object_x, double object_y, double object_z,
+                                float threshold, srl_stream_t stream);
+
+/* ---- a15: episode bookkeeping of StackEnv.step / reset on the device --------------
+ * (env.py:233-293 around the physics call; Simulator.positions /
+ * distances_from_place, simulator.py:86-127, for the discounted rewards).
+ * HOST struct of DEVICE pointers describing E environments:
+ *   mesh_ranges [M,4] i32 (vert_begin, vert_count, tri_begin, tri_count), mesh_coms
+ *   [M,3] f64 (inertial origin of each URDF), spawn_rows [M] instances at the spawn
+ *   pose; instances [E*capacity] + counts [E]: the placed rocks srl_raster draws into
+ *   the wall image; order [E,length] i32: mesh of every step of the episode (the
+ *   env's episode list, env.py:268-272, in pop order); cursor/current/n_placed [E]
+ *   i32; hist_rest / hist_placed [E,length,7] f64 (x,y,z,qx,qy,qz,qw) and hist_mesh
+ *   [E,length] i32: rest pose, placement pose and mesh of every placed rock; done [E]
+ *   u8; rock_instances [E]: the spawned rock srl_raster draws into the rock images;
+ *   memory [E,4] f64: Rewarder._memory (IoU, OR, DIoU, DOR). */
+typedef struct srl_env_state {
+  int32_t E, capacity, length, reserved;
+  const int32_t* mesh_ranges;
+  const double* mesh_coms;
+  const srl_raster_instance* spawn_rows;
+  srl_raster_instance* instances;
+  int32_t* counts;
+  const int32_t* order;
+  int32_t* cursor;
+  int32_t* current;
+  double* hist_rest;
+  double* hist_placed;
+  int32_t* hist_mesh;
+  int32_t* n_placed;
+  uint8_t* done;
+  srl_raster_instance* rock_instances;
+  double* memory;
+} srl_env_state;
+/* Start episodes for env_ids [n] i32 (NULL: environments 0..n-1): empty instance
+ * table, first rock of `order` spawned, reward memory cleared (env.py:266-293). */
+SRL_API int srl_env_reset(const srl_env_state* host_state, const int32_t* env_ids, int n,
+                          srl_stream_t stream);
+/* One step for every environment that is not done: the spawned rock comes to rest at
+ * rest[e] (x,y,z,qx,qy,qz,qw; inertial frame, like resetBasePositionAndOrientation),
+ * its instance (rotation from the quaternion, position - R*com) is appended, the
+ * history rows are written (placed == NULL: placed = rest), and the next rock of the
+ * episode is spawned or the environment is marked done (env.py:245-249). */
+SRL_API int srl_env_advance(const srl_env_state* host_state, const double* rest,
+                            const double* placed, srl_stream_t stream);
+/* Rewrite the rest poses of the first n_given placed rocks of every environment
+ * (poses [E,n_given,7]): a physics step that moved earlier rocks. */
+SRL_API int srl_env_set_poses(const srl_env_state* host_state, const double* poses,
+                              int n_given, srl_stream_t stream);
+
+/* ---- a13: the goal map of Rewarder._reset_goal (rewarder.py:252-258) ----------------
+ * goals[e, u0:u1, v0:v1] = goal_z[e], 0 elsewhere, for e = env_ids[k] (NULL: e = k),
+ * rects [n,4] i32 = (u0, v0, u1, v1) = Rewarder._goal_lims.  goal_z is indexed by e. */
+SRL_API int srl_fill_goals_f32(const int32_t* rects, const float* goal_z,
+                               const int32_t* env_ids, float* goals, int n, int H, int W,
+                               srl_stream_t stream);
+/* get_inputs' goal.max() (baselines.py:23) per environment: level [E]. */
+SRL_API int srl_goal_level_f32(const float* goals, float* level, int E, int HW,
+                               srl_stream_t stream);
+SRL_API int srl_goal_level_u8(const uint8_t* goals, uint8_t* level, int E, int HW,
+                              srl_stream_t stream);
+
+/* ---- a11/a12: Rewarder.call (rewarder.py:162-179, 261-307) ---------------------------
+ * metric 0 IoU, 1 OR, 2 DIoU, 3 DOR, 4 all (Rewarder.metrics order).  reward[e] =
+ * (value - memory[e][metric]) * scale and memory is updated; metric 4 writes reward
+ * [E,4].  value [E,4] f64 (raw metric values) may be NULL.  IoU / OR: float64
+ * accumulation of the float32 maps rounded once (1e-6 relative, see
+ * srl_reward_sums_f32), then the reference's float32 division.  DIoU / DOR: the
+ * sequential float64 sum of rewarder.py:261-295 over hist_rest / hist_placed with
+ * Python's float floor division for xy_to_pixel; pexp / oexp < 0 mean "no discount". */
+SRL_API int srl_rewards_f32(const srl_env_state* host_state, const float* walls,
+                            const float* goals, const float* goal_z, const int32_t* rects,
+                            float* reward, double* value, int H, int W, int metric,
+                            double scale, double pixel_h, double pixel_w, double pmax,
+                            double pexp, double oexp, srl_stream_t stream);
+
+/* StackEnv._return's uint8 cast (env.py:171-178) on the planar maps (the form the
+ * scoring kernels take): q = trunc(x*255/scale) in float32. */
+SRL_API int srl_quantise_planes_u8(const float* walls, const float* goals,
+                                   const float* rocks, uint8_t* walls8, uint8_t* goals8,
+                                   uint8_t* rocks8, int E, int R, int H, int W, int h,
+                                   float scale, srl_stream_t stream);
 
 /* ---- measurement helpers (not part of the reference's surface) --------------
  * Issue-rate micro-benchmark used to fix the FP32 roofline of the max-plus

@@ -18,6 +18,7 @@ import numpy as np
 from oracle import raster_np as R
 
 GUI, DIRECT, GEOM_BOX, COV_ENABLE_GUI = 1, 2, 3, 1
+GEOM_MESH = 5
 
 
 def load_obj(path):
@@ -56,8 +57,11 @@ def box_mesh(half):
 
 
 class _Body(object):
-  def __init__(self, verts, tris, pos, orn, com=(0., 0., 0.), visible=True):
+  def __init__(self, verts, tris, pos, orn, com=(0., 0., 0.), visible=True, shape=None):
     self.verts, self.tris = verts, tris
+    # (geometry type, dimensions, mesh file, local visual frame position) as
+    # pybullet.getVisualShapeData reports them
+    self.shape = shape
     self.pos, self.orn = tuple(pos), tuple(orn)
     self.com = np.asarray(com, dtype='float64')   # inertial origin in the link frame
     self.visible = visible
@@ -124,7 +128,9 @@ class FakeBullet(object):
                         visualFramePosition=(0, 0, 0), **_):
     sid = self._new_id()
     v, t = box_mesh(halfExtents)
-    self._shapes[sid] = (v + np.asarray(visualFramePosition, dtype='float32'), t)
+    self._shapes[sid] = (v + np.asarray(visualFramePosition, dtype='float32'), t,
+                         (GEOM_BOX, tuple(2. * h for h in halfExtents), '',
+                          tuple(float(x) for x in visualFramePosition)))
     return sid
 
   def createMultiBody(self, baseMass=0, baseCollisionShapeIndex=-1,
@@ -132,8 +138,8 @@ class FakeBullet(object):
                       baseOrientation=(0, 0, 0, 1), **_):
     bid = self._new_id()
     if baseVisualShapeIndex in self._shapes:
-      v, t = self._shapes[baseVisualShapeIndex]
-      self._bodies[bid] = _Body(v, t, basePosition, baseOrientation)
+      v, t, shape = self._shapes[baseVisualShapeIndex]
+      self._bodies[bid] = _Body(v, t, basePosition, baseOrientation, shape=shape)
     else:
       self._bodies[bid] = _Body(np.zeros((0, 3), 'float32'), np.zeros((0, 3), 'int32'),
                                 basePosition, baseOrientation, visible=False)
@@ -143,7 +149,9 @@ class FakeBullet(object):
     mesh, com = parse_urdf(fileName)
     v, t = load_obj(mesh)
     bid = self._new_id()
-    self._bodies[bid] = _Body(v, t, basePosition, baseOrientation, com=com)
+    self._bodies[bid] = _Body(v, t, basePosition, baseOrientation, com=com,
+                              shape=(GEOM_MESH, (1., 1., 1.), mesh,
+                                     tuple(float(-c) for c in com)))
     return bid
 
   def removeBody(self, bodyUniqueId, **_):
@@ -176,6 +184,24 @@ class FakeBullet(object):
       b.mass = mass
     if localInertiaDiagonal is not None:
       b.inertia = tuple(localInertiaDiagonal)
+
+  # -- scene queries (what stackrl_b200.observer.PybulletScene reads) ---------------- #
+  def getNumBodies(self, **_):
+    return len(self._bodies)
+
+  def getBodyUniqueId(self, serialIndex, **_):
+    return list(self._bodies.keys())[serialIndex]
+
+  def getVisualShapeData(self, objectUniqueId, **_):
+    """[(body, link, geometry type, dimensions, mesh file, local visual frame position,
+    local visual frame orientation, rgba)], the visual frame relative to the inertial
+    frame getBasePositionAndOrientation reports."""
+    b = self._bodies[objectUniqueId]
+    if not b.visible or b.shape is None:
+      return []
+    geom, dims, filename, lpos = b.shape
+    return [(objectUniqueId, -1, geom, dims, filename.encode(), lpos, (0., 0., 0., 1.),
+             (1., 1., 1., 1.))]
 
   # -- transforms -------------------------------------------------------------- #
   def getQuaternionFromEuler(self, eulerAngles, **_):

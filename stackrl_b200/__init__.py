@@ -13,8 +13,8 @@ import importlib
 
 __version__ = '0.1.0'
 
-_LAZY = ('capi', 'baselines', 'observer', 'rewards', 'envs', 'meshes',
-         'sharding', 'synth')
+_LAZY = ('capi', 'baselines', 'observer', 'envs', 'episodes', 'meshes', 'nets',
+         'sharding', 'synth', 'camera')
 
 
 def __getattr__(name):

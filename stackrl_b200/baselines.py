@@ -61,11 +61,11 @@ def _height_device(walls, goals, rocks, quantum_log2=None, level=None):
   ``level``: goal.max() per environment when the caller already has it."""
   if walls.dtype == torch.float32:
     if level is None:
-      level = goals.amax(dim=(1, 2))        # get_inputs: goal.max() (baselines.py:23)
+      level = capi.goal_level(goals)        # get_inputs: goal.max() (baselines.py:23)
     return capi.maxplus_f32(walls, rocks, level, quantum_log2=quantum_log2)
   if walls.dtype == torch.uint8:
     # uint8/uint8 is float64 in numpy: IEEE float64 a/g + b/g per cell.
-    return capi.maxplus_u8(walls, rocks, goals.amax(dim=(1, 2)))
+    return capi.maxplus_u8(walls, rocks, capi.goal_level(goals) if level is None else level)
   raise TypeError(
     'observations must be float32 or uint8 (the dtypes the reference registers), '
     'got {}'.format(walls.dtype))
@@ -100,7 +100,7 @@ def difference(inputs, mask=None, difference_exponent=2, weights_exponent=2,
   if walls.dtype not in (torch.float32, torch.uint8):
     raise TypeError('observations must be float32 or uint8, got {}'.format(walls.dtype))
   u8 = walls.dtype == torch.uint8
-  level = goals.amax(dim=(1, 2))
+  level = capi.goal_level(goals)
   if weights_exponent in (0, 2):
     weights = capi.difference_weights(rocks, None if u8 else level, weights_exponent)
   else:
@@ -133,7 +133,7 @@ def correlate(inputs, **kwargs):
   walls, goals, rocks = _planes(inputs)
   if walls.dtype != torch.float32:
     raise TypeError('correlate is wired for float32 observations')
-  corr, _ = capi.correlate_f32(walls, rocks, goals.amax(dim=(1, 2)), want_coef=False)
+  corr, _ = capi.correlate_f32(walls, rocks, capi.goal_level(goals), want_coef=False)
   return corr[0, 0].cpu().numpy()
 
 
@@ -146,13 +146,13 @@ def corrcoef(inputs, mask=None, localized=False, **kwargs):
   arithmetic type; float32 and uint8 observations)."""
   walls, goals, rocks = _planes(inputs)
   if localized:
-    f = capi.corrcoef_localized(walls, rocks, goals.amax(dim=(1, 2)))[0, 0].cpu().numpy()
+    f = capi.corrcoef_localized(walls, rocks, capi.goal_level(goals))[0, 0].cpu().numpy()
     if mask is not None:
       f = np.where(mask, f, 0.)
     return f
   if walls.dtype != torch.float32:
     raise TypeError('corrcoef is wired for float32 observations')
-  _, coef = capi.correlate_f32(walls, rocks, goals.amax(dim=(1, 2)), want_corr=False)
+  _, coef = capi.correlate_f32(walls, rocks, capi.goal_level(goals), want_corr=False)
   return coef[0, 0].cpu().numpy()
 
 
@@ -211,7 +211,7 @@ class PlacementScorer(object):
   def values(self, walls, goals, rocks, level=None):
     if self.method == 'difference':
       if level is None:
-        level = goals.amax(dim=(1, 2))
+        level = capi.goal_level(goals)
       u8 = walls.dtype == torch.uint8
       weights = capi.difference_weights(rocks, None if u8 else level, self.weights_exponent)
       run = capi.difference_u8 if u8 else capi.difference_f32
@@ -233,7 +233,7 @@ class PlacementScorer(object):
       try:
         values, actions, best = capi.score_f32(
           walls, goals if self.goal else None, rocks,
-          None if self.goal else goals.amax(dim=(1, 2)),
+          None if self.goal else capi.goal_level(goals),
           level_mode=2 if self.goal else 1, minorder=self.minorder or 0,
           overlap_threshold=self.threshold)
         return {'values': values, 'counts': None, 'actions': actions, 'best': best,
@@ -409,7 +409,7 @@ class Baseline(object):
     elif self.model is difference and walls.dtype == torch.float32 and \
         self.kwargs.get('difference_exponent', 2) in (1, 2) and \
         self.kwargs.get('weights_exponent', 2) in (0, 2):
-      level = goals.amax(dim=(1, 2))
+      level = capi.goal_level(goals)
       weights = capi.difference_weights(rocks, level,
                                         self.kwargs.get('weights_exponent', 2))
       values, _ = capi.difference_f32(walls, rocks, level, weights,

@@ -58,8 +58,21 @@ _SIGNATURES = {
   'srl_correlate_f32': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
   'srl_siam_correlation_f32': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
   'srl_raster': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _P]),
+  'srl_raster_ex': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _I, _P]),
   'srl_reward_sums_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
   'srl_pack_obs': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_float, _I, _P]),
+  'srl_place_poses_f32': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_double,
+                                _c.c_double, _c.c_double, _c.c_double, _c.c_double,
+                                _c.c_float, _P]),
+  'srl_env_reset': (_I, [_P, _P, _I, _P]),
+  'srl_env_advance': (_I, [_P, _P, _P, _P]),
+  'srl_env_set_poses': (_I, [_P, _P, _I, _P]),
+  'srl_fill_goals_f32': (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+  'srl_goal_level_f32': (_I, [_P, _P, _I, _I, _P]),
+  'srl_goal_level_u8': (_I, [_P, _P, _I, _I, _P]),
+  'srl_rewards_f32': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _c.c_double, _c.c_double,
+                            _c.c_double, _c.c_double, _c.c_double, _c.c_double, _P]),
+  'srl_quantise_planes_u8': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_float, _P]),
   'srl_microbench_addmax': (_I, [_I, _I, _c.POINTER(_c.c_double)]),
   'srl_microbench_fma': (_I, [_I, _I, _c.POINTER(_c.c_double)]),
 }
@@ -86,6 +99,32 @@ def _dev(t, dtype, name):
   if not t.is_contiguous():
     raise ValueError('{} must be contiguous'.format(name))
   return _P(t.data_ptr())
+
+
+def _out(t, dtype, shape, like, name='out'):
+  """A caller-provided output buffer: right dtype, element count and device (the
+  kernels write ``prod(shape)`` values into it, partly with bulk TMA stores)."""
+  n = 1
+  for d in shape:
+    n *= int(d)
+  if t.numel() != n:
+    raise ValueError('{} must hold {} values ({}), got {}'.format(
+      name, n, tuple(shape), tuple(t.shape)))
+  if t.device != like.device:
+    raise ValueError('{} is on {}, the inputs on {}'.format(name, t.device, like.device))
+  return _dev(t, dtype, name)
+
+
+def _same_device(*tensors):
+  dev = None
+  for t in tensors:
+    if t is None:
+      continue
+    if dev is None:
+      dev = t.device
+    elif t.device != dev:
+      raise ValueError('all tensors of one call must live on one device ({} vs {})'.format(
+        dev, t.device))
 
 
 def _opt(t, dtype, name):
@@ -115,11 +154,13 @@ def maxplus_f32(walls, rocks, level=None, threshold=0., out=None, quantum_log2=N
   E2, R, h, h2 = rocks.shape
   if E2 != E or h != h2:
     raise ValueError('rocks must be [E, R, h, h] matching walls [E, H, W]')
+  _same_device(walls, rocks, level)
   args = (_dev(walls, torch.float32, 'walls'), _dev(rocks, torch.float32, 'rocks'),
           _opt(level, torch.float32, 'level'))
+  shape = (E, R, H - h + 1, W - h + 1)
   if out is None:
-    out = torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.float32,
-                      device=walls.device)
+    out = torch.empty(shape, dtype=torch.float32, device=walls.device)
+  _out(out, torch.float32, shape, walls)
   with torch.cuda.device(walls.device):
     if quantum_log2 is None:
       _check(lib.srl_maxplus_f32(*args, _dev(out, torch.float32, 'out'),
@@ -134,11 +175,13 @@ def maxplus_f32(walls, rocks, level=None, threshold=0., out=None, quantum_log2=N
 def maxplus_u8(walls, rocks, level, out=None):
   """uint8 walls [E,H,W], rocks [E,R,h,h], level [E] -> float64 [E,R,Ph,Pw]."""
   E, R, H, W, h = _batch_dims(walls, rocks)
+  _same_device(walls, rocks, level)
   args = (_dev(walls, torch.uint8, 'walls'), _dev(rocks, torch.uint8, 'rocks'),
           _dev(level, torch.uint8, 'level'))
+  shape = (E, R, H - h + 1, W - h + 1)
   if out is None:
-    out = torch.empty((E, R, H - h + 1, W - h + 1), dtype=torch.float64,
-                      device=walls.device)
+    out = torch.empty(shape, dtype=torch.float64, device=walls.device)
+  _out(out, torch.float64, shape, walls)
   with torch.cuda.device(walls.device):
     _check(lib.srl_maxplus_u8(*args, _dev(out, torch.float64, 'out'),
                               E, R, H, W, h, _stream()))
@@ -286,10 +329,13 @@ assert INSTANCE_DTYPE.itemsize == 112 and JOB_DTYPE.itemsize == 272
 RASTER_DEPTH, RASTER_WALL, RASTER_ROCK = 0, 1, 2
 
 
-def raster(verts, tris, instances, jobs, rows, cols, mode, far_plane=1000., out=None):
+def raster(verts, tris, instances, jobs, rows, cols, mode, far_plane=1000., out=None,
+           inst_counts=None, max_cached_verts=0):
   """verts [NV,3] f32 / tris [NT,3] i32 CUDA tensors (the mesh bank),
   instances / jobs numpy structured arrays (INSTANCE_DTYPE / JOB_DTYPE) or
-  CUDA uint8 tensors holding them -> [njobs, rows, cols] float32."""
+  CUDA uint8 tensors holding them -> [njobs, rows, cols] float32.
+  ``inst_counts`` [njobs] int32 (device) overrides the jobs' instance counts;
+  ``max_cached_verts`` sizes the shared-memory vertex cache (srl_raster_ex)."""
   dev = verts.device
   def as_bytes(a, dtype):
     if isinstance(a, torch.Tensor):
@@ -307,12 +353,15 @@ def raster(verts, tris, instances, jobs, rows, cols, mode, far_plane=1000., out=
     tris = torch.zeros((1, 3), dtype=torch.int32, device=dev)
   if out is None:
     out = torch.empty((njobs, rows, cols), dtype=torch.float32, device=dev)
+  _out(out, torch.float32, (njobs, rows, cols), verts)
+  _same_device(verts, tris, inst_t, jobs_t)
   args = (_dev(verts, torch.float32, 'verts'), _dev(tris, torch.int32, 'tris'),
           _dev(inst_t, torch.uint8, 'instances'), _dev(jobs_t, torch.uint8, 'jobs'),
           _dev(out, torch.float32, 'out'))
   with torch.cuda.device(dev):
-    _check(lib.srl_raster(*args, int(njobs), int(rows), int(cols), int(mode),
-                          float(far_plane), _stream()))
+    _check(lib.srl_raster_ex(*args[:4], _opt(inst_counts, torch.int32, 'inst_counts'), args[4],
+                             int(njobs), int(rows), int(cols), int(mode), float(far_plane),
+                             int(max_cached_verts), _stream()))
   return out
 
 
@@ -331,9 +380,10 @@ def reward_sums(walls, goals, goal_z):
   return inter, uni, vol
 
 
-def pack_obs(walls, goals, rocks, dtype='float32', scale=1., repeat_wall=False):
+def pack_obs(walls, goals, rocks, dtype='float32', scale=1., repeat_wall=False, out=None):
   """Planar maps -> reference-layout observation tensors
-  ([E,(R,)H,W,2], [E,R,h,h,1]) in float32 or uint8."""
+  ([E,(R,)H,W,2], [E,R,h,h,1]) in float32 or uint8.  ``out``: (wall_goal, rock)
+  buffers to fill instead of new tensors."""
   E, R, H, W, h = _batch_dims(walls, rocks)
   dev = walls.device
   tdt = {'float32': torch.float32, 'uint8': torch.uint8}[str(dtype)]
@@ -341,8 +391,13 @@ def pack_obs(walls, goals, rocks, dtype='float32', scale=1., repeat_wall=False):
   wg_shape = (E, R, H, W, 2) if repeat_wall else (E, H, W, 2)
   args = (_dev(walls, torch.float32, 'walls'), _dev(goals, torch.float32, 'goals'),
           _dev(rocks, torch.float32, 'rocks'))
-  wall_goal = torch.empty(wg_shape, dtype=tdt, device=dev)
-  rock = torch.empty((E, R, h, h, 1), dtype=tdt, device=dev)
+  if out is None:
+    wall_goal = torch.empty(wg_shape, dtype=tdt, device=dev)
+    rock = torch.empty((E, R, h, h, 1), dtype=tdt, device=dev)
+  else:
+    wall_goal, rock = out
+    _out(wall_goal, tdt, wg_shape, walls, 'wall_goal')
+    _out(rock, tdt, (E, R, h, h, 1), walls, 'rock')
   with torch.cuda.device(dev):
     _check(lib.srl_pack_obs(*args, _P(wall_goal.data_ptr()), _P(rock.data_ptr()),
                             E, R, H, W, h, code, float(scale), int(bool(repeat_wall)),
@@ -434,6 +489,181 @@ def correlate_f32(walls, rocks, level=None, want_corr=True, want_coef=True):
     _check(lib.srl_correlate_f32(*args, _opt(corr, torch.float32, 'corr'),
                                  _opt(coef, torch.float32, 'coef'), E, R, H, W, h, _stream()))
   return corr, coef
+
+
+# ---- device-side environment step (include/stackrl_b200.h: srl_env_state) ---------- #
+class EnvStateStruct(ctypes.Structure):
+  _fields_ = [('E', _c.c_int32), ('capacity', _c.c_int32), ('length', _c.c_int32),
+              ('reserved', _c.c_int32)] + [(name, _P) for name in (
+                'mesh_ranges', 'mesh_coms', 'spawn_rows', 'instances', 'counts', 'order',
+                'cursor', 'current', 'hist_rest', 'hist_placed', 'hist_mesh', 'n_placed',
+                'done', 'rock_instances', 'memory')]
+
+
+class EnvState(object):
+  """Owner of the device buffers behind one ``srl_env_state`` (E environments,
+  ``capacity`` instance slots each, episodes of ``length`` rocks)."""
+
+  def __init__(self, E, capacity, length, mesh_ranges, mesh_coms, spawn_rows, device):
+    isz = INSTANCE_DTYPE.itemsize
+    z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
+    self.E, self.capacity, self.length = int(E), int(capacity), int(length)
+    self.mesh_ranges = mesh_ranges          # [M,4] i32
+    self.mesh_coms = mesh_coms              # [M,3] f64
+    self.spawn_rows = spawn_rows            # [M,14] f64 (instance structs)
+    self.instances = z((self.E * self.capacity * isz,), torch.uint8)
+    self.counts = z((self.E,), torch.int32)
+    self.order = z((self.E, self.length), torch.int32)
+    self.cursor = z((self.E,), torch.int32)
+    self.current = z((self.E,), torch.int32)
+    self.hist_rest = z((self.E, self.length, 7), torch.float64)
+    self.hist_placed = z((self.E, self.length, 7), torch.float64)
+    self.hist_mesh = z((self.E, self.length), torch.int32)
+    self.n_placed = z((self.E,), torch.int32)
+    self.done = torch.ones((self.E,), dtype=torch.uint8, device=device)
+    self.rock_instances = z((self.E * isz,), torch.uint8)
+    self.memory = z((self.E, 4), torch.float64)
+    self.device = device
+    self.struct = EnvStateStruct(
+      self.E, self.capacity, self.length, 0,
+      *[getattr(self, name).data_ptr() for name, _ in EnvStateStruct._fields_[4:]])
+
+  def ref(self):
+    return ctypes.byref(self.struct)
+
+
+def place_poses(walls, rocks, views, flat, orientations, geometry, threshold=1e-4,
+                poses=None, status=None):
+  """Observer.pose for a batch (observer.py:392-421).  ``views`` [E] int64 or None,
+  ``flat`` [E] int64 device tensors; ``orientations`` [R,4] float64; ``geometry`` =
+  (pixel_h, pixel_w, object_x, object_y, object_z).  -> (poses [E,7] float64,
+  status [E] int32: 1 where the action was out of range, env.py:237)."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  dev = walls.device
+  _same_device(walls, rocks, views, flat, orientations, poses, status)
+  if poses is None:
+    poses = torch.empty((E, 7), dtype=torch.float64, device=dev)
+  if status is None:
+    status = torch.empty((E,), dtype=torch.int32, device=dev)
+  if flat.shape != (E,) or (views is not None and views.shape != (E,)):
+    raise ValueError('actions must be [E] tensors')
+  if orientations.shape != (R, 4):
+    raise ValueError('orientations must be [R, 4]')
+  # [E] tensors, or equally strided column views of one table (the `best` [E,2]
+  # tensor of the selection kernels): the kernel reads them in place.
+  stride = flat.stride(0) if E > 1 else 1
+  for name, t in (('views', views), ('flat', flat)):
+    if t is None:
+      continue
+    if not t.is_cuda or t.dtype != torch.int64:
+      raise TypeError('{} must be an int64 CUDA tensor'.format(name))
+    if E > 1 and t.stride(0) != stride:
+      raise ValueError('views and flat must have the same stride')
+  if stride < 1:
+    raise ValueError('actions must have a positive stride')
+  with torch.cuda.device(dev):
+    _check(lib.srl_place_poses_f32(
+      _dev(walls, torch.float32, 'walls'), _dev(rocks, torch.float32, 'rocks'),
+      _P(None) if views is None else _P(views.data_ptr()), _P(flat.data_ptr()),
+      _dev(orientations, torch.float64, 'orientations'),
+      _out(poses, torch.float64, (E, 7), walls, 'poses'),
+      _out(status, torch.int32, (E,), walls, 'status'), E, R, H, W, h, int(stride),
+      *[float(x) for x in geometry], float(threshold), _stream()))
+  return poses, status
+
+
+def env_reset(state, env_ids=None):
+  """Start episodes for ``env_ids`` (int32 device tensor; None: all)."""
+  n = state.E if env_ids is None else env_ids.numel()
+  with torch.cuda.device(state.device):
+    _check(lib.srl_env_reset(state.ref(), _opt(env_ids, torch.int32, 'env_ids'), int(n),
+                             _stream()))
+
+
+def env_advance(state, rest, placed=None):
+  with torch.cuda.device(state.device):
+    _check(lib.srl_env_advance(state.ref(), _out(rest, torch.float64, (state.E, 7), state.done,
+                                                 'rest'),
+                               _P(None) if placed is None else
+                               _out(placed, torch.float64, (state.E, 7), state.done, 'placed'),
+                               _stream()))
+
+
+def env_set_poses(state, poses):
+  """poses [E, n, 7] float64: rest poses of the first n placed rocks."""
+  n = int(poses.shape[1])
+  with torch.cuda.device(state.device):
+    _check(lib.srl_env_set_poses(state.ref(), _out(poses, torch.float64, (state.E, n, 7),
+                                                   state.done, 'poses'), n, _stream()))
+
+
+def fill_goals(rects, goal_z, goals, env_ids=None):
+  """goals[e, u0:u1, v0:v1] = goal_z[e] (rewarder.py:252-258); rects [n,4] int32."""
+  n = rects.shape[0]
+  E, H, W = goals.shape
+  _same_device(rects, goal_z, goals, env_ids)
+  if env_ids is None and n != E:
+    raise ValueError('rects must be [E, 4] when env_ids is not given')
+  with torch.cuda.device(goals.device):
+    _check(lib.srl_fill_goals_f32(_dev(rects, torch.int32, 'rects'),
+                                  _out(goal_z, torch.float32, (E,), goals, 'goal_z'),
+                                  _opt(env_ids, torch.int32, 'env_ids'),
+                                  _dev(goals, torch.float32, 'goals'), int(n), H, W, _stream()))
+  return goals
+
+
+def goal_level(goals, out=None):
+  """goal.max() per environment (baselines.py:23), float32 or uint8 planes."""
+  E = goals.shape[0]
+  HW = goals[0].numel()
+  if out is None:
+    out = torch.empty((E,), dtype=goals.dtype, device=goals.device)
+  fn = {torch.float32: lib.srl_goal_level_f32, torch.uint8: lib.srl_goal_level_u8}.get(goals.dtype)
+  if fn is None:
+    raise TypeError('goal_level takes float32 or uint8 planes, got {}'.format(goals.dtype))
+  with torch.cuda.device(goals.device):
+    _check(fn(_dev(goals, goals.dtype, 'goals'), _out(out, goals.dtype, (E,), goals, 'level'),
+              E, HW, _stream()))
+  return out
+
+
+METRICS = {'iou': 0, 'or': 1, 'diou': 2, 'dor': 3, 'all': 4}
+
+
+def rewards(state, walls, goals, goal_z, rects, metric, scale, pixel, pmax, pexp, oexp,
+            reward=None, value=None):
+  """Rewarder.call on the device (rewarder.py:162-179): -> reward [E] (or [E,4] for
+  'all') float32; updates ``state.memory``."""
+  m = METRICS[metric]
+  E, H, W = walls.shape
+  shape = (E, 4) if m == 4 else (E,)
+  if reward is None:
+    reward = torch.empty(shape, dtype=torch.float32, device=walls.device)
+  with torch.cuda.device(walls.device):
+    _check(lib.srl_rewards_f32(
+      state.ref(), _dev(walls, torch.float32, 'walls'), _dev(goals, torch.float32, 'goals'),
+      _dev(goal_z, torch.float32, 'goal_z'), _dev(rects, torch.int32, 'rects'),
+      _out(reward, torch.float32, shape, walls, 'reward'), _opt(value, torch.float64, 'value'),
+      H, W, m, float(scale), float(pixel[0]), float(pixel[1]), float(pmax),
+      -1.0 if pexp is None else float(pexp), -1.0 if oexp is None else float(oexp), _stream()))
+  return reward
+
+
+def quantise_planes(walls, goals, rocks, scale, out=None):
+  """StackEnv._return's uint8 cast (env.py:171-178) on planar maps -> uint8 planes."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  dev = walls.device
+  if out is None:
+    out = (torch.empty((E, H, W), dtype=torch.uint8, device=dev),
+           torch.empty((E, H, W), dtype=torch.uint8, device=dev),
+           torch.empty((E, R, h, h), dtype=torch.uint8, device=dev))
+  with torch.cuda.device(dev):
+    _check(lib.srl_quantise_planes_u8(
+      _dev(walls, torch.float32, 'walls'), _dev(goals, torch.float32, 'goals'),
+      _dev(rocks, torch.float32, 'rocks'), _out(out[0], torch.uint8, (E, H, W), walls),
+      _out(out[1], torch.uint8, (E, H, W), walls), _out(out[2], torch.uint8, (E, R, h, h), walls),
+      E, R, H, W, h, float(scale), _stream()))
+  return out
 
 
 def microbench_addmax(variant, iters=2000):

@@ -157,8 +157,16 @@ int srl_corrcoef_localized_u8(const uint8_t* walls, const uint8_t* rocks,
 int srl_raster(const float* verts, const int32_t* tris, const srl_raster_instance* insts,
                const srl_raster_job* jobs, float* out, int njobs, int rows, int cols,
                int mode, double far_plane, srl_stream_t stream) {
-  return srl::raster(verts, tris, insts, jobs, out, njobs, rows, cols, mode, far_plane,
-                     (cudaStream_t)stream);
+  return srl::raster(verts, tris, insts, jobs, nullptr, out, njobs, rows, cols, mode,
+                     far_plane, 0, (cudaStream_t)stream);
+}
+
+int srl_raster_ex(const float* verts, const int32_t* tris, const srl_raster_instance* insts,
+                  const srl_raster_job* jobs, const int32_t* inst_counts, float* out,
+                  int njobs, int rows, int cols, int mode, double far_plane,
+                  int max_cached_verts, srl_stream_t stream) {
+  return srl::raster(verts, tris, insts, jobs, inst_counts, out, njobs, rows, cols, mode,
+                     far_plane, max_cached_verts, (cudaStream_t)stream);
 }
 
 int srl_reward_sums_f32(const float* walls, const float* goals, const float* goal_z,
@@ -217,6 +225,61 @@ int srl_correlate_f32(const float* walls, const float* rocks, const float* level
 int srl_siam_correlation_f32(const float* x, const float* w, float* out, int B, int H, int W,
                              int C, int h, int wd, srl_stream_t stream) {
   return srl::siam_correlation_f32(x, w, out, B, H, W, C, h, wd, (cudaStream_t)stream);
+}
+
+int srl_place_poses_f32(const float* walls, const float* rocks, const int64_t* views,
+                        const int64_t* flat, const double* orientations, double* poses,
+                        int32_t* status, int E, int R, int H, int W, int h,
+                        int action_stride, double pixel_h, double pixel_w, double object_x,
+                        double object_y, double object_z, float threshold,
+                        srl_stream_t stream) {
+  return srl::place_poses_f32(walls, rocks, views, flat, orientations, poses, status, E, R, H,
+                              W, h, action_stride, pixel_h, pixel_w, object_x, object_y,
+                              object_z, threshold, (cudaStream_t)stream);
+}
+
+int srl_env_reset(const srl_env_state* host_state, const int32_t* env_ids, int n,
+                  srl_stream_t stream) {
+  return srl::env_reset(host_state, env_ids, n, (cudaStream_t)stream);
+}
+
+int srl_env_advance(const srl_env_state* host_state, const double* rest, const double* placed,
+                    srl_stream_t stream) {
+  return srl::env_advance(host_state, rest, placed, (cudaStream_t)stream);
+}
+
+int srl_env_set_poses(const srl_env_state* host_state, const double* poses, int n_given,
+                      srl_stream_t stream) {
+  return srl::env_set_poses(host_state, poses, n_given, (cudaStream_t)stream);
+}
+
+int srl_fill_goals_f32(const int32_t* rects, const float* goal_z, const int32_t* env_ids,
+                       float* goals, int n, int H, int W, srl_stream_t stream) {
+  return srl::fill_goals_f32(rects, goal_z, env_ids, goals, n, H, W, (cudaStream_t)stream);
+}
+
+int srl_goal_level_f32(const float* goals, float* level, int E, int HW, srl_stream_t stream) {
+  return srl::goal_level_f32(goals, level, E, HW, (cudaStream_t)stream);
+}
+
+int srl_goal_level_u8(const uint8_t* goals, uint8_t* level, int E, int HW,
+                      srl_stream_t stream) {
+  return srl::goal_level_u8(goals, level, E, HW, (cudaStream_t)stream);
+}
+
+int srl_rewards_f32(const srl_env_state* host_state, const float* walls, const float* goals,
+                    const float* goal_z, const int32_t* rects, float* reward, double* value,
+                    int H, int W, int metric, double scale, double pixel_h, double pixel_w,
+                    double pmax, double pexp, double oexp, srl_stream_t stream) {
+  return srl::rewards_f32(host_state, walls, goals, goal_z, rects, reward, value, H, W, metric,
+                          scale, pixel_h, pixel_w, pmax, pexp, oexp, (cudaStream_t)stream);
+}
+
+int srl_quantise_planes_u8(const float* walls, const float* goals, const float* rocks,
+                           uint8_t* walls8, uint8_t* goals8, uint8_t* rocks8, int E, int R,
+                           int H, int W, int h, float scale, srl_stream_t stream) {
+  return srl::quantise_planes_u8(walls, goals, rocks, walls8, goals8, rocks8, E, R, H, W, h,
+                                 scale, (cudaStream_t)stream);
 }
 
 int srl_microbench_addmax(int variant, int iters, double* host_cells_per_s) {

@@ -65,8 +65,9 @@ int corrcoef_localized_u8(const uint8_t* walls, const uint8_t* rocks, const uint
                           cudaStream_t stream);
 
 int raster(const float* verts, const int32_t* tris, const srl_raster_instance* insts,
-           const srl_raster_job* jobs, float* out, int njobs, int rows, int cols, int mode,
-           double far_plane, cudaStream_t stream);
+           const srl_raster_job* jobs, const int32_t* inst_counts, float* out, int njobs,
+           int rows, int cols, int mode, double far_plane, int vert_cap_hint,
+           cudaStream_t stream);
 
 int pack_obs(const float* walls, const float* goals, const float* rocks, void* wall_goal,
              void* rock, int E, int R, int H, int W, int h, int dtype_code, float scale,
@@ -84,6 +85,28 @@ int correlate_f32(const float* walls, const float* rocks, const float* level, fl
 
 int siam_correlation_f32(const float* x, const float* w, float* out, int B, int H, int W,
                          int C, int h, int wd, cudaStream_t stream);
+
+int place_poses_f32(const float* walls, const float* rocks, const int64_t* views,
+                    const int64_t* flat, const double* orientations, double* poses,
+                    int32_t* status, int E, int R, int H, int W, int h, int action_stride,
+                    double pixel_h, double pixel_w, double object_x, double object_y,
+                    double object_z, float threshold, cudaStream_t stream);
+int env_advance(const srl_env_state* st, const double* rest, const double* placed,
+                cudaStream_t stream);
+int env_reset(const srl_env_state* st, const int32_t* env_ids, int n, cudaStream_t stream);
+int env_set_poses(const srl_env_state* st, const double* poses, int n_given,
+                  cudaStream_t stream);
+int fill_goals_f32(const int32_t* rects, const float* goal_z, const int32_t* env_ids,
+                   float* goals, int n, int H, int W, cudaStream_t stream);
+int goal_level_f32(const float* goals, float* level, int E, int HW, cudaStream_t stream);
+int goal_level_u8(const uint8_t* goals, uint8_t* level, int E, int HW, cudaStream_t stream);
+int rewards_f32(const srl_env_state* st, const float* walls, const float* goals,
+                const float* goal_z, const int32_t* rects, float* reward, double* value,
+                int H, int W, int metric, double scale, double pixel_h, double pixel_w,
+                double pmax, double pexp, double oexp, cudaStream_t stream);
+int quantise_planes_u8(const float* walls, const float* goals, const float* rocks,
+                       uint8_t* walls8, uint8_t* goals8, uint8_t* rocks8, int E, int R, int H,
+                       int W, int h, float scale, cudaStream_t stream);
 
 int microbench_addmax(int variant, int iters, double* host_cells_per_s);
 

@@ -1018,7 +1018,14 @@ static int maxplus_f32_impl(const float* walls, const float* rocks, const float*
     const int blocks_s = p.units < sms ? p.units : sms;
     // index spaces of the fast divisions (n * d < 2^32) and the TMA tx count
     const double per_cta = (double)p.items / blocks_s + 2.0 * p.ipe + 64;
+    // A consumer warp waits until every environment its 32-item unit touches is
+    // resident, and a ring slot is recycled only when all `ipe` items of its tenant
+    // are done: a unit that spans more environments than the ring has slots would
+    // wait for a slot that only its own completion can free.  32 consecutive items
+    // touch at most (30 + ipe) / ipe + 1 environments.
+    const int unit_span = (30 + p.ipe) / p.ipe + 1;
     const bool ok = paired && p.tma_wall && p.tma_rock && ns >= 3 && mode == 2 &&
+                    unit_span <= ns &&
                     raw_b < (1u << 20) && per_cta * p.ipe < 4.0e9 && p.ipe < (1 << 20) &&
                     (size_t)H * W < 65536 && (size_t)R * h * p.hp < 65536 &&
                     p.items < (1ll << 40);

@@ -5,17 +5,24 @@ batches N of them over ``multiprocessing.Pipe`` (``ParallelEnv``,
 stackrl/envs/utils.py:302-576).  ``BatchedStackEnv`` keeps that contract --
 ``reset() / step(action) -> (observation, reward, terminal)`` with a leading
 batch axis, ``batch_size``, ``observation_spec``, ``action_spec``, ``sample()``,
-``seed()`` -- for E environments on one GPU: observation capture, placement
-pose, rewards and packing are the sm_100a kernels; the rigid-body settle step is
-NOT part of this package (BASELINE north_star: it stays the reference's pybullet
-code) and is plugged in as ``settle``: a callable that receives the placement
-poses and returns where the rocks came to rest.  The default ``settle=None``
-leaves every rock where it was placed, which is also what the golden episodes
-(reference env on the static fake backend) do.
+``seed()`` -- for E environments on one GPU.  A step is a chain of sm_100a
+kernels with NO device->host round trip: placement pose (a4) -> instance append
+and next rock (a15) -> wall and rock rasterisation (a2/a3) -> reward (a11/a12)
+-> packing (a14); ``capture()`` records the chain (optionally with the policy in
+front) as one CUDA graph.  The rigid-body settle step is NOT part of this
+package (BASELINE north_star: it stays the reference's pybullet code) and is
+plugged in as ``settle``: a host callable that receives the placement poses and
+returns where the rocks came to rest -- the only point where a step
+synchronises.  The default ``settle=None`` leaves every rock where it was placed,
+which is also what the golden episodes (reference env on the static fake
+backend) do.
 
-Host-side randomness (rock order, goal rectangle) uses numpy RandomState like
-the reference (env.py:105, rewarder.py:211-259); the streams are per
-environment, seeded ``seed + i`` (utils.py:433).
+Host-side randomness follows the reference: per environment one RandomState for
+the rock order (env.py:105, 268-272) and a second one for the goal rectangle,
+seeded with ``randint(2**32)`` of the first (env.py:166, 346; rewarder.py:
+211-259); environment i is seeded ``seed + i`` (utils.py:433, 530-532).
+``vector_rng=True`` replaces the 2E streams by one vectorised stream (same
+distributions, not the reference's draw sequence) for very large batches.
 """
 import numpy as np
 import torch
@@ -23,7 +30,10 @@ import torch
 from stackrl_b200 import capi
 from stackrl_b200.baselines import PlacementScorer
 from stackrl_b200.camera import HEIGHT_QUANTUM_LOG2
+from stackrl_b200.episodes import EpisodeSampler
 from stackrl_b200.observer import BatchedObserver
+
+METRIC_NAMES = ('IoU', 'OR', 'DIoU', 'DOR')      # Rewarder.metrics (rewarder.py:7)
 
 
 class BatchedStackEnv(object):
@@ -33,10 +43,14 @@ class BatchedStackEnv(object):
                observable_size_ratio=4, resolution_factor=5, max_z=0.375,
                rewarder=None, goal_size_ratio=.25, reward_scale=1., reward_params=None,
                orientation_freedom=0, dtype='float32', settle=None, seed=None,
-               device=None):
+               device=None, vector_rng=False):
     """Arguments follow StackEnv (env.py:28-50); ``bank`` is the MeshBank of
     candidate rocks (the reference's ``urdfs`` list), ``orientation_freedom``
-    the TestStackEnv option (env.py:443-463), ``settle`` the physics hook."""
+    the TestStackEnv option (env.py:443-463), ``settle`` the physics hook:
+    ``settle(mesh_ids [E], positions [E,3], quaternions [E,4]) -> (positions,
+    quaternions)`` of the new rocks at rest, optionally followed by a third item,
+    the rest poses [E, n_placed, 7] of ALL placed rocks including the new one
+    (Simulator.positions re-reads every body, simulator.py:86-92)."""
     if dtype not in self.metadata['dtypes']:
       raise ValueError('Invalid value {} for argument dtype.'.format(dtype))
     if len(bank) == 0:
@@ -55,20 +69,24 @@ class BatchedStackEnv(object):
     self.obs = BatchedObserver(
       bank, self.E, self._length, overhead_resolution, object_resolution,
       object_max_dimension / object_resolution, max_z, orientation_freedom,
-      spawn_pose=((0., 0., max_z + object_max_dimension), (0., 0., 0., 1.)), device=device)
+      spawn_pose=((0., 0., max_z + object_max_dimension), (0., 0., 0., 1.)), device=device,
+      episode_length=self._length)
     self.dev = self.obs.dev
     g = self.obs.geo
     self.R = g.n_orientations
     self._settle = settle
     # -- rewards (rewarder.py:17-142) --------------------------------------------- #
     metric = 'iou' if rewarder is None else str(rewarder).lower()
-    if metric not in ('iou', 'or', 'dor', 'diou'):
+    if metric not in capi.METRICS:
       raise ValueError('Invalid value {} for argument metric'.format(rewarder))
     self.metric = metric
     self.scale = float(reward_scale) if reward_scale is not None else float(episode_length)
     if reward_params is None:
       self._pexp = self._oexp = None
     elif np.isscalar(reward_params):
+      if reward_params < 0:
+        raise ValueError('Invalid value {} for argument params. Must be non negative.'.format(
+          reward_params))
       self._pexp = self._oexp = reward_params
     else:
       self._pexp, self._oexp = (list(reward_params) * 2)[:2]
@@ -76,23 +94,27 @@ class BatchedStackEnv(object):
     self._goal_z = g.max_z
     self._goal_size_ratio = goal_size_ratio
     H, W = g.overhead_h, g.overhead_w
-    self.goals = torch.zeros((self.E, H, W), dtype=torch.float32, device=self.dev)
-    self._goal_z_d = torch.full((self.E,), self._goal_z, dtype=torch.float32, device=self.dev)
-    self.goal_lims = np.zeros((self.E, 2, 2), dtype='int64')
-    self._memory = np.zeros(self.E, dtype='float64')
-    # Per-environment episode state as arrays (no Python loop over E per step):
-    # rest pose / placement pose of every placed rock, rock order and cursor.
-    self._rest = np.zeros((self.E, self._length, 3), dtype='float64')
-    self._placed_at = np.zeros((self.E, self._length, 3), dtype='float64')
-    self._quats = np.zeros((self.E, self._length, 4), dtype='float64')
-    self._placed_quats = np.zeros((self.E, self._length, 4), dtype='float64')
-    self._n_placed = np.zeros(self.E, dtype='int64')
+    E = self.E
+    self.goals = torch.zeros((E, H, W), dtype=torch.float32, device=self.dev)
+    self._goal_z_d = torch.full((E,), self._goal_z, dtype=torch.float32, device=self.dev)
+    self.goal_lims = np.zeros((E, 2, 2), dtype='int64')
+    self._rects_d = torch.zeros((E, 4), dtype=torch.int32, device=self.dev)
+    self._zero_reward = torch.zeros(E, dtype=torch.float32, device=self.dev)
     self._Ph, self._Pw = H - g.object_h + 1, W - g.object_w + 1
+    # uint8 observations: StackEnv._return's scale and the level the quantised goal
+    # plane reaches (env.py:171-178): trunc(goal_z * 255 / scale) in float32.
+    self._scale = max(self._max_z, self._omd)
+    level8 = np.array(np.float32(self._goal_z) * np.float32(255) / np.float32(self._scale))
+    self._level8_d = torch.full((E,), int(level8.astype('uint8')), dtype=torch.uint8,
+                                device=self.dev)
+    # host mirror of the (deterministic) episode cursors: no device read-back
+    self._order = np.zeros((E, self._length), dtype='int32')
+    self._cursor = np.zeros(E, dtype='int64')
+    self._done = np.ones(E, dtype=bool)
+    self._sampler = EpisodeSampler(E, len(bank), self._length, (H, W), (g.object_h, g.object_w),
+                                   goal_size_ratio, vector=vector_rng)
+    self._graph = None
     self.seed(seed)
-    self._done = np.ones(self.E, dtype=bool)
-    self._order = np.zeros((self.E, self._length), dtype='int64')
-    self._cursor = np.zeros(self.E, dtype='int64')     # rocks consumed so far
-    self._current = np.zeros(self.E, dtype='int64')
 
   # -- ParallelEnv-style metadata (utils.py:185-300) --------------------------------- #
   @property
@@ -116,10 +138,10 @@ class BatchedStackEnv(object):
     return ((self.R, n), 'int64') if self.R > 1 else (n, 'int64')
 
   def seed(self, seed=None):
-    """Per-environment streams seeded seed + i (utils.py:433, 530-532)."""
-    if seed is None:
-      seed = int(np.random.SeedSequence().generate_state(1)[0])
-    self._rngs = [np.random.RandomState((seed + i) % 2 ** 32) for i in range(self.E)]
+    """Per-environment streams seeded seed + i (utils.py:433, 530-532); the goal
+    stream of each environment is seeded from its rock stream like
+    StackEnv.seed -> Rewarder.seed (env.py:340-346, rewarder.py:196-200)."""
+    seed = self._sampler.seed(seed)
     self._action_rng = np.random.RandomState(seed % 2 ** 32)
     return [seed]
 
@@ -130,118 +152,191 @@ class BatchedStackEnv(object):
       return torch.from_numpy(self._action_rng.randint(self.R, size=self.E)), flat
     return flat
 
-  # -- goal (rewarder.py:211-259) ------------------------------------------------------ #
-  def _new_goal(self, rng):
-    g = self.obs.geo
-    H, W = g.overhead_h, g.overhead_w
-    min_h, min_w, max_h, max_w = g.object_h, g.object_w, H, W
-    ratio = self._goal_size_ratio
-    if not ratio:
-      b = 1 + rng.randint(2) * 2
-      h = int(min_h + rng.beta(b, 4 - b) * (min_h - min_h))       # quirk Q13
-      w = int(min_w + rng.beta(4 - b, b) * (max_w - min_w))
-    elif np.isscalar(ratio):
-      size = int(ratio * H * W)
-      min_h = max(min_h, size // max_w)
-      max_h = min(max_h, size // min_w)
-      b = 1 + rng.randint(2) * 2
-      h = int(min_h + rng.beta(b, 4 - b) * (max_h - min_h))
-      w = min(max(min_w, size // h), max_w)
-    else:
-      size = tuple(int(s * r) for s, r in zip(ratio, (H, W)))
-      i = rng.randint(2)
-      h, w = min(size[i], max_h), min(size[1 - i], max_w)
-    u_max, v_max = H - h, W - w
-    u = rng.randint(u_max // 8, 7 * u_max // 8 + 1)
-    v = rng.randint(v_max // 8, 7 * v_max // 8 + 1)
-    return u, v, h, w
-
   def set_goals(self, lims, env_ids=None):
-    """Install goal rectangles ((u, v), (u+h, v+w)) (rewarder.py:252-258)."""
-    env_ids = range(self.E) if env_ids is None else env_ids
-    goals = np.zeros((len(lims),) + tuple(self.goals.shape[1:]), dtype='float32')
-    for k, ((u0, v0), (u1, v1)) in enumerate(lims):
-      goals[k, u0:u1, v0:v1] = self._goal_z
-    ids = torch.as_tensor(list(env_ids), device=self.dev, dtype=torch.long)
-    self.goals[ids] = torch.from_numpy(goals).to(self.dev)
-    self.goal_lims[list(env_ids)] = np.asarray(lims, dtype='int64')
+    """Install goal rectangles ((u, v), (u+h, v+w)) (rewarder.py:252-258): the
+    limits go to the device, the maps are filled there."""
+    ids = np.arange(self.E) if env_ids is None else np.asarray(list(env_ids), dtype='int64')
+    self.goal_lims[ids] = np.asarray(lims, dtype='int64').reshape(len(ids), 2, 2)
+    self._rects_d.copy_(torch.from_numpy(
+      np.ascontiguousarray(self.goal_lims.reshape(self.E, 4), dtype='int32')), non_blocking=True)
+    if env_ids is None:
+      capi.fill_goals(self._rects_d, self._goal_z_d, self.goals)
+    else:
+      rects = torch.from_numpy(np.ascontiguousarray(
+        self.goal_lims[ids].reshape(len(ids), 4), dtype='int32')).to(self.dev, non_blocking=True)
+      ids_d = torch.from_numpy(ids.astype('int32')).to(self.dev, non_blocking=True)
+      capi.fill_goals(rects, self._goal_z_d, self.goals, env_ids=ids_d)
 
   # -- episode control ----------------------------------------------------------------- #
   def reset(self, env_ids=None, rock_orders=None, goal_lims=None):
     """Start new episodes (env.py:266-293).  ``rock_orders`` / ``goal_lims``
     override the random draws (used to replay recorded episodes)."""
-    ids = list(range(self.E)) if env_ids is None else list(env_ids)
-    lims = []
-    for k, e in enumerate(ids):
-      rng = self._rngs[e]
-      if rock_orders is not None:
-        order = list(rock_orders[k])
-      else:
-        order = list(rng.choice(len(self.bank), size=self._length, replace=self._replace))
-      self._order[e] = order[::-1]       # the reference pops from the end (env.py:245)
-      self._cursor[e] = 1
-      self._current[e] = self._order[e, 0]
-      if goal_lims is not None:
-        lims.append(goal_lims[k])
-      else:
-        u, v, h, w = self._new_goal(rng)
-        lims.append(((u, v), (u + h, v + w)))
-      self._n_placed[e] = 0
-      self._memory[e] = 0.
-      self._done[e] = False
-    self.set_goals(lims, ids)
-    self.obs.reset(None if env_ids is None else ids)
+    ids = np.arange(self.E) if env_ids is None else np.asarray(list(env_ids), dtype='int64')
+    n = len(ids)
+    # draw order of the reference: episode list first (env.py:268-272), then the
+    # goal (rewarder.reset, env.py:283); an override skips that draw
+    if rock_orders is not None:
+      orders = np.asarray(rock_orders, dtype='int64').reshape(n, self._length)
+    else:
+      orders = self._sampler.orders(ids)
+    if goal_lims is not None:
+      lims = np.asarray(goal_lims, dtype='int64').reshape(n, 2, 2)
+    else:
+      lims = self._sampler.goals(ids)
+    self._order[ids] = orders[:, ::-1]       # the reference pops from the end (env.py:245)
+    self._cursor[ids] = 1
+    self._done[ids] = False
+    self.set_goals(lims, None if env_ids is None else ids)
+    self.obs.begin(self._order, None if env_ids is None else ids)
+    self._observe()
+    return self.observation, self._zero_reward, self.obs.state.done.view(torch.bool)
+
+  @property
+  def _current(self):
+    """Mesh id of the spawned rock of every environment (host mirror)."""
+    rows = np.arange(self.E)
+    return self._order[rows, np.maximum(self._cursor, 1) - 1].astype('int64')
+
+  @property
+  def _n_placed(self):
+    return self.obs.state.n_placed.cpu().numpy().astype('int64')
+
+  @property
+  def _rest(self):
+    """Rest positions [E, length, 3] of the placed rocks (device history)."""
+    return self.obs.state.hist_rest.cpu().numpy()[..., :3]
+
+  @property
+  def _quats(self):
+    return self.obs.state.hist_rest.cpu().numpy()[..., 3:]
+
+  def _observe(self):
     self.obs.observe_walls()
-    self.obs.observe_rocks(self._current)
-    return self.observation, torch.zeros(self.E, device=self.dev), \
-      torch.zeros(self.E, dtype=torch.bool, device=self.dev)
+    self.obs.observe_rocks()
+
+  def _pack(self, out=None):
+    wall_goal, rock = capi.pack_obs(self.obs.walls, self.goals, self.obs.rocks,
+                                    dtype=self._dtype, scale=self._scale,
+                                    repeat_wall=self.R > 1, out=out)
+    return wall_goal, (rock if self.R > 1 else rock[:, 0])
 
   @property
   def observation(self):
     """Packed observation in the env dtype (env.py:226-231; the TestStackEnv
     layout of env.py:472-480 when orientation_freedom > 0)."""
-    scale = max(self._max_z, self._omd)
-    wall_goal, rock = capi.pack_obs(self.obs.walls, self.goals, self.obs.rocks,
-                                    dtype=self._dtype, scale=scale,
-                                    repeat_wall=self.R > 1)
-    if self.R == 1:
-      rock = rock[:, 0]
-    return wall_goal, rock
+    return self._pack()
 
   def planes(self):
     """Planar float32 maps for device-side scoring: (walls, goals, rocks)."""
     return self.obs.walls, self.goals, self.obs.rocks
 
-  def step(self, action):
-    """action: [E] flat indices, or (views [E], flat indices [E]) when
-    orientation_freedom > 0 (env.py:233-264, 482-520)."""
-    if self._done.any():
-      raise RuntimeError('reset() the finished environments before stepping them')
+  def planes_u8(self):
+    """The same maps cast like the uint8 observation (env.py:171-178), planar."""
+    self._planes8 = capi.quantise_planes(self.obs.walls, self.goals, self.obs.rocks,
+                                         self._scale, out=getattr(self, '_planes8', None))
+    return self._planes8
+
+  # -- one step ------------------------------------------------------------------------- #
+  def _as_action(self, action):
     if self.R > 1:
       views, flat = action
     else:
-      views, flat = np.zeros(self.E, dtype='int64'), action
-    positions, quats = self.obs.poses(views, flat)
-    place_positions, place_quats = positions.copy(), quats.copy()
-    if self._settle is not None:
-      positions, quats = self._settle(self._current.copy(), positions, quats)
-    self.obs.place(self._current, positions, quats)
-    rows = np.arange(self.E)
-    self._rest[rows, self._n_placed] = positions
-    self._placed_at[rows, self._n_placed] = place_positions
-    self._quats[rows, self._n_placed] = quats
-    self._placed_quats[rows, self._n_placed] = place_quats
-    self._n_placed += 1
+      views, flat = None, action
+    def dev64(a):
+      if a is None:
+        return None
+      if isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.int64:
+        return a
+      a = a.cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+      return torch.from_numpy(np.ascontiguousarray(a, dtype='int64')).to(self.dev)
+    return dev64(views), dev64(flat)
+
+  def _step_device(self, views, flat):
+    """The kernel chain of one step (no host synchronisation when settle is None)."""
+    obs = self.obs
+    obs.poses_device(views, flat)
+    if self._settle is None:
+      obs.advance()
+    else:
+      placed = obs.pose_buf.cpu().numpy()
+      if bool(obs.status.any()):
+        raise AssertionError('Invalid action.')
+      res = self._settle(self._current.copy(), placed[:, :3].copy(), placed[:, 3:].copy())
+      rest = np.concatenate([np.asarray(res[0], dtype='float64').reshape(self.E, 3),
+                             np.asarray(res[1], dtype='float64').reshape(self.E, 4)], axis=1)
+      obs.advance(torch.from_numpy(np.ascontiguousarray(rest)).to(self.dev), obs.pose_buf)
+      if len(res) > 2 and res[2] is not None:
+        obs.set_poses(res[2])
+    self._observe()
+    return self._reward()
+
+  def step(self, action):
+    """action: [E] flat indices, or (views [E], flat indices [E]) when
+    orientation_freedom > 0 (env.py:233-264, 482-520).  Device int64 tensors are
+    used in place; anything else is uploaded."""
+    if self._done.any():
+      raise RuntimeError('reset() the finished environments before stepping them')
+    views, flat = self._as_action(action)
+    if self._graph is not None and self._graph_policy is None:
+      if views is not None:
+        self._g_views.copy_(views, non_blocking=True)
+      self._g_flat.copy_(flat, non_blocking=True)
+      self._graph.replay()
+      reward, observation = self._g_reward, self._g_obs
+    else:
+      reward = self._step_device(views, flat)
+      observation = self.observation
+    self._advance_host()
+    return observation, reward, self.obs.state.done.view(torch.bool)
+
+  def _advance_host(self):
     more = self._cursor < self._length
-    self._current = np.where(more, self._order[rows, np.minimum(self._cursor, self._length - 1)],
-                             self._current)
     self._cursor += more
     self._done = ~more
-    self.obs.observe_walls()
-    self.obs.observe_rocks(self._current)
-    reward = self._reward()
-    terminal = torch.from_numpy(self._done.copy()).to(self.dev)
-    return self.observation, reward, terminal
+
+  def check_actions(self):
+    """Synchronises and raises like env.py:237 if any action of the steps so far
+    was outside the action space (such actions place nothing valid: NaN pose)."""
+    if bool(self.obs.status.any()):
+      raise AssertionError('Invalid action.')
+
+  # -- CUDA graph ------------------------------------------------------------------------ #
+  def capture(self, policy=None):
+    """Record one step -- ``policy(self)`` first when given -- as ONE CUDA graph.
+    Afterwards ``step(action)`` (or ``step_policy()``) replays it: one launch per
+    step instead of 7-9.  Needs settle=None (a host hook cannot be captured) and
+    at least one eager step before (lazy kernel attributes).  Returns self."""
+    if self._settle is not None:
+      raise RuntimeError('a settle hook runs on the host and cannot be captured')
+    dev = self.dev
+    self._g_views = torch.zeros(self.E, dtype=torch.int64, device=dev) if self.R > 1 else None
+    self._g_flat = torch.zeros(self.E, dtype=torch.int64, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    stream.wait_stream(torch.cuda.current_stream(dev))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+      with torch.cuda.graph(graph, stream=stream):
+        if policy is not None:
+          action = policy(self)
+          views, flat = self._as_action(action)
+          self._g_action = action
+        else:
+          views, flat = self._g_views, self._g_flat
+        self._g_reward = self._step_device(views, flat)
+        self._g_obs = self._pack()
+    torch.cuda.current_stream(dev).wait_stream(stream)
+    self._graph, self._graph_policy = graph, policy
+    return self
+
+  def step_policy(self):
+    """Replay the graph captured with a policy: action selection + step."""
+    if self._graph is None or self._graph_policy is None:
+      raise RuntimeError('capture(policy) first')
+    if self._done.any():
+      raise RuntimeError('reset() the finished environments before stepping them')
+    self._graph.replay()
+    self._advance_host()
+    return self._g_obs, self._g_reward, self.obs.state.done.view(torch.bool)
 
   # -- rewards (rewarder.py:144-179, 261-307) ------------------------------------------ #
   def reward_terms(self):
@@ -249,41 +344,20 @@ class BatchedStackEnv(object):
     return capi.reward_sums(self.obs.walls, self.goals, self._goal_z_d)
 
   def _reward(self):
-    if self.metric in ('iou', 'or'):
-      inter, uni, vol = self.reward_terms()
-      value = inter / uni if self.metric == 'iou' else inter / vol
-      value = value.double().cpu().numpy()
-    else:
-      # DOR / DIoU (rewarder.py:261-295): per placed rock, inside-goal test on its
-      # rest position and the distance discount from where it was placed.
-      g = self.obs.geo
-      live = np.arange(self._length)[None, :] < self._n_placed[:, None]
-      u = self._rest[..., 0] // g.pixel_h
-      v = self._rest[..., 1] // g.pixel_w
-      lims = self.goal_lims
-      inside = live & (u >= lims[:, 0, 0, None]) & (v >= lims[:, 0, 1, None]) & \
-        (u < lims[:, 1, 0, None]) & (v < lims[:, 1, 1, None])
-      perr = np.linalg.norm(self._placed_at - self._rest, axis=-1)
-      disc = np.ones_like(perr)
-      if self._pexp is not None:
-        disc = disc * np.maximum(0., 1 - (perr / self._pmax) ** self._pexp)
-      if self._oexp is not None:
-        # rotation distance 2*acos(min(w, 1)) of the difference quaternion
-        # (simulator.py:116-117); w = <q_placed, q_rest> for unit quaternions
-        w = np.minimum((self._placed_quats * self._quats).sum(axis=-1), 1.)
-        oerr = 2 * np.arccos(np.where(live, w, 1.))
-        disc = disc * np.maximum(0., 1 - (oerr / np.pi) ** self._oexp)
-      total = np.where(inside, disc, 0.).sum(axis=1)
-      n_out = (live & ~inside).sum(axis=1)
-      value = total / self._length if self.metric == 'dor' else total / (self._length + n_out)
-    out = (value - self._memory) * self.scale
-    self._memory = value
-    return torch.from_numpy(out.astype('float32')).to(self.dev)
+    g = self.obs.geo
+    r = capi.rewards(self.obs.state, self.obs.walls, self.goals, self._goal_z_d, self._rects_d,
+                     self.metric, self.scale, (g.pixel_h, g.pixel_w), self._pmax, self._pexp,
+                     self._oexp)
+    if self.metric == 'all':
+      # the reference returns the four metrics as the info dict (env.py:258-262)
+      return {name: r[:, k] for k, name in enumerate(METRIC_NAMES)}
+    return r
 
 
 class HeightPolicy(object):
   """Device-side ``Baseline('height', batched=True, batchwise=True)`` for a
-  BatchedStackEnv: returns the action tensor(s) ``step`` expects."""
+  BatchedStackEnv: returns the action tensor(s) ``step`` expects (column views of
+  the selection kernel's ``best`` table, read in place by the pose kernel)."""
 
   def __init__(self, goal=True, minorder=1, threshold=0.75):
     # float32 maps come straight from the rasteriser: multiples of 2^-14 m
@@ -291,19 +365,13 @@ class HeightPolicy(object):
                                    quantum_log2=HEIGHT_QUANTUM_LOG2)
 
   def __call__(self, env):
-    walls, goals, rocks = env.planes()
     if env._dtype == 'uint8':
       # The reference policy scores the observation it is given: for the
       # registered uint8 envs that is the quantised maps (float64 arithmetic).
-      wall_goal, rock = env.observation
-      if env.R > 1:
-        wall_goal = wall_goal[:, 0]
-      walls = wall_goal[..., 0].contiguous()
-      goals = wall_goal[..., 1].contiguous()
-      rocks = rock[..., 0].contiguous()
-      if env.R == 1:
-        rocks = rocks[:, None].contiguous()
-    # a goal rectangle is never empty, so goal.max() is the goal height
-    level = env._goal_z_d if walls.dtype == torch.float32 else None
+      walls, goals, rocks = env.planes_u8()
+      level = env._level8_d
+    else:
+      walls, goals, rocks = env.planes()
+      level = env._goal_z_d          # a goal rectangle is never empty: goal.max() == goal_z
     best = self._scorer(walls, goals, rocks, level=level)['best']
     return (best[:, 0], best[:, 1]) if env.R > 1 else best[:, 1]

@@ -36,8 +36,9 @@ class PybulletScene(object):
 
   Written against pybullet's documented query API (getNumBodies,
   getBodyUniqueId, getVisualShapeData, getBasePositionAndOrientation); pybullet
-  is not installable in the build image, so this adapter is exercised only
-  through the fake backend's identical surface in tests."""
+  is not installable in the build image, so this adapter is exercised through the
+  fake backend's restatement of that surface (oracle/fake_pybullet.py;
+  tests/test_observer_host.py)."""
 
   GEOM_BOX, GEOM_MESH = 3, 5
 
@@ -79,6 +80,67 @@ class PybulletScene(object):
         out.append((v, t, rot.dot(camera.rotation_matrix(lorn)),
                     np.asarray(pos) + rot.dot(np.asarray(lpos))))
     return out
+
+
+class GpuCamera(object):
+  """Seam b2: a simulator proxy whose ``getCameraImage`` is the CUDA
+  rasteriser, so that the reference's UNMODIFIED ``Observer`` -- which asks its
+  simulator for ``getCameraImage(width=, height=, viewMatrix=, projectionMatrix=)``
+  and applies the depth -> elevation arithmetic itself (observer.py:252-260,
+  267-277) -- runs on the GPU path without a line changed:
+
+      env = StackEnv(..., simulator=lambda **kw: GpuCamera(Simulator(**kw)))
+
+  Every other attribute (camera matrices, transforms, ``new_pose``,
+  ``has_new_object``, the physics calls) is forwarded to the wrapped simulator.  The
+  scene comes from the simulator's ``scene()`` when it has one, else from pybullet's
+  own query API (``PybulletScene``).  Returns pybullet's 5-tuple
+  ``(width, height, rgb, depth, segmentation)`` with ``depth`` a fresh float32
+  [height, width] array in [0, 1] (GL convention, background 1) and ``rgb`` /
+  ``segmentation`` ``None`` (the reference discards them)."""
+
+  def __init__(self, simulator, device=None):
+    object.__setattr__(self, '_sim', simulator)
+    object.__setattr__(self, '_scene', simulator.scene if hasattr(simulator, 'scene')
+                       else PybulletScene(simulator))
+    object.__setattr__(self, '_device', device)
+
+  def __getattr__(self, name):
+    return getattr(object.__getattribute__(self, '_sim'), name)
+
+  def __setattr__(self, name, value):
+    setattr(object.__getattribute__(self, '_sim'), name, value)
+
+  def getCameraImage(self, width, height, viewMatrix, projectionMatrix, **_):
+    dev = object.__getattribute__(self, '_device') or _device()
+    bodies = object.__getattribute__(self, '_scene')()
+    verts, tris, inst = _instances(bodies)
+    job = _job(viewMatrix, projectionMatrix, 0, len(inst), 0.)
+    depth = capi.raster(torch.from_numpy(verts).to(dev), torch.from_numpy(tris).to(dev), inst,
+                        job, int(height), int(width), capi.RASTER_DEPTH)
+    return int(width), int(height), None, depth[0].cpu().numpy(), None
+
+
+def gpu_simulator_class(base):
+  """Seam b2 as a subclass: ``base`` is the reference's ``Simulator``
+  (simulator.py); the returned class is a ``Simulator`` (so it passes Rewarder's
+  isinstance gate, rewarder.py:52-57) whose ``getCameraImage`` -- which the base
+  class forwards to pybullet's TinyRenderer (simulator.py:57-61) -- is the CUDA
+  rasteriser.  ``StackEnv(simulator=gpu_simulator_class(Simulator))`` then runs the
+  reference's unmodified Observer, Rewarder and env on GPU depth images."""
+
+  class GpuCameraSimulator(base):
+    def getCameraImage(self, width, height, viewMatrix, projectionMatrix, **_):
+      if not hasattr(self, '_gpu_scene'):
+        self._gpu_scene = PybulletScene(self)      # pybullet's own scene queries
+      dev = _device()
+      verts, tris, inst = _instances(self._gpu_scene())
+      job = _job(viewMatrix, projectionMatrix, 0, len(inst), 0.)
+      depth = capi.raster(torch.from_numpy(verts).to(dev), torch.from_numpy(tris).to(dev),
+                          inst, job, int(height), int(width), capi.RASTER_DEPTH)
+      return int(width), int(height), None, depth[0].cpu().numpy(), None
+
+  return GpuCameraSimulator
 
 
 def _instances(bodies):
@@ -148,15 +210,23 @@ def gpu_observer_class(base=object):
       self._multi_object = object_pose is None
       self._object_orientations = [] if self._multi_view else None
       self._object_indexes = [] if self._multi_object else None
-      self._dev = _device()
-      self._wall_d = torch.zeros((1, g.overhead_h, g.overhead_w), dtype=torch.float32,
-                                 device=self._dev)
+      # The CUDA device is taken at the first capture, not here: the constructor
+      # has to work wherever the reference's own does (e.g. to pass Rewarder's
+      # isinstance gate, rewarder.py:58-63, in a process that only builds the env).
+      self._dev_cache = None
+      self._wall_d = None
       self._rock_d = None
       self._overhead_map = np.zeros((g.overhead_h, g.overhead_w), dtype='float32')
       if self._multi_view or self._multi_object:
         self._object_map = []
       else:
         self._object_map = np.zeros((g.object_h, g.object_w), dtype='float32')
+
+    @property
+    def _dev(self):
+      if self._dev_cache is None:
+        self._dev_cache = _device()
+      return self._dev_cache
 
     # -- capture ---------------------------------------------------------------- #
     def _render(self, jobs, rows, cols, mode, bodies):
@@ -280,15 +350,17 @@ GpuObserver = gpu_observer_class(object)
 class BatchedObserver(object):
   """E environments observed at once; everything stays on the GPU.
 
-  ``bank`` is the MeshBank of rock meshes.  Per environment the observer keeps
-  a fixed-capacity table of placed instances on the device (a placed rock is
-  appended with ``place``; with real physics every pose can be rewritten with
-  ``set_poses``).  ``walls`` [E,H,W] and ``rocks`` [E,R,h,h] are float32 CUDA
-  tensors in the reference's float32 elevation arithmetic."""
+  ``bank`` is the MeshBank of rock meshes.  Per environment the observer keeps a
+  fixed-capacity table of placed instances on the device plus the episode
+  bookkeeping of ``srl_env_state`` (rock order, cursor, pose history), so a step is
+  a chain of kernels with no device->host round trip: ``poses_device`` (a4) ->
+  ``advance`` (instance append + next rock) -> ``observe_walls`` / ``observe_rocks``
+  (a2/a3).  ``walls`` [E,H,W] and ``rocks`` [E,R,h,h] are float32 CUDA tensors in the
+  reference's float32 elevation arithmetic."""
 
   def __init__(self, bank, envs, capacity, overhead_resolution=128, object_resolution=32,
                pixel_size=0.125 / 32, max_z=0.375, orientation_freedom=0,
-               spawn_pose=None, device=None):
+               spawn_pose=None, device=None, episode_length=None):
     self.geo = g = camera.ObserverGeometry(
       overhead_resolution, object_resolution, pixel_size, max_z, orientation_freedom)
     self.bank = bank
@@ -297,20 +369,27 @@ class BatchedObserver(object):
     self.spawn_pose = spawn_pose if spawn_pose is not None else \
       ((0., 0., max_z + g.object_z), (0., 0., 0., 1.))
     self._verts, self._tris = bank.device(self.dev)
-    self._ranges = np.asarray(bank.ranges, dtype='int32').reshape(-1, 4)
-    self._coms = np.asarray(bank.coms, dtype='float64').reshape(-1, 3)
+    self._ranges = np.ascontiguousarray(np.asarray(bank.ranges, dtype='int32').reshape(-1, 4))
+    self._coms = np.ascontiguousarray(np.asarray(bank.coms, dtype='float64').reshape(-1, 3))
     E, cap, R = self.E, self.cap, self.R
-    # -- device tables (byte tensors holding the C structs) ---------------------- #
     isz, jsz = capi.INSTANCE_DTYPE.itemsize, capi.JOB_DTYPE.itemsize
-    self._inst = torch.zeros(E * cap * isz, dtype=torch.uint8, device=self.dev)
-    self._inst_rows = self._inst.view(torch.float64).view(E * cap, isz // 8)
+    # Instance row of every mesh of the bank at the spawn pose: observing a new
+    # rock is a device-side row copy by mesh id, no per-step host work.
+    n = len(bank)
+    spawn_rows = self._rows(np.arange(n), [self.spawn_pose[0]] * n, [self.spawn_pose[1]] * n)
+    self._spawn_rows = self._upload_rows(spawn_rows)
+    self.state = capi.EnvState(
+      E, cap, int(episode_length if episode_length is not None else cap),
+      torch.from_numpy(self._ranges).to(self.dev), torch.from_numpy(self._coms).to(self.dev),
+      self._spawn_rows, self.dev)
+    self._inst = self.state.instances
+    self._rock_inst = self.state.rock_instances
+    self.counts = self.state.counts
     jobs = np.zeros(E, dtype=capi.JOB_DTYPE)
     jobs['view'], jobs['proj'] = g.overhead_view, g.overhead_projection
     jobs['inst_begin'] = np.arange(E) * cap
     jobs['zrange'] = g.overhead_z
     self._wall_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(self.dev)
-    self._wall_counts = self._wall_jobs.view(torch.int32).view(E, jsz // 4)[:, 65]
-    self.counts = torch.zeros(E, dtype=torch.int32, device=self.dev)
     jobs = np.zeros((E, R), dtype=capi.JOB_DTYPE)
     for k in range(R):
       jobs[:, k]['view'] = g.object_view(self.spawn_pose, k)
@@ -319,12 +398,14 @@ class BatchedObserver(object):
     jobs['inst_count'] = 1
     jobs['zrange'] = g.object_z
     self._rock_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(self.dev)
-    self._rock_inst = torch.zeros(E * isz, dtype=torch.uint8, device=self.dev)
-    # Instance row of every mesh of the bank at the spawn pose: observing a new
-    # rock is then a device-side gather by mesh id, no per-step host work.
-    n = len(bank)
-    spawn_rows = self._rows(np.arange(n), [self.spawn_pose[0]] * n, [self.spawn_pose[1]] * n)
-    self._spawn_rows = self._upload_rows(spawn_rows)
+    # every orientation's camera looks at the same instance: the per-job instance
+    # count of the wall images is the environment's `counts` entry, read on the device
+    self._max_verts = int(self._ranges[:, 1].max()) if n else 0
+    self._orientations = torch.from_numpy(
+      np.ascontiguousarray(np.asarray(g.orientations, dtype='float64').reshape(R, 4))).to(self.dev)
+    self._pose_geometry = (g.pixel_h, g.pixel_w, g.object_x, g.object_y, g.object_z)
+    self.pose_buf = torch.zeros((E, 7), dtype=torch.float64, device=self.dev)
+    self.status = torch.zeros((E,), dtype=torch.int32, device=self.dev)
     self.walls = torch.zeros((E, g.overhead_h, g.overhead_w), dtype=torch.float32,
                              device=self.dev)
     self.rocks = torch.zeros((E, R, g.object_h, g.object_w), dtype=torch.float32,
@@ -344,7 +425,11 @@ class BatchedObserver(object):
                     s * (x * z - y * w), s * (y * z + x * w), 1.0 - s * (x * x + y * y)], -1)
     rows = np.zeros(len(mesh_ids), dtype=capi.INSTANCE_DTYPE)
     rows['rot'] = rot
-    rows['pos'] = p - np.einsum('nij,nj->ni', rot.reshape(-1, 3, 3), self._coms[mesh_ids])
+    com = self._coms[mesh_ids]
+    r3 = rot.reshape(-1, 3, 3)
+    # same left-to-right sum as the device kernel (srl_env_advance)
+    rows['pos'] = p - ((r3[:, :, 0] * com[:, None, 0] + r3[:, :, 1] * com[:, None, 1]) +
+                       r3[:, :, 2] * com[:, None, 2])
     rng = self._ranges[mesh_ids]
     rows['vert_begin'], rows['vert_count'] = rng[:, 0], rng[:, 1]
     rows['tri_begin'], rows['tri_count'] = rng[:, 2], rng[:, 3]
@@ -354,6 +439,18 @@ class BatchedObserver(object):
     return torch.from_numpy(rows.view(np.uint8).reshape(len(rows), -1)).to(
       self.dev, non_blocking=True).view(torch.float64)
 
+  # -- episodes --------------------------------------------------------------------- #
+  def begin(self, orders, env_ids=None):
+    """Start episodes (env.py:266-293): ``orders`` is the full [E, length] host table
+    of mesh ids in pop order (uploaded whole); ``env_ids``: the environments to
+    restart (None: all)."""
+    st = self.state
+    st.order.copy_(torch.from_numpy(np.ascontiguousarray(orders, dtype='int32')),
+                   non_blocking=True)
+    ids = None if env_ids is None else torch.from_numpy(
+      np.ascontiguousarray(env_ids, dtype='int32')).to(self.dev, non_blocking=True)
+    capi.env_reset(st, ids)
+
   def reset(self, env_ids=None):
     """Forget the placed rocks of the given environments (all by default)."""
     if env_ids is None:
@@ -362,54 +459,71 @@ class BatchedObserver(object):
       self.counts[torch.as_tensor(env_ids, device=self.dev, dtype=torch.long)] = 0
 
   def place(self, mesh_ids, positions, quaternions, env_ids=None):
-    """Append one placed rock per environment."""
+    """Append one placed rock per environment from HOST poses (set-up paths and
+    tests; a step uses ``advance``)."""
     env_ids = torch.arange(self.E, device=self.dev) if env_ids is None else \
       torch.as_tensor(env_ids, device=self.dev, dtype=torch.long)
     rows = self._upload_rows(self._rows(mesh_ids, positions, quaternions))
     slot = env_ids * self.cap + self.counts[env_ids].long()
-    # (the caller bounds the number of placed rocks by `capacity`; a full table
-    # would otherwise need a device->host sync here on every step)
-    self._inst_rows.index_copy_(0, torch.clamp(slot, max=self.E * self.cap - 1), rows)
+    inst_rows = self._inst.view(torch.float64).view(self.E * self.cap, -1)
+    inst_rows.index_copy_(0, torch.clamp(slot, max=self.E * self.cap - 1), rows)
     self.counts[env_ids] = torch.clamp(self.counts[env_ids] + 1, max=self.cap)
+
+  def poses_device(self, views, flat):
+    """Observer.pose for every environment on the device (observer.py:392-421):
+    ``views`` [E] int64 or None, ``flat`` [E] int64 CUDA tensors (any stride).
+    Fills ``pose_buf`` [E,7] float64 = (x, y, z, qx, qy, qz, qw) and ``status``."""
+    capi.place_poses(self.walls, self.rocks, views, flat, self._orientations,
+                     self._pose_geometry, threshold=10 ** (-4), poses=self.pose_buf,
+                     status=self.status)
+    return self.pose_buf
+
+  def advance(self, rest=None, placed=None):
+    """The spawned rocks come to rest at ``rest`` [E,7] (default: where they were
+    placed, ``pose_buf``); next rock of every episode spawned (env.py:245-249)."""
+    capi.env_advance(self.state, self.pose_buf if rest is None else rest, placed)
+
+  def set_poses(self, poses):
+    """Rewrite the rest poses of the first n placed rocks of every environment:
+    ``poses`` [E,n,7] float64 (a physics step that disturbed earlier rocks)."""
+    poses = torch.as_tensor(np.ascontiguousarray(poses, dtype='float64')) \
+      if not isinstance(poses, torch.Tensor) else poses
+    capi.env_set_poses(self.state, poses.to(self.dev).contiguous())
 
   # -- capture -------------------------------------------------------------------- #
   def observe_walls(self):
     """Rasterise every environment's placed rocks into ``walls``
     (observer.py:252-260)."""
     g = self.geo
-    self._wall_counts.copy_(self.counts)
     capi.raster(self._verts, self._tris, self._inst, self._wall_jobs, g.overhead_h,
-                g.overhead_w, capi.RASTER_WALL, far_plane=FAR, out=self.walls)
+                g.overhead_w, capi.RASTER_WALL, far_plane=FAR, out=self.walls,
+                inst_counts=self.counts,
+                max_cached_verts=min(2048, max(256, self._max_verts * self.cap)))
     return self.walls
 
-  def observe_rocks(self, mesh_ids):
-    """Rasterise the undersides of the new rocks (one mesh per environment,
-    spawned at ``spawn_pose``) at every orientation into ``rocks``
-    (observer.py:262-293)."""
+  def observe_rocks(self, mesh_ids=None):
+    """Rasterise the undersides of the spawned rocks at every orientation into
+    ``rocks`` (observer.py:262-293).  ``mesh_ids`` (host array) replaces the
+    device-side episode state with explicit meshes (set-up paths)."""
     g = self.geo
-    ids = torch.as_tensor(np.asarray(mesh_ids, dtype='int64')).to(self.dev, non_blocking=True)
-    torch.index_select(self._spawn_rows, 0, ids,
-                       out=self._rock_inst.view(torch.float64).view(self.E, -1))
+    if mesh_ids is not None:
+      ids = torch.as_tensor(np.asarray(mesh_ids, dtype='int64')).to(self.dev, non_blocking=True)
+      torch.index_select(self._spawn_rows, 0, ids,
+                         out=self._rock_inst.view(torch.float64).view(self.E, -1))
     capi.raster(self._verts, self._tris, self._rock_inst, self._rock_jobs, g.object_h,
                 g.object_w, capi.RASTER_ROCK, far_plane=FAR,
-                out=self.rocks.view(self.E * self.R, g.object_h, g.object_w))
+                out=self.rocks.view(self.E * self.R, g.object_h, g.object_w),
+                max_cached_verts=max(256, self._max_verts))
     return self.rocks
 
   def poses(self, views, flat_actions):
-    """Observer.pose for every environment (observer.py:392-421):
+    """Observer.pose for every environment, on the host (observer.py:392-421):
     ``views`` [E] orientation index, ``flat_actions`` [E] row-major position.
-    Returns (positions [E,3] float64 numpy, quaternions [E,4])."""
-    g = self.geo
-    Pw = g.overhead_w - g.object_w + 1
-    views = torch.as_tensor(views, device=self.dev).to(torch.int32)
-    flat = torch.as_tensor(flat_actions, device=self.dev).to(torch.int32)
-    picks = torch.stack([views, flat // Pw, flat % Pw], dim=1).contiguous()
-    z = capi.drop_height_f32(self.walls, self.rocks, picks, threshold=10 ** (-4))
-    picks_h = picks.cpu().numpy()
-    z = z.cpu().numpy()
-    pos = np.empty((self.E, 3), dtype='float64')
-    pos[:, 0] = picks_h[:, 1] * g.pixel_h + g.object_x / 2
-    pos[:, 1] = picks_h[:, 2] * g.pixel_w + g.object_y / 2
-    pos[:, 2] = z - g.object_z / 2          # float32 array - weak scalar: float32, like numpy
-    quat = np.asarray(g.orientations, dtype='float64')[picks_h[:, 0]]
-    return pos, quat
+    Returns (positions [E,3] float64 numpy, quaternions [E,4]); raises on an
+    action outside the action space (env.py:237)."""
+    as_dev = lambda a: None if a is None else torch.as_tensor(
+      np.asarray(a.cpu() if isinstance(a, torch.Tensor) else a, dtype='int64')).to(self.dev)
+    poses = self.poses_device(as_dev(views), as_dev(flat_actions)).cpu().numpy()
+    if bool(self.status.any()):
+      raise AssertionError('Invalid action.')
+    return poses[:, :3].copy(), poses[:, 3:].copy()

@@ -74,6 +74,50 @@ def _episode(ns, fb, env_cls, urdfs, dtype, steps, policy_kwargs, out, prefix, *
   env.close()
 
 
+def make_goal_draws():
+  """a13 fixture: what the reference's two RandomState streams (StackEnv._random for
+  the episode list, env.py:268-272; Rewarder._random for the goal rectangle,
+  rewarder.py:211-259, seeded through env.seed -> Rewarder.seed, env.py:340-346)
+  draw for a given seed: rock order and goal limits of the first two episodes, for
+  24 seeds and the three goal_size_ratio modes (scalar, tuple, None)."""
+  fb = fake_pybullet.FakeBullet()
+  ns = refload.load(pybullet=fb)
+  names = ['0_0', '0_3', '50_000', '55_017', '60_250', '75_003', '80_499', '95_042']
+  urdfs = [os.path.join(ns.root, 'stackrl/envs/data/generated', n + '.urdf') for n in names]
+  index = {os.path.basename(u): k for k, u in enumerate(urdfs)}
+  loaded = []
+  real_load = fb.loadURDF
+
+  def logging_load(fileName, *a, **k):
+    loaded.append(index[os.path.basename(fileName)])
+    return real_load(fileName, *a, **k)
+  fb.loadURDF = logging_load
+  out = {'n_meshes': np.int64(len(urdfs))}
+  modes = [('scalar', .25, 6), ('tuple', (.5, .25), 12), ('none', None, 5)]
+  seeds = list(range(20)) + [123, 4242, 2 ** 31 + 5, 2 ** 32 - 2]
+  out['seeds'] = np.array(seeds, dtype='int64')
+  for tag, ratio, length in modes:
+    lims = np.zeros((len(seeds), 2, 2, 2), dtype='int64')
+    orders = np.zeros((len(seeds), 2, length), dtype='int64')
+    env = ns.env.StackEnv(urdfs=urdfs, seed=0, goal_size_ratio=ratio, episode_length=length)
+    for k, s in enumerate(seeds):
+      env.seed(s)
+      for ep in range(2):
+        del loaded[:]
+        env.reset()
+        lims[k, ep] = np.array(env._rew._goal_lims)
+        # pop order: the rock loaded by reset, then the list from its end (env.py:245)
+        rest = [index[os.path.basename(u)] for u in env._episode_list][::-1]
+        orders[k, ep] = [loaded[0]] + rest
+    env.close()
+    out[tag + '/goal_lims'] = lims
+    out[tag + '/orders'] = orders
+    out[tag + '/episode_length'] = np.int64(length)
+  path = os.path.join(HERE, 'goal_draws.npz')
+  np.savez_compressed(path, **out)
+  print('goal_draws.npz: {} arrays, {:.0f} KB'.format(len(out), os.path.getsize(path) / 1024))
+
+
 def main(ns=None):
   fb = fake_pybullet.FakeBullet()
   ns = refload.load(pybullet=fb)
@@ -114,3 +158,4 @@ def main(ns=None):
 
 if __name__ == '__main__':
   main()
+  make_goal_draws()

@@ -67,6 +67,57 @@ def test_batched_matches_oracle(capi, monkeypatch, shape, variant):
   assert np.array_equal(got, want)
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize('shape', [
+  # Few items per environment: a 32-item unit of the stream kernel spans more
+  # environments than the ring has slots unless the dispatcher refuses (a consumer
+  # would wait for a slot only its own completion can free: a hang, not an error).
+  (64, 1, 16, 16, 16),      # 1 item per environment, unit spans 32 environments
+  (8, 1, 64, 64, 60),       # 5 items per environment, 3 ring slots
+  (100, 2, 20, 16, 16),     # 10 items per environment
+  (300, 1, 32, 32, 32),     # one candidate position per map
+  (40, 1, 48, 48, 44),      # big rock, few positions
+])
+def test_tiny_maps_do_not_wrap_the_stream_ring(capi, shape):
+  E, R, H, W, h = shape
+  walls, rocks, level = synth.placement_batch(21, E, R, H, W, h)
+  dev = torch.device('cuda')
+  got = capi.maxplus_f32(torch.from_numpy(walls).to(dev), torch.from_numpy(rocks).to(dev),
+                         torch.from_numpy(level).to(dev))
+  torch.cuda.synchronize()
+  assert np.array_equal(got.cpu().numpy(), _oracle_maps(walls, rocks, level))
+
+
+def test_caller_buffers_are_validated(capi):
+  """An undersized / misplaced `out` is refused before any kernel writes into it."""
+  dev = torch.device('cuda')
+  walls, rocks, level = synth.placement_batch(1, 4, 2, 32, 32, 16)
+  w, r, l = (torch.from_numpy(x).to(dev) for x in (walls, rocks, level))
+  with pytest.raises(ValueError):
+    capi.maxplus_f32(w, r, l, out=torch.empty((4, 2, 17, 16), device=dev))
+  with pytest.raises(ValueError):
+    capi.maxplus_f32(w, r, l, out=torch.empty((4, 2, 17, 17)).pin_memory())
+  with pytest.raises(TypeError):
+    capi.maxplus_f32(w, r, l, out=torch.empty((4, 2, 17, 17), device=dev, dtype=torch.float64))
+  w8 = (w * 600).to(torch.uint8)
+  r8 = (r * 600).to(torch.uint8)
+  l8 = torch.full((4,), 170, dtype=torch.uint8, device=dev)
+  with pytest.raises(ValueError):
+    capi.maxplus_u8(w8, r8, l8, out=torch.empty((4, 2, 17), dtype=torch.float64, device=dev))
+
+
+def test_goal_level_kernel(capi):
+  """get_inputs' goal.max() (baselines.py:23) without a torch reduction."""
+  dev = torch.device('cuda')
+  goals = synth.goals(3, 37, 40, 24)
+  goals[5] = 0.
+  got = capi.goal_level(torch.from_numpy(goals).to(dev)).cpu().numpy()
+  assert np.array_equal(got, goals.reshape(37, -1).max(axis=1))
+  g8 = synth.to_dtype(goals, 'uint8')
+  got8 = capi.goal_level(torch.from_numpy(g8).to(dev)).cpu().numpy()
+  assert np.array_equal(got8, g8.reshape(37, -1).max(axis=1))
+
+
 def test_no_level_and_pose_threshold(capi):
   """level=None, threshold=1e-4: the Observer.pose mask (observer.py:405-409)."""
   E, R, H, W, h = 3, 2, 24, 24, 8

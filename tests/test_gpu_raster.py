@@ -159,25 +159,36 @@ def _fixture_bank(mods, g):
   return bank
 
 
+@pytest.mark.parametrize('drawn', [False, True])
 @pytest.mark.parametrize('name,dtype,freedom', [('stack_f32', 'float32', 0),
                                                 ('stack_u8', 'uint8', 0),
                                                 ('test_f32_rot8', 'float32', 3)])
-def test_batched_env_replays_reference_episode(mods, observe_golden, name, dtype, freedom):
+def test_batched_env_replays_reference_episode(mods, observe_golden, name, dtype, freedom, drawn):
   """BatchedStackEnv + the GPU height policy reproduce, step for step, the
   episode the UNMODIFIED reference StackEnv / TestStackEnv produced with
   Baseline('height') on the static fake backend: same observations (bitwise),
-  same actions, same rewards (IoU within 1e-6)."""
+  same actions, same four rewards (IoU / OR within 1e-6, DIoU / DOR exactly --
+  rows a11, a12).  ``drawn``: the rock order and the goal come from the
+  environment's own seed-7 streams instead of being handed over (row a13)."""
   g = observe_golden
   envs = mods['envs']
   bank = _fixture_bank(mods, g)
   steps = int(g[name + '/n_steps'])
   order = [bank.names[str(n)] for n in g[name + '/urdf_order']][::-1]
   lims = g[name + '/goal_lims']
-  E = 3                                                # three identical replicas
-  env = envs.BatchedStackEnv(bank, E, episode_length=steps, dtype=dtype, rewarder='iou',
-                             orientation_freedom=freedom, seed=0)
+  E = 3
+  # reward parameters of the golden run: rewarder='all', defaults (scale 1, no discount)
+  env = envs.BatchedStackEnv(bank, E, episode_length=steps, dtype=dtype, rewarder='all',
+                             orientation_freedom=freedom, seed=7)
   policy = envs.HeightPolicy()
-  obs, _, _ = env.reset(rock_orders=[order] * E, goal_lims=[lims] * E)
+  if drawn:
+    obs, _, _ = env.reset()
+    assert np.array_equal(env.goal_lims[0], lims)          # environment 0 is seeded 7 + 0
+    assert [int(x) for x in env._order[0]] == order[::-1]
+    # the other environments (seeds 8, 9) replay environment 0's episode from here on
+    obs, _, _ = env.reset(rock_orders=[order] * E, goal_lims=[lims] * E)
+  else:
+    obs, _, _ = env.reset(rock_orders=[order] * E, goal_lims=[lims] * E)
   assert np.array_equal(env.goals[0].cpu().numpy(), g[name + '/goal'])
   for k in range(steps):
     key = '{}/s{}'.format(name, k)
@@ -197,9 +208,15 @@ def test_batched_env_replays_reference_episode(mods, observe_golden, name, dtype
     assert np.array_equal(env._rest[0, k], g[key + '/pose_position'])
     if freedom:
       assert np.allclose(env._quats[0, k], g[key + '/pose_orientation'], atol=1e-15)
-    np.testing.assert_allclose(reward.cpu().numpy(), g[key + '/rewards'][0], rtol=1e-6,
-                               atol=1e-9)
+    want = g[key + '/rewards']                       # IoU, OR, DIoU, DOR (rewarder='all')
+    assert sorted(reward) == sorted(['IoU', 'OR', 'DIoU', 'DOR'])
+    for e in range(E):
+      np.testing.assert_allclose(float(reward['IoU'][e]), want[0], rtol=1e-6, atol=1e-9)
+      np.testing.assert_allclose(float(reward['OR'][e]), want[1], rtol=1e-6, atol=1e-9)
+      assert float(reward['DIoU'][e]) == np.float32(want[2])
+      assert float(reward['DOR'][e]) == np.float32(want[3])
     assert bool(terminal[0]) == (k == steps - 1)
+  env.check_actions()
   assert np.array_equal(obs[0][0].cpu().numpy(), g['{}/s{}/obs0'.format(name, steps)])
 
 
@@ -339,3 +356,229 @@ def test_rasterised_maps_take_the_fixed_point_sweep_unchanged():
   assert torch.equal(plain['values'], hinted['values'])
   assert torch.equal(plain['actions'], hinted['actions'])
   assert torch.equal(plain['best'], hinted['best'])
+
+
+# --------------------------------------------------------------------------- #
+# round 2: device-side step, both rasterisers, CUDA graph
+# --------------------------------------------------------------------------- #
+def _synthetic_env(mods, E, dtype='float32', freedom=0, steps=6, seed=3, **kw):
+  meshes, envs = mods['meshes'], mods['envs']
+  bank = meshes.MeshBank()
+  v, t = meshes.synthetic_rocks(5, 16, 1, max_dimension=0.12)
+  for k in range(16):
+    bank.add(v[k], t, com=(0.002 * k, -0.001 * k, 0.0015 * k))
+  return envs.BatchedStackEnv(bank, E, episode_length=steps, observable_size_ratio=4,
+                              resolution_factor=4, dtype=dtype, seed=seed,
+                              orientation_freedom=freedom, **kw)
+
+
+@pytest.mark.parametrize('mode', ['rock2k', 'walls', 'big_mesh', 'many_instances'])
+def test_round2_rasteriser_equals_round1_and_oracle(mods, monkeypatch, mode):
+  """raster.cu (shared-memory set-up records, head-flag owner search) against the
+  round-1 kernel (raster_v1.cuh, SRL_RASTER_MODE=1) and the oracle's C z-buffer:
+  same bits, for 2000-triangle rocks (BASELINE config 3), multi-instance wall
+  images, a mesh larger than the vertex cache and more instances than a chunk."""
+  camera, capi, meshes, obs_mod = (mods[k] for k in ('camera', 'capi', 'meshes', 'observer'))
+  dev = torch.device('cuda')
+  if mode == 'rock2k':
+    geo = camera.ObserverGeometry(128, 32, 0.005, 0.375)
+    verts, tris = meshes.synthetic_rocks(4, 6, max_dimension=0.16, frequency=10)
+    spawn = ((0., 0., 0.375 + 0.16), (0., 0., 0., 1.))
+    scenes = [[(verts[k], tris, np.identity(3), np.array(spawn[0]))] for k in range(6)]
+    view, proj, rows, cols = geo.object_view(spawn, 0), geo.object_projection, 32, 32
+    rmode, zr, hint = capi.RASTER_ROCK, geo.object_z, 1002
+  elif mode == 'big_mesh':
+    geo = camera.ObserverGeometry(128, 32, 0.005, 0.375)
+    verts, tris = meshes.synthetic_rocks(9, 2, max_dimension=0.16, frequency=16)   # 2562 verts
+    assert verts.shape[1] > 2048
+    spawn = ((0., 0., 0.375 + 0.16), (0., 0., 0., 1.))
+    scenes = [[(verts[k], tris, np.identity(3), np.array(spawn[0]))] for k in range(2)]
+    view, proj, rows, cols = geo.object_view(spawn, 0), geo.object_projection, 32, 32
+    rmode, zr, hint = capi.RASTER_ROCK, geo.object_z, 0
+  else:
+    geo = camera.ObserverGeometry(64, 16, 0.125 / 16, 0.375)
+    n = 5 if mode == 'walls' else 40
+    scenes = [_random_scene(meshes, 30 + s, n, 1 if n > 8 else 2) for s in range(3)]
+    view, proj, rows, cols = geo.overhead_view, geo.overhead_projection, 64, 64
+    rmode, zr, hint = capi.RASTER_WALL, 0.375, 300
+  flat = [b for sc in scenes for b in sc]
+  v, t, inst = obs_mod._instances(flat)
+  jobs, at = [], 0
+  for sc in scenes:
+    jobs.append(obs_mod._job(view, proj, at, len(sc), zr))
+    at += len(sc)
+  jobs = np.concatenate(jobs)
+  vd, td = torch.from_numpy(v).to(dev), torch.from_numpy(t).to(dev)
+  got = {}
+  for tag, env_mode in (('r2', '0'), ('r1', '1')):
+    monkeypatch.setenv('SRL_RASTER_MODE', env_mode)
+    got[tag] = capi.raster(vd, td, inst, jobs, rows, cols, rmode, max_cached_verts=hint).cpu().numpy()
+    got[tag + 'd'] = capi.raster(vd, td, inst, jobs, rows, cols, capi.RASTER_DEPTH,
+                                 max_cached_verts=hint).cpu().numpy()
+  assert np.array_equal(got['r2d'], got['r1d'])
+  assert np.array_equal(got['r2'], got['r1'])
+  for k, sc in enumerate(scenes):
+    want = R.render_depth(view, proj, rows, cols, sc)
+    assert np.array_equal(got['r2d'][k], want)
+    assert (want < 1).sum() > 20
+  # the device-side instance-count override draws a prefix of each job's instances
+  if mode == 'walls':
+    monkeypatch.setenv('SRL_RASTER_MODE', '0')
+    counts = torch.tensor([2, 0, 5], dtype=torch.int32, device=dev)
+    part = capi.raster(vd, td, inst, jobs, rows, cols, capi.RASTER_DEPTH, inst_counts=counts,
+                       max_cached_verts=hint).cpu().numpy()
+    for k, c in enumerate([2, 0, 5]):
+      assert np.array_equal(part[k], R.render_depth(view, proj, rows, cols, scenes[k][:c]))
+
+
+def test_place_poses_kernel_and_invalid_actions(mods):
+  """srl_place_poses_f32 = Observer.pose (observer.py:392-421) per environment, on
+  strided action columns; out-of-range actions give NaN poses and a status flag
+  instead of reading out of bounds (env.py:237 asserts)."""
+  capi = mods['capi']
+  dev = torch.device('cuda')
+  E, R_, H, W, h = 9, 4, 40, 32, 8
+  walls, rocks, _ = synth.placement_batch(8, E, R_, H, W, h)
+  rocks = np.where(rocks < 2e-4, rocks * 0.3, rocks).astype('float32')   # cells under 1e-4
+  rng = np.random.default_rng(1)
+  Ph, Pw = H - h + 1, W - h + 1
+  best = np.stack([rng.integers(0, R_, E), rng.integers(0, Ph * Pw, E)], 1).astype('int64')
+  best[2] = (R_, 5)            # view out of range
+  best[4] = (0, Ph * Pw)       # position out of range
+  best[6] = (-1, 3)
+  bd = torch.from_numpy(best).to(dev)
+  orient = np.random.default_rng(2).normal(size=(R_, 4))
+  geom = (0.01, 0.0125, 0.08, 0.1, 0.1)
+  poses, status = capi.place_poses(torch.from_numpy(walls).to(dev), torch.from_numpy(rocks).to(dev),
+                                   bd[:, 0], bd[:, 1], torch.from_numpy(orient).to(dev), geom)
+  poses, status = poses.cpu().numpy(), status.cpu().numpy()
+  assert list(status) == [0, 0, 1, 0, 1, 0, 1, 0, 0]
+  for e in range(E):
+    if status[e]:
+      assert np.isnan(poses[e]).all()
+      continue
+    r, a = best[e]
+    i, j = a // Pw, a % Pw
+    n = rocks[e, r]
+    z = (walls[e, i:i + h, j:j + h] + n)[n > np.float32(1e-4)].max()
+    x = i * geom[0] + geom[2] / 2
+    y = j * geom[1] + geom[3] / 2
+    z = z - np.float32(geom[4] / 2)
+    assert np.array_equal(poses[e], np.array([x, y, z, *orient[r]], dtype='float64'))
+
+
+@pytest.mark.parametrize('dtype,freedom', [('float32', 0), ('uint8', 0), ('float32', 2)])
+def test_step_graph_replays_the_eager_chain(mods, dtype, freedom):
+  """capture(policy): policy + step as ONE CUDA graph gives the same observations,
+  rewards, terminals and device state as the eager kernel chain."""
+  envs = mods['envs']
+  E, steps = 40, 5
+  a = _synthetic_env(mods, E, dtype, freedom, steps)
+  b = _synthetic_env(mods, E, dtype, freedom, steps)
+  pa, pb = envs.HeightPolicy(), envs.HeightPolicy()
+  a.reset()
+  b.reset()
+  oa, ra, ta = a.step(pa(a))                       # one eager step each (lazy attributes)
+  ob, rb, tb = b.step(pb(b))
+  b.capture(pb)
+  for k in range(1, steps):
+    oa, ra, ta = a.step(pa(a))
+    ob, rb, tb = b.step_policy()
+    assert torch.equal(oa[0], ob[0]) and torch.equal(oa[1], ob[1])
+    assert torch.equal(ra, rb) and torch.equal(ta, tb)
+    assert bool(ta.all()) == (k == steps - 1)
+  assert torch.equal(a.obs.state.hist_rest, b.obs.state.hist_rest)
+  assert torch.equal(a.obs.state.counts, b.obs.state.counts)
+  a.check_actions()
+  b.check_actions()
+  with pytest.raises(RuntimeError):
+    b.step_policy()
+  # a new episode replays through the same graph
+  a.reset()
+  b.reset()
+  oa, ra, ta = a.step(pa(a))
+  ob, rb, tb = b.step_policy()
+  assert torch.equal(oa[0], ob[0]) and torch.equal(ra, rb)
+  # graph without a policy: the action is copied into the captured buffers
+  c = _synthetic_env(mods, E, dtype, freedom, steps)
+  d = _synthetic_env(mods, E, dtype, freedom, steps)
+  c.reset()
+  d.reset()
+  act = pa(c)
+  oc, rc, _ = c.step(act)
+  od, rd, _ = d.step(act)
+  d.capture()
+  act = pa(c)
+  oc, rc, _ = c.step(act)
+  od, rd, _ = d.step(act)
+  assert torch.equal(oc[0], od[0]) and torch.equal(oc[1], od[1]) and torch.equal(rc, rd)
+
+
+def test_uint8_policy_scores_the_packed_observation(mods):
+  """The planar uint8 cast HeightPolicy scores equals the channels of the packed
+  uint8 observation (env.py:171-178), and its level is the quantised goal height."""
+  env = _synthetic_env(mods, 12, 'uint8', 1)
+  env.reset()
+  env.step(mods['envs'].HeightPolicy()(env))
+  w8, g8, r8 = env.planes_u8()
+  wall_goal, rock = env.observation
+  assert torch.equal(w8, wall_goal[:, 0, ..., 0]) and torch.equal(g8, wall_goal[:, 0, ..., 1])
+  assert torch.equal(r8, rock[..., 0])
+  assert torch.equal(env._level8_d, g8.amax(dim=(1, 2)))
+
+
+def test_discounted_rewards_and_settle_hook_moving_every_rock(mods):
+  """DOR / DIoU (rewarder.py:261-295) with position and orientation discounts when
+  the settle hook moves the new rock AND, through the all-poses return, the rocks
+  placed earlier; checked against a plain Python evaluation of the reference's loop."""
+  envs = mods['envs']
+  E, steps = 5, 4
+  rng = np.random.default_rng(0)
+  log = {'rest': [[] for _ in range(E)], 'placed': [[] for _ in range(E)]}
+
+  def settle(mesh_ids, positions, quats):
+    d = rng.normal(scale=0.004, size=positions.shape)
+    q = quats + rng.normal(scale=0.02, size=quats.shape)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    new = np.concatenate([positions + d, q], axis=1)
+    for e in range(E):
+      log['placed'][e].append(np.concatenate([positions[e], quats[e]]))
+      # earlier rocks drift a little too
+      log['rest'][e] = [p + np.r_[rng.normal(scale=0.001, size=3), np.zeros(4)]
+                        for p in log['rest'][e]] + [new[e]]
+    allp = np.stack([np.stack(log['rest'][e]) for e in range(E)])
+    return new[:, :3], new[:, 3:], allp
+
+  for metric in ('dor', 'diou'):
+    for e in range(E):
+      log['rest'][e], log['placed'][e] = [], []
+    env = _synthetic_env(mods, E, steps=steps, rewarder=metric, reward_params=(2, 1),
+                         reward_scale=None, settle=settle, freedom=1)
+    policy = envs.HeightPolicy()
+    env.reset()
+    geo = env.obs.geo
+    pmax = max(geo.object_h * geo.pixel_h, geo.object_w * geo.pixel_w)
+    memory = np.zeros(E)
+    for k in range(steps):
+      _, r, _ = env.step(policy(env))
+      r = r.cpu().numpy()
+      hist = env.obs.state.hist_rest.cpu().numpy()
+      for e in range(E):
+        assert np.array_equal(hist[e, :k + 1], np.stack(log['rest'][e]))
+        (u0, v0), (u1, v1) = env.goal_lims[e]
+        acc, n_out = 0., 0
+        for rest, placed in zip(log['rest'][e], log['placed'][e]):
+          u, v = float(rest[0]) // geo.pixel_h, float(rest[1]) // geo.pixel_w
+          if u0 <= u < u1 and v0 <= v < v1:
+            perr = np.linalg.norm(np.subtract(placed[:3], rest[:3]))
+            oerr = 2 * np.arccos(min(float(np.dot(placed[3:], rest[3:])), 1.))
+            acc += max(0., 1 - (perr / pmax) ** 2) * max(0., 1 - (oerr / np.pi) ** 1)
+          else:
+            n_out += 1
+        value = acc / steps if metric == 'dor' else acc / (steps + n_out)
+        np.testing.assert_allclose(r[e], (value - memory[e]) * steps, rtol=1e-6, atol=1e-7)
+        memory[e] = value
+    # the wall image shows the drifted rocks: re-rasterising the history gives it back
+    walls = env.obs.walls.clone()
+    env.obs.observe_walls()
+    assert torch.equal(walls, env.obs.walls)
