@@ -290,8 +290,9 @@ SRL_API int srl_pack_obs(const float* walls, const float* goals, const float* ro
  * of the `best` [E,2] table the selection kernels write); orientations [R,4] float64
  * (Observer._object_orientations).
  * The reference asserts action_space.contains(action) (env.py:237): an action out
- * of range reads nothing, yields a NaN pose and status[e] = 1 (status [E] i32,
- * may be NULL; 0 = valid). */
+ * of range reads nothing, yields a NaN pose and sets status[e] = 1 (status [E] i32,
+ * may be NULL; the kernel never clears it, so one read after many steps tells
+ * whether any of them was invalid). */
 SRL_API int srl_place_poses_f32(const float* walls, const float* rocks, const int64_t* views,
                                 const int64_t* flat, const double* orientations,
                                 double* poses, int32_t* status, int E, int R, int H, int W,

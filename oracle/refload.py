@@ -27,7 +27,18 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get('STACKRL_REFERENCE', '/root/reference')
+def _root():
+  """The reference tree: $STACKRL_REFERENCE, /root/reference (build container), or the
+  byte-for-byte staging of the hot-path files under oracle/_ref (oracle/make_ref.py;
+  travels with the repo snapshot to the GPU box, never committed)."""
+  if os.environ.get('STACKRL_REFERENCE'):
+    return os.environ['STACKRL_REFERENCE']
+  if os.path.isfile('/root/reference/stackrl/baselines.py'):
+    return '/root/reference'
+  return os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+
+
+REF_ROOT = _root()
 
 
 def available():

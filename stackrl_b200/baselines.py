@@ -265,56 +265,80 @@ class PlacementScorer(object):
 class HostPipeline(object):
   """``PlacementScorer`` for batches that live in HOST memory.
 
-  The batch is cut into chunks of environments; chunk k+1's host->device copies
-  (from pinned staging buffers, on a copy stream) overlap chunk k's kernels, and
+  The batch is cut into chunks of environments; chunk k+1's host->device copy
+  (from a pinned staging slab, on a copy stream) overlaps chunk k's kernels, and
   only the actions / batch-wise picks travel back.  This is the end-to-end call
-  bench.py times (``e2e``): numpy in, numpy out."""
+  bench.py times (``e2e``): numpy in, numpy out.
+
+  ``goal_rects=True``: the goal of an environment is handed over as what it is in
+  the reference -- a rectangle ``Rewarder._goal_lims`` at height ``goal_z``
+  (rewarder.py:252-258) -- i.e. ``goals`` is an int32 [E,4] array (u0, v0, u1, v1)
+  plus ``levels`` [E]; the [E,H,W] goal planes the kernels read are filled on the
+  device (srl_fill_goals_f32) instead of crossing PCIe (a quarter of the bytes of a
+  float32 step)."""
 
   def __init__(self, scorer, envs, rotations, H, W, h, chunks=4, device=None,
-               dtype=torch.float32):
+               dtype=torch.float32, goal_rects=False):
     """``dtype``: observation dtype, float32 or uint8 (the dtype of the registered
     Stack-v0/1/2 environments, env.py:171-178: a quarter of the bytes per step)."""
     if dtype not in (torch.float32, torch.uint8):
       raise TypeError('observations must be float32 or uint8, got {}'.format(dtype))
+    if goal_rects and dtype != torch.float32:
+      raise TypeError('goal rectangles are filled as float32 planes')
     self.scorer = scorer
     self.dev = device if device is not None else _device()
     self.E, self.R = int(envs), int(rotations)
+    self.rects = bool(goal_rects)
     self.bounds = [(k * self.E // chunks, (k + 1) * self.E // chunks) for k in range(chunks)]
     self.bounds = [b for b in self.bounds if b[1] > b[0]]
-    # One pinned slab and one device slab per chunk, [walls | goals | rocks] of the
-    # chunk's environments back to back (256-byte aligned parts): ONE host->device
-    # copy per chunk instead of three.
-    es = torch.empty((), dtype=dtype).element_size()
-    shapes = lambda n: (('walls', (n, H, W)), ('goals', (n, H, W)), ('rocks', (n, self.R, h, h)))
+    # One pinned slab and one device slab per chunk, the chunk's arrays back to back
+    # (256-byte aligned parts): ONE host->device copy per chunk.
+    def parts(n):
+      out = [('walls', (n, H, W), dtype), ('rocks', (n, self.R, h, h), dtype)]
+      if self.rects:
+        out += [('rects', (n, 4), torch.int32), ('levels', (n,), torch.float32)]
+      else:
+        out += [('goals', (n, H, W), dtype)]
+      return out
     self.pin_slabs, self.dev_slabs, self.pin, self.dev_in = [], [], [], []
+    self.goal_planes = []
     self.h2d_bytes = 0
     for lo, hi in self.bounds:
       offsets, total = [], 0
-      for name, shape in shapes(hi - lo):
-        nbytes = es * int(np.prod(shape))
-        offsets.append((name, shape, total, nbytes))
+      for name, shape, dt in parts(hi - lo):
+        nbytes = torch.empty((), dtype=dt).element_size() * int(np.prod(shape))
+        offsets.append((name, shape, dt, total, nbytes))
         total += (nbytes + 255) // 256 * 256
         self.h2d_bytes += nbytes
       pin = torch.empty((total,), dtype=torch.uint8).pin_memory()
       dev = torch.empty((total,), dtype=torch.uint8, device=self.dev)
-      view = lambda slab: {name: slab[off:off + nbytes].view(dtype).view(shape)
-                           for name, shape, off, nbytes in offsets}
+      view = lambda slab: {name: slab[off:off + nbytes].view(dt).view(shape)
+                           for name, shape, dt, off, nbytes in offsets}
       self.pin_slabs.append(pin)
       self.dev_slabs.append(dev)
       self.pin.append(view(pin))
       self.dev_in.append(view(dev))
+      if self.rects:
+        self.goal_planes.append(torch.empty((hi - lo, H, W), dtype=torch.float32,
+                                            device=self.dev))
     self.actions = torch.empty((self.E, self.R), dtype=torch.int64).pin_memory()
     self.best = torch.empty((self.E, 2), dtype=torch.int64).pin_memory()
     self.copy_stream = torch.cuda.Stream(device=self.dev)
     self.graph = None
     self.d2h_bytes = (self.actions.numel() + self.best.numel()) * 8
 
-  def stage(self, walls, goals, rocks):
-    """Copy caller arrays into the pinned staging slabs (host memcpy)."""
+  def stage(self, walls, goals, rocks, levels=None):
+    """Copy caller arrays into the pinned staging slabs (host memcpy; bench.py's
+    e2e timing starts after this, with the inputs in pinned host memory).
+    With ``goal_rects`` ``goals`` is the [E,4] limits array and ``levels`` [E]."""
     for (lo, hi), pin in zip(self.bounds, self.pin):
       pin['walls'].numpy()[...] = walls[lo:hi]
-      pin['goals'].numpy()[...] = goals[lo:hi]
       pin['rocks'].numpy()[...] = rocks[lo:hi]
+      if self.rects:
+        pin['rects'].numpy()[...] = goals[lo:hi]
+        pin['levels'].numpy()[...] = levels[lo:hi]
+      else:
+        pin['goals'].numpy()[...] = goals[lo:hi]
 
   def _enqueue(self, main):
     """One step's copies and kernels on ``main`` (+ the copy stream, forked from
@@ -327,9 +351,13 @@ class HostPipeline(object):
         ev = torch.cuda.Event()
         ev.record(self.copy_stream)
         ready.append(ev)
-    for (lo, hi), ev, dev_in in zip(self.bounds, ready, self.dev_in):
+    for k, ((lo, hi), ev, dev_in) in enumerate(zip(self.bounds, ready, self.dev_in)):
       main.wait_event(ev)
-      out = self.scorer(dev_in['walls'], dev_in['goals'], dev_in['rocks'])
+      if self.rects:
+        goals = capi.fill_goals(dev_in['rects'], dev_in['levels'], self.goal_planes[k])
+        out = self.scorer(dev_in['walls'], goals, dev_in['rocks'], level=dev_in['levels'])
+      else:
+        out = self.scorer(dev_in['walls'], dev_in['goals'], dev_in['rocks'])
       self.actions[lo:hi].copy_(out['actions'], non_blocking=True)
       self.best[lo:hi].copy_(out['best'], non_blocking=True)
 
@@ -361,8 +389,8 @@ class HostPipeline(object):
     main.synchronize()
     return self.actions.numpy(), self.best.numpy()
 
-  def __call__(self, walls, goals, rocks):
-    self.stage(walls, goals, rocks)
+  def __call__(self, walls, goals, rocks, levels=None):
+    self.stage(walls, goals, rocks, levels)
     return self.run()
 
 

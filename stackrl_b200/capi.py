@@ -158,6 +158,10 @@ def maxplus_f32(walls, rocks, level=None, threshold=0., out=None, quantum_log2=N
   args = (_dev(walls, torch.float32, 'walls'), _dev(rocks, torch.float32, 'rocks'),
           _opt(level, torch.float32, 'level'))
   shape = (E, R, H - h + 1, W - h + 1)
+  if h > H or h > W:
+    # no candidate position: the library's own argument check reports it
+    with torch.cuda.device(walls.device):
+      _check(lib.srl_maxplus_f32(*args, _P(None), E, R, H, W, h, float(threshold), _stream()))
   if out is None:
     out = torch.empty(shape, dtype=torch.float32, device=walls.device)
   _out(out, torch.float32, shape, walls)
@@ -537,14 +541,15 @@ def place_poses(walls, rocks, views, flat, orientations, geometry, threshold=1e-
   """Observer.pose for a batch (observer.py:392-421).  ``views`` [E] int64 or None,
   ``flat`` [E] int64 device tensors; ``orientations`` [R,4] float64; ``geometry`` =
   (pixel_h, pixel_w, object_x, object_y, object_z).  -> (poses [E,7] float64,
-  status [E] int32: 1 where the action was out of range, env.py:237)."""
+  status [E] int32: set to 1 where the action was out of range, env.py:237; a
+  caller-provided ``status`` is never cleared, so it accumulates over steps)."""
   E, R, H, W, h = _batch_dims(walls, rocks)
   dev = walls.device
   _same_device(walls, rocks, views, flat, orientations, poses, status)
   if poses is None:
     poses = torch.empty((E, 7), dtype=torch.float64, device=dev)
   if status is None:
-    status = torch.empty((E,), dtype=torch.int32, device=dev)
+    status = torch.zeros((E,), dtype=torch.int32, device=dev)
   if flat.shape != (E,) or (views is not None and views.shape != (E,)):
     raise ValueError('actions must be [E] tensors')
   if orientations.shape != (R, 4):

@@ -27,3 +27,36 @@ def correlation(in0, in1, parallel_iterations=None):
     raise TypeError('correlation is float32 like the reference layer, got {} and {}'.format(
       in0.dtype, in1.dtype))
   return capi.siam_correlation_f32(in0.contiguous(), in1.contiguous())
+
+
+def benchmark(torch_module, device, samples=148, channels=16, side=128, rock=32, reps=10):
+  """Throughput of the correlation layer at the config.gin geometry (config.gin:55):
+  ``samples`` x (side^2 x channels (*) rock^2 x channels).  Returned as the dict
+  bench.py puts under ``extra.siam_correlation``."""
+  gen = torch_module.Generator(device=device).manual_seed(0)
+  x = torch_module.randn((samples, side, side, channels), device=device, generator=gen)
+  w = torch_module.randn((samples, rock, rock, channels), device=device, generator=gen)
+  out = torch_module.empty((samples, side - rock + 1, side - rock + 1, 1), device=device)
+  for _ in range(3):
+    capi.siam_correlation_f32(x, w, out=out)
+  a = torch_module.cuda.Event(enable_timing=True)
+  b = torch_module.cuda.Event(enable_timing=True)
+  torch_module.cuda.synchronize()
+  a.record()
+  for _ in range(reps):
+    capi.siam_correlation_f32(x, w, out=out)
+  b.record()
+  torch_module.cuda.synchronize()
+  ms = a.elapsed_time(b) / reps
+  flops = 2.0 * samples * (side - rock + 1) ** 2 * rock * rock * channels
+  fma_peak = 2 * max(capi.microbench_fma(v, 400) for v in (0, 1, 2)) / 1e12
+  return {
+    'workload': '{} samples, {}x{}x{} wall features * {}x{}x{} rock features, float32 '
+                '(stackrl.nets.correlation, config.gin geometry)'.format(
+                  samples, side, side, channels, rock, rock, channels),
+    'ms': ms, 'samples_per_s': samples / (ms * 1e-3),
+    'roofline': {'bound': 'fp32-fma', 'achieved': flops / (ms * 1e-3) / 1e12,
+                 'peak': fma_peak, 'unit': 'TFLOP/s',
+                 'frac': flops / (ms * 1e-3) / 1e12 / fma_peak,
+                 'peak_source': 'srl_microbench_fma, best of FFMA / FFMA2 measured in this run '
+                                '(nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4)'}}

@@ -406,6 +406,7 @@ class BatchedObserver(object):
     self._pose_geometry = (g.pixel_h, g.pixel_w, g.object_x, g.object_y, g.object_z)
     self.pose_buf = torch.zeros((E, 7), dtype=torch.float64, device=self.dev)
     self.status = torch.zeros((E,), dtype=torch.int32, device=self.dev)
+    self._status_zero = torch.zeros((E,), dtype=torch.int32, device=self.dev)
     self.walls = torch.zeros((E, g.overhead_h, g.overhead_w), dtype=torch.float32,
                              device=self.dev)
     self.rocks = torch.zeros((E, R, g.object_h, g.object_w), dtype=torch.float32,
@@ -450,6 +451,8 @@ class BatchedObserver(object):
     ids = None if env_ids is None else torch.from_numpy(
       np.ascontiguousarray(env_ids, dtype='int32')).to(self.dev, non_blocking=True)
     capi.env_reset(st, ids)
+    if env_ids is None:
+      self.status.copy_(self._status_zero, non_blocking=True)     # device memcpy
 
   def reset(self, env_ids=None):
     """Forget the placed rocks of the given environments (all by default)."""

@@ -72,11 +72,12 @@ def rocks(seed, count, rotations, side, zero_fraction=0.3):
   return out
 
 
-def goals(seed, count, H, W, ratio=0.25, level=GOAL_LEVEL):
-  """[count, H, W] float32 goal maps: one rectangle of ~ratio*H*W pixels at
-  ``level`` per map, kept 1/8 away from the borders like rewarder.py:239-249."""
+def goal_rects(seed, count, H, W, ratio=0.25):
+  """[count, 4] int32 goal limits (u0, v0, u1, v1) = Rewarder._goal_lims flattened:
+  one rectangle of ~ratio*H*W pixels per map, kept 1/8 away from the borders like
+  rewarder.py:239-249."""
   rng = np.random.default_rng(seed)
-  g = np.zeros((count, H, W), dtype='float32')
+  rects = np.zeros((count, 4), dtype='int32')
   area = int(ratio * H * W)
   for e in range(count):
     gh = int(rng.integers(max(2, area // W), min(H, max(3, area // 2)) + 1))
@@ -84,7 +85,15 @@ def goals(seed, count, H, W, ratio=0.25, level=GOAL_LEVEL):
     gw = min(max(2, area // gh), W)
     u = int(rng.integers((H - gh) // 8, 7 * (H - gh) // 8 + 1))
     v = int(rng.integers((W - gw) // 8, 7 * (W - gw) // 8 + 1))
-    g[e, u:u + gh, v:v + gw] = level
+    rects[e] = (u, v, u + gh, v + gw)
+  return rects
+
+
+def goals(seed, count, H, W, ratio=0.25, level=GOAL_LEVEL):
+  """[count, H, W] float32 goal maps: the rectangles of ``goal_rects`` at ``level``."""
+  g = np.zeros((count, H, W), dtype='float32')
+  for e, (u0, v0, u1, v1) in enumerate(goal_rects(seed, count, H, W, ratio)):
+    g[e, u0:u1, v0:v1] = level
   return g
 
 

@@ -16,7 +16,7 @@ for k in range(64):
   bank.add(v[k], t)
 env = envs.BatchedStackEnv(bank, E, episode_length=12, observable_size_ratio=4,
                            resolution_factor=4, dtype='float32', rewarder='iou', seed=5,
-                           device=dev)
+                           device=dev, vector_rng=True)
 policy = envs.HeightPolicy()
 env.reset()
 for _ in range(6):
@@ -37,8 +37,36 @@ def timeit(fn, reps=20):
   return a.elapsed_time(b) / reps
 
 
+print('mode %s, E=%d' % (os.environ.get('SRL_RASTER_MODE', '0'), E))
 print('walls  %.3f ms' % timeit(env.obs.observe_walls))
-print('rocks  %.3f ms' % timeit(lambda: env.obs.observe_rocks(env._current)))
-print('reward %.3f ms' % timeit(env.reward_terms))
+print('rocks  %.3f ms' % timeit(env.obs.observe_rocks))
+print('reward %.3f ms' % timeit(env._reward))
 print('pack   %.3f ms' % timeit(lambda: env.observation))
 print('policy %.3f ms' % timeit(lambda: policy(env)))
+view = torch.zeros(E, dtype=torch.int64, device=dev)
+print('poses+advance (state frozen: done envs skip) %.3f ms' % timeit(
+  lambda: (env.obs.poses_device(None, view), env.obs.advance())))
+
+
+def episode(step):
+  """Wall-clock of whole episodes: reset + 12 (policy + step), host bookkeeping included."""
+  import time
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  n = 0
+  for _ in range(3):
+    env.reset()
+    for _ in range(12):
+      step()
+      n += 1
+  torch.cuda.synchronize()
+  return (time.perf_counter() - t0) / n * 1e3
+
+
+ms = episode(lambda: env.step(policy(env)))
+print('eager step (policy + step, resets amortised) %.3f ms  %.3e env steps/s' % (ms, E / ms * 1e3))
+env.reset()
+env.step(policy(env))
+env.capture(policy)
+ms = episode(env.step_policy)
+print('graph step (policy + step, resets amortised) %.3f ms  %.3e env steps/s' % (ms, E / ms * 1e3))

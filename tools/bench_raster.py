@@ -29,7 +29,7 @@ def main():
   out = obs.rocks.view(n, g.object_h, g.object_w)
   def run():
     capi.raster(obs._verts, obs._tris, obs._rock_inst, obs._rock_jobs, g.object_h, g.object_w,
-                capi.RASTER_ROCK, out=out)
+                capi.RASTER_ROCK, out=out, max_cached_verts=verts.shape[1])
   for _ in range(3):
     run()
   torch.cuda.synchronize()
@@ -41,8 +41,8 @@ def main():
   torch.cuda.synchronize()
   ms = a.elapsed_time(b) / reps
   nb = 12 * verts.shape[1] + 12 * len(tris) + 4 * 32 * 32
-  print('%d rocks x %d tris: %.3f ms  %.3e rocks/s  %.3e tris/s  %.1f GB/s algorithmic' % (
-    n, len(tris), ms, n / ms * 1e3, n * len(tris) / ms * 1e3, n * nb / ms / 1e6))
+  print('mode %s: %d rocks x %d tris: %.3f ms  %.3e rocks/s  %.3e tris/s  %.1f GB/s algorithmic' % (
+    os.environ.get('SRL_RASTER_MODE', '0'), n, len(tris), ms, n / ms * 1e3, n * len(tris) / ms * 1e3, n * nb / ms / 1e6))
 
 
 if __name__ == '__main__':
