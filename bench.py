@@ -613,14 +613,12 @@ def run_c4(args, su):
     obs.poses_device(None, action)
     obs.advance()
     mark('pose + instance append')
-    obs.observe_walls()
-    mark('wall raster')
+    obs.observe_walls(True)
+    mark('wall raster (the appended rock onto the kept depth image)')
     obs.observe_rocks()
     mark('rock raster')
-    env._reward()
-    mark('reward')
-    env.observation
-    mark('pack')
+    env._reward_and_pack()
+    mark('reward + pack')
     env._advance_host()
     state['left'] -= 1
   torch.cuda.synchronize()
@@ -689,10 +687,10 @@ def run_c4(args, su):
       'value': total_E / (float(stats[:, 2].max()) * 1e-3), 'unit': w['unit'],
       'd2h_bytes_per_step': obs_bytes + 13 * E,
       'api': 'same, plus the packed float32 observation copied to pinned host memory'},
-    'gpu_launches': 9 * args.steps,
+    'gpu_launches': 7 * args.steps,
     'kernels_per_step': ['maxplus_stream_kernel', 'mask_select_packed_kernel',
                          'place_poses_kernel', 'env_advance_kernel', 'raster_kernel (walls)',
-                         'raster_kernel (rocks)', 'rewards_kernel', 'pack_obs_kernel'],
+                         'raster_kernel (rocks)', 'pack_rewards_kernel'],
     'roofline': {
       'bound': 'hbm', 'kernel': 'env observation chain (pose, append, wall raster, rock '
                                 'raster, reward, pack) of one mid-episode step',
@@ -702,7 +700,7 @@ def run_c4(args, su):
       'bytes_per_obs': alg, 'peak_source': peak_src,
       'breakdown_ms': breakdown, 'mean_placed_rocks': n_inst},
     'notes': {'envs_per_gpu': E, 'resets_in_timed_region': args.steps // L,
-              'rng': 'vector_rng=True (one vectorised host stream per rank)',
+              'rng': 'vector_rng=True (episode draws on the device, srl_env_draw)',
               'rocks': '{} synthetic rocks of {} triangles / {} vertices'.format(w['bank'], F, V)},
   }
   return line

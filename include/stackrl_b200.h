@@ -260,6 +260,23 @@ SRL_API int srl_raster_ex(const float* verts, const int32_t* tris,
                           int cols, int mode, double far_plane, int max_cached_verts,
                           srl_stream_t stream);
 
+/* Incremental form for scenes that only GROW between observations (a placed rock
+ * stays where it is: the static backend, or a settle step that moved nothing else).
+ * depth_state [njobs, rows, cols] f32 is the GL depth image kept between calls.
+ * only_last == 0: draw every instance (like srl_raster_ex) and leave the depth image
+ * in depth_state; only_last != 0: start from depth_state and draw ONLY the last
+ * instance of each job.  The depth image is a minimum over triangles, so the result
+ * is bit-identical to re-drawing all instances (the reference re-renders the whole
+ * scene every step, observer.py:252-257, because pybullet's renderer has no such
+ * mode); the wall image of a 30-rock episode costs one rock per step instead of 15 on
+ * average. */
+SRL_API int srl_raster_incremental(const float* verts, const int32_t* tris,
+                                   const srl_raster_instance* insts,
+                                   const srl_raster_job* jobs, const int32_t* inst_counts,
+                                   float* depth_state, int only_last, float* out, int njobs,
+                                   int rows, int cols, int mode, double far_plane,
+                                   int max_cached_verts, srl_stream_t stream);
+
 /* ---- a11: Rewarder._intersection/_union (rewarder.py:297-307) ---------------
  * inter[e] = sum(min(walls[e][goal != 0], goal_z[e])), uni[e] = sum(max(walls[e],
  * goals[e])), vol[e] = sum(goals[e]).  Accumulated in float64 and rounded once;
@@ -347,6 +364,21 @@ SRL_API int srl_env_advance(const srl_env_state* host_state, const double* rest,
 SRL_API int srl_env_set_poses(const srl_env_state* host_state, const double* poses,
                               int n_given, srl_stream_t stream);
 
+/* Episode draws on the device, for batches too large for 2E host RandomState streams:
+ * order[e, 0..length) = the episode's rock list (env.py:268-272: without replacement
+ * when n_meshes >= length) and rects[e] = a goal rectangle of Rewarder._reset_goal
+ * (rewarder.py:211-250; goal_mode 0: goal_size_ratio None, 1: scalar -> goal_size =
+ * int(ratio*H*W), 2: tuple -> goal_size_h/w = int(ratio_k * H|W)), from a counter-based
+ * generator keyed by (seed, episode, e).  Same distributions as the reference, NOT its
+ * numpy draw sequence (the per-environment RandomState streams stay on the host:
+ * stackrl_b200/episodes.py).  order: [E, length] i32 (normally host_state->order),
+ * rects [E,4] i32, both indexed by environment. */
+SRL_API int srl_env_draw(const srl_env_state* host_state, int32_t* order, int32_t* rects,
+                         const int32_t* env_ids, int n, int n_meshes, int H, int W,
+                         int object_h, int object_w, int goal_mode, int goal_size,
+                         int goal_size_h, int goal_size_w, uint64_t seed, uint64_t episode,
+                         srl_stream_t stream);
+
 /* ---- a13: the goal map of Rewarder._reset_goal (rewarder.py:252-258) ----------------
  * goals[e, u0:u1, v0:v1] = goal_z[e], 0 elsewhere, for e = env_ids[k] (NULL: e = k),
  * rects [n,4] i32 = (u0, v0, u1, v1) = Rewarder._goal_lims.  goal_z is indexed by e. */
@@ -372,6 +404,18 @@ SRL_API int srl_rewards_f32(const srl_env_state* host_state, const float* walls,
                             float* reward, double* value, int H, int W, int metric,
                             double scale, double pixel_h, double pixel_w, double pmax,
                             double pexp, double oexp, srl_stream_t stream);
+
+/* a14 + a11/a12 in one pass over the wall and goal maps: srl_pack_obs and
+ * srl_rewards_f32 of the same step (what StackEnv.step returns, env.py:255-264) --
+ * the observation is packed while the reward sums are taken, so the maps are read
+ * once.  Arguments as in those two; obs_scale is srl_pack_obs's `scale`. */
+SRL_API int srl_pack_rewards_f32(const srl_env_state* host_state, const float* walls,
+                                 const float* goals, const float* rocks, const float* goal_z,
+                                 const int32_t* rects, void* wall_goal, void* rock,
+                                 float* reward, double* value, int R, int H, int W, int h,
+                                 int dtype_code, float obs_scale, int repeat_wall, int metric,
+                                 double scale, double pixel_h, double pixel_w, double pmax,
+                                 double pexp, double oexp, srl_stream_t stream);
 
 /* StackEnv._return's uint8 cast (env.py:171-178) on the planar maps (the form the
  * scoring kernels take): q = trunc(x*255/scale) in float32. */

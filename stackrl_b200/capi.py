@@ -59,6 +59,8 @@ _SIGNATURES = {
   'srl_siam_correlation_f32': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
   'srl_raster': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_raster_ex': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _I, _P]),
+  'srl_raster_incremental': (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _c.c_double,
+                                   _I, _P]),
   'srl_reward_sums_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
   'srl_pack_obs': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_float, _I, _P]),
   'srl_place_poses_f32': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_double,
@@ -67,11 +69,14 @@ _SIGNATURES = {
   'srl_env_reset': (_I, [_P, _P, _I, _P]),
   'srl_env_advance': (_I, [_P, _P, _P, _P]),
   'srl_env_set_poses': (_I, [_P, _P, _I, _P]),
+  'srl_env_draw': (_I, [_P, _P, _P, _P] + [_I] * 10 + [_c.c_uint64, _c.c_uint64, _P]),
   'srl_fill_goals_f32': (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
   'srl_goal_level_f32': (_I, [_P, _P, _I, _I, _P]),
   'srl_goal_level_u8': (_I, [_P, _P, _I, _I, _P]),
   'srl_rewards_f32': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _c.c_double, _c.c_double,
                             _c.c_double, _c.c_double, _c.c_double, _c.c_double, _P]),
+  'srl_pack_rewards_f32': (_I, [_P] * 10 + [_I, _I, _I, _I, _I, _c.c_float, _I, _I] +
+                           [_c.c_double] * 6 + [_P]),
   'srl_quantise_planes_u8': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_float, _P]),
   'srl_microbench_addmax': (_I, [_I, _I, _c.POINTER(_c.c_double)]),
   'srl_microbench_fma': (_I, [_I, _I, _c.POINTER(_c.c_double)]),
@@ -334,12 +339,15 @@ RASTER_DEPTH, RASTER_WALL, RASTER_ROCK = 0, 1, 2
 
 
 def raster(verts, tris, instances, jobs, rows, cols, mode, far_plane=1000., out=None,
-           inst_counts=None, max_cached_verts=0):
+           inst_counts=None, max_cached_verts=0, depth_state=None, only_last=False):
   """verts [NV,3] f32 / tris [NT,3] i32 CUDA tensors (the mesh bank),
   instances / jobs numpy structured arrays (INSTANCE_DTYPE / JOB_DTYPE) or
   CUDA uint8 tensors holding them -> [njobs, rows, cols] float32.
   ``inst_counts`` [njobs] int32 (device) overrides the jobs' instance counts;
-  ``max_cached_verts`` sizes the shared-memory vertex cache (srl_raster_ex)."""
+  ``max_cached_verts`` sizes the shared-memory vertex cache (srl_raster_ex).
+  ``depth_state`` [njobs, rows, cols] float32: the GL depth image kept between calls
+  (srl_raster_incremental); with ``only_last`` only the last instance of every job
+  is drawn onto it -- same bits as re-drawing the whole scene."""
   dev = verts.device
   def as_bytes(a, dtype):
     if isinstance(a, torch.Tensor):
@@ -363,9 +371,16 @@ def raster(verts, tris, instances, jobs, rows, cols, mode, far_plane=1000., out=
           _dev(inst_t, torch.uint8, 'instances'), _dev(jobs_t, torch.uint8, 'jobs'),
           _dev(out, torch.float32, 'out'))
   with torch.cuda.device(dev):
-    _check(lib.srl_raster_ex(*args[:4], _opt(inst_counts, torch.int32, 'inst_counts'), args[4],
-                             int(njobs), int(rows), int(cols), int(mode), float(far_plane),
-                             int(max_cached_verts), _stream()))
+    if depth_state is not None:
+      _check(lib.srl_raster_incremental(
+        *args[:4], _opt(inst_counts, torch.int32, 'inst_counts'),
+        _out(depth_state, torch.float32, (njobs, rows, cols), verts, 'depth_state'),
+        int(bool(only_last)), args[4], int(njobs), int(rows), int(cols), int(mode),
+        float(far_plane), int(max_cached_verts), _stream()))
+    else:
+      _check(lib.srl_raster_ex(*args[:4], _opt(inst_counts, torch.int32, 'inst_counts'), args[4],
+                               int(njobs), int(rows), int(cols), int(mode), float(far_plane),
+                               int(max_cached_verts), _stream()))
   return out
 
 
@@ -602,6 +617,26 @@ def env_set_poses(state, poses):
                                                    state.done, 'poses'), n, _stream()))
 
 
+def env_draw(state, rects, n_meshes, shape, object_shape, goal_size_ratio, seed, episode,
+             env_ids=None):
+  """Device-side episode draws (srl_env_draw): fills ``state.order`` and ``rects``."""
+  H, W = shape
+  if not goal_size_ratio:
+    mode, size, sh, sw = 0, 0, 0, 0
+  elif isinstance(goal_size_ratio, (int, float)):
+    mode, size, sh, sw = 1, int(goal_size_ratio * H * W), 0, 0
+  else:
+    mode, size = 2, 0
+    sh, sw = int(goal_size_ratio[0] * H), int(goal_size_ratio[1] * W)
+  n = state.E if env_ids is None else env_ids.numel()
+  with torch.cuda.device(state.device):
+    _check(lib.srl_env_draw(state.ref(), _dev(state.order, torch.int32, 'order'),
+                            _out(rects, torch.int32, (state.E, 4), state.done, 'rects'),
+                            _opt(env_ids, torch.int32, 'env_ids'), int(n), int(n_meshes),
+                            int(H), int(W), int(object_shape[0]), int(object_shape[1]), mode,
+                            size, sh, sw, int(seed) & (2 ** 64 - 1), int(episode), _stream()))
+
+
 def fill_goals(rects, goal_z, goals, env_ids=None):
   """goals[e, u0:u1, v0:v1] = goal_z[e] (rewarder.py:252-258); rects [n,4] int32."""
   n = rects.shape[0]
@@ -652,6 +687,34 @@ def rewards(state, walls, goals, goal_z, rects, metric, scale, pixel, pmax, pexp
       H, W, m, float(scale), float(pixel[0]), float(pixel[1]), float(pmax),
       -1.0 if pexp is None else float(pexp), -1.0 if oexp is None else float(oexp), _stream()))
   return reward
+
+
+def pack_rewards(state, walls, goals, rocks, goal_z, rects, metric, scale, pixel, pmax, pexp,
+                 oexp, dtype='float32', obs_scale=1., repeat_wall=False, out=None):
+  """pack_obs + rewards of one step in one launch -> (wall_goal, rock, reward)."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  dev = walls.device
+  m = METRICS[metric]
+  tdt = {'float32': torch.float32, 'uint8': torch.uint8}[str(dtype)]
+  wg_shape = (E, R, H, W, 2) if repeat_wall else (E, H, W, 2)
+  if out is None:
+    wall_goal = torch.empty(wg_shape, dtype=tdt, device=dev)
+    rock = torch.empty((E, R, h, h, 1), dtype=tdt, device=dev)
+  else:
+    wall_goal, rock = out
+    _out(wall_goal, tdt, wg_shape, walls, 'wall_goal')
+    _out(rock, tdt, (E, R, h, h, 1), walls, 'rock')
+  reward = torch.empty((E, 4) if m == 4 else (E,), dtype=torch.float32, device=dev)
+  with torch.cuda.device(dev):
+    _check(lib.srl_pack_rewards_f32(
+      state.ref(), _dev(walls, torch.float32, 'walls'), _dev(goals, torch.float32, 'goals'),
+      _dev(rocks, torch.float32, 'rocks'), _dev(goal_z, torch.float32, 'goal_z'),
+      _dev(rects, torch.int32, 'rects'), _P(wall_goal.data_ptr()), _P(rock.data_ptr()),
+      _P(reward.data_ptr()), _P(None), R, H, W, h, 0 if tdt == torch.float32 else 1,
+      float(obs_scale), int(bool(repeat_wall)), m, float(scale), float(pixel[0]),
+      float(pixel[1]), float(pmax), -1.0 if pexp is None else float(pexp),
+      -1.0 if oexp is None else float(oexp), _stream()))
+  return wall_goal, rock, reward
 
 
 def quantise_planes(walls, goals, rocks, scale, out=None):

@@ -157,16 +157,27 @@ int srl_corrcoef_localized_u8(const uint8_t* walls, const uint8_t* rocks,
 int srl_raster(const float* verts, const int32_t* tris, const srl_raster_instance* insts,
                const srl_raster_job* jobs, float* out, int njobs, int rows, int cols,
                int mode, double far_plane, srl_stream_t stream) {
-  return srl::raster(verts, tris, insts, jobs, nullptr, out, njobs, rows, cols, mode,
-                     far_plane, 0, (cudaStream_t)stream);
+  return srl::raster(verts, tris, insts, jobs, nullptr, nullptr, 0, out, njobs, rows, cols,
+                     mode, far_plane, 0, (cudaStream_t)stream);
 }
 
 int srl_raster_ex(const float* verts, const int32_t* tris, const srl_raster_instance* insts,
                   const srl_raster_job* jobs, const int32_t* inst_counts, float* out,
                   int njobs, int rows, int cols, int mode, double far_plane,
                   int max_cached_verts, srl_stream_t stream) {
-  return srl::raster(verts, tris, insts, jobs, inst_counts, out, njobs, rows, cols, mode,
-                     far_plane, max_cached_verts, (cudaStream_t)stream);
+  return srl::raster(verts, tris, insts, jobs, inst_counts, nullptr, 0, out, njobs, rows, cols,
+                     mode, far_plane, max_cached_verts, (cudaStream_t)stream);
+}
+
+int srl_raster_incremental(const float* verts, const int32_t* tris,
+                           const srl_raster_instance* insts, const srl_raster_job* jobs,
+                           const int32_t* inst_counts, float* depth_state, int only_last,
+                           float* out, int njobs, int rows, int cols, int mode,
+                           double far_plane, int max_cached_verts, srl_stream_t stream) {
+  SRL_REQUIRE(depth_state != nullptr || njobs == 0, SRL_E_INVALID,
+              "raster_incremental: depth_state is null");
+  return srl::raster(verts, tris, insts, jobs, inst_counts, depth_state, only_last, out, njobs,
+                     rows, cols, mode, far_plane, max_cached_verts, (cudaStream_t)stream);
 }
 
 int srl_reward_sums_f32(const float* walls, const float* goals, const float* goal_z,
@@ -253,6 +264,15 @@ int srl_env_set_poses(const srl_env_state* host_state, const double* poses, int 
   return srl::env_set_poses(host_state, poses, n_given, (cudaStream_t)stream);
 }
 
+int srl_env_draw(const srl_env_state* host_state, int32_t* order, int32_t* rects,
+                 const int32_t* env_ids, int n, int n_meshes, int H, int W, int object_h,
+                 int object_w, int goal_mode, int goal_size, int goal_size_h, int goal_size_w,
+                 uint64_t seed, uint64_t episode, srl_stream_t stream) {
+  return srl::env_draw(host_state, order, rects, env_ids, n, n_meshes, H, W, object_h, object_w,
+                       goal_mode, goal_size, goal_size_h, goal_size_w, seed, episode,
+                       (cudaStream_t)stream);
+}
+
 int srl_fill_goals_f32(const int32_t* rects, const float* goal_z, const int32_t* env_ids,
                        float* goals, int n, int H, int W, srl_stream_t stream) {
   return srl::fill_goals_f32(rects, goal_z, env_ids, goals, n, H, W, (cudaStream_t)stream);
@@ -273,6 +293,19 @@ int srl_rewards_f32(const srl_env_state* host_state, const float* walls, const f
                     double pmax, double pexp, double oexp, srl_stream_t stream) {
   return srl::rewards_f32(host_state, walls, goals, goal_z, rects, reward, value, H, W, metric,
                           scale, pixel_h, pixel_w, pmax, pexp, oexp, (cudaStream_t)stream);
+}
+
+int srl_pack_rewards_f32(const srl_env_state* host_state, const float* walls,
+                         const float* goals, const float* rocks, const float* goal_z,
+                         const int32_t* rects, void* wall_goal, void* rock, float* reward,
+                         double* value, int R, int H, int W, int h, int dtype_code,
+                         float obs_scale, int repeat_wall, int metric, double scale,
+                         double pixel_h, double pixel_w, double pmax, double pexp, double oexp,
+                         srl_stream_t stream) {
+  return srl::pack_rewards_f32(host_state, walls, goals, rocks, goal_z, rects, wall_goal, rock,
+                               reward, value, R, H, W, h, dtype_code, obs_scale, repeat_wall,
+                               metric, scale, pixel_h, pixel_w, pmax, pexp, oexp,
+                               (cudaStream_t)stream);
 }
 
 int srl_quantise_planes_u8(const float* walls, const float* goals, const float* rocks,

@@ -65,9 +65,9 @@ int corrcoef_localized_u8(const uint8_t* walls, const uint8_t* rocks, const uint
                           cudaStream_t stream);
 
 int raster(const float* verts, const int32_t* tris, const srl_raster_instance* insts,
-           const srl_raster_job* jobs, const int32_t* inst_counts, float* out, int njobs,
-           int rows, int cols, int mode, double far_plane, int vert_cap_hint,
-           cudaStream_t stream);
+           const srl_raster_job* jobs, const int32_t* inst_counts, float* depth_state,
+           int only_last, float* out, int njobs, int rows, int cols, int mode,
+           double far_plane, int vert_cap_hint, cudaStream_t stream);
 
 int pack_obs(const float* walls, const float* goals, const float* rocks, void* wall_goal,
              void* rock, int E, int R, int H, int W, int h, int dtype_code, float scale,
@@ -96,6 +96,10 @@ int env_advance(const srl_env_state* st, const double* rest, const double* place
 int env_reset(const srl_env_state* st, const int32_t* env_ids, int n, cudaStream_t stream);
 int env_set_poses(const srl_env_state* st, const double* poses, int n_given,
                   cudaStream_t stream);
+int env_draw(const srl_env_state* st, int32_t* order, int32_t* rects, const int32_t* env_ids,
+             int n, int n_meshes, int H, int W, int object_h, int object_w, int goal_mode,
+             int goal_size, int goal_size_h, int goal_size_w, unsigned long long seed,
+             unsigned long long episode, cudaStream_t stream);
 int fill_goals_f32(const int32_t* rects, const float* goal_z, const int32_t* env_ids,
                    float* goals, int n, int H, int W, cudaStream_t stream);
 int goal_level_f32(const float* goals, float* level, int E, int HW, cudaStream_t stream);
@@ -104,6 +108,12 @@ int rewards_f32(const srl_env_state* st, const float* walls, const float* goals,
                 const float* goal_z, const int32_t* rects, float* reward, double* value,
                 int H, int W, int metric, double scale, double pixel_h, double pixel_w,
                 double pmax, double pexp, double oexp, cudaStream_t stream);
+int pack_rewards_f32(const srl_env_state* st, const float* walls, const float* goals,
+                     const float* rocks, const float* goal_z, const int32_t* rects,
+                     void* wall_goal, void* rock, float* reward, double* value, int R, int H,
+                     int W, int h, int dtype_code, float obs_scale, int repeat_wall, int metric,
+                     double scale, double pixel_h, double pixel_w, double pmax, double pexp,
+                     double oexp, cudaStream_t stream);
 int quantise_planes_u8(const float* walls, const float* goals, const float* rocks,
                        uint8_t* walls8, uint8_t* goals8, uint8_t* rocks8, int E, int R, int H,
                        int W, int h, float scale, cudaStream_t stream);

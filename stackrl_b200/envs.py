@@ -97,7 +97,7 @@ class BatchedStackEnv(object):
     E = self.E
     self.goals = torch.zeros((E, H, W), dtype=torch.float32, device=self.dev)
     self._goal_z_d = torch.full((E,), self._goal_z, dtype=torch.float32, device=self.dev)
-    self.goal_lims = np.zeros((E, 2, 2), dtype='int64')
+    self._goal_lims = np.zeros((E, 2, 2), dtype='int64')
     self._rects_d = torch.zeros((E, 4), dtype=torch.int32, device=self.dev)
     self._zero_reward = torch.zeros(E, dtype=torch.float32, device=self.dev)
     self._Ph, self._Pw = H - g.object_h + 1, W - g.object_w + 1
@@ -108,7 +108,9 @@ class BatchedStackEnv(object):
     self._level8_d = torch.full((E,), int(level8.astype('uint8')), dtype=torch.uint8,
                                 device=self.dev)
     # host mirror of the (deterministic) episode cursors: no device read-back
-    self._order = np.zeros((E, self._length), dtype='int32')
+    self._order_h = np.zeros((E, self._length), dtype='int32')
+    self._host_stale = False      # device-side draws not yet mirrored on the host
+    self._episode = 0
     self._cursor = np.zeros(E, dtype='int64')
     self._done = np.ones(E, dtype=bool)
     self._sampler = EpisodeSampler(E, len(bank), self._length, (H, W), (g.object_h, g.object_w),
@@ -142,6 +144,7 @@ class BatchedStackEnv(object):
     stream of each environment is seeded from its rock stream like
     StackEnv.seed -> Rewarder.seed (env.py:340-346, rewarder.py:196-200)."""
     seed = self._sampler.seed(seed)
+    self._seed = seed
     self._action_rng = np.random.RandomState(seed % 2 ** 32)
     return [seed]
 
@@ -152,18 +155,37 @@ class BatchedStackEnv(object):
       return torch.from_numpy(self._action_rng.randint(self.R, size=self.E)), flat
     return flat
 
+  # -- host mirrors of what may have been drawn on the device (vector_rng) --------------- #
+  def _sync_host(self):
+    if self._host_stale:
+      self._order_h[...] = self.obs.state.order.cpu().numpy()
+      self._goal_lims[...] = self._rects_d.cpu().numpy().reshape(self.E, 2, 2)
+      self._host_stale = False
+
+  @property
+  def goal_lims(self):
+    """Goal limits ((u, v), (u + h, v + w)) per environment, Rewarder._goal_lims."""
+    self._sync_host()
+    return self._goal_lims
+
+  @property
+  def _order(self):
+    self._sync_host()
+    return self._order_h
+
   def set_goals(self, lims, env_ids=None):
     """Install goal rectangles ((u, v), (u+h, v+w)) (rewarder.py:252-258): the
     limits go to the device, the maps are filled there."""
     ids = np.arange(self.E) if env_ids is None else np.asarray(list(env_ids), dtype='int64')
-    self.goal_lims[ids] = np.asarray(lims, dtype='int64').reshape(len(ids), 2, 2)
+    self._sync_host()
+    self._goal_lims[ids] = np.asarray(lims, dtype='int64').reshape(len(ids), 2, 2)
     self._rects_d.copy_(torch.from_numpy(
-      np.ascontiguousarray(self.goal_lims.reshape(self.E, 4), dtype='int32')), non_blocking=True)
+      np.ascontiguousarray(self._goal_lims.reshape(self.E, 4), dtype='int32')), non_blocking=True)
     if env_ids is None:
       capi.fill_goals(self._rects_d, self._goal_z_d, self.goals)
     else:
       rects = torch.from_numpy(np.ascontiguousarray(
-        self.goal_lims[ids].reshape(len(ids), 4), dtype='int32')).to(self.dev, non_blocking=True)
+        self._goal_lims[ids].reshape(len(ids), 4), dtype='int32')).to(self.dev, non_blocking=True)
       ids_d = torch.from_numpy(ids.astype('int32')).to(self.dev, non_blocking=True)
       capi.fill_goals(rects, self._goal_z_d, self.goals, env_ids=ids_d)
 
@@ -173,21 +195,35 @@ class BatchedStackEnv(object):
     override the random draws (used to replay recorded episodes)."""
     ids = np.arange(self.E) if env_ids is None else np.asarray(list(env_ids), dtype='int64')
     n = len(ids)
-    # draw order of the reference: episode list first (env.py:268-272), then the
-    # goal (rewarder.reset, env.py:283); an override skips that draw
-    if rock_orders is not None:
-      orders = np.asarray(rock_orders, dtype='int64').reshape(n, self._length)
-    else:
-      orders = self._sampler.orders(ids)
-    if goal_lims is not None:
-      lims = np.asarray(goal_lims, dtype='int64').reshape(n, 2, 2)
-    else:
-      lims = self._sampler.goals(ids)
-    self._order[ids] = orders[:, ::-1]       # the reference pops from the end (env.py:245)
     self._cursor[ids] = 1
     self._done[ids] = False
-    self.set_goals(lims, None if env_ids is None else ids)
-    self.obs.begin(self._order, None if env_ids is None else ids)
+    if self._sampler.vector and rock_orders is None and goal_lims is None:
+      # one counter-based stream for the whole batch, drawn on the device: no host
+      # loop, no upload (same distributions, not the reference's draw sequence)
+      g = self.obs.geo
+      ids_d = None if env_ids is None else torch.from_numpy(ids.astype('int32')).to(self.dev)
+      capi.env_draw(self.obs.state, self._rects_d, len(self.bank),
+                    (g.overhead_h, g.overhead_w), (g.object_h, g.object_w),
+                    self._goal_size_ratio, self._seed, self._episode, ids_d)
+      self._episode += 1
+      self._host_stale = True
+      capi.fill_goals(self._rects_d, self._goal_z_d, self.goals)     # idempotent for the rest
+      self.obs.begin(None, None if env_ids is None else ids)
+    else:
+      # draw order of the reference: episode list first (env.py:268-272), then the
+      # goal (rewarder.reset, env.py:283); an override skips that draw
+      if rock_orders is not None:
+        orders = np.asarray(rock_orders, dtype='int64').reshape(n, self._length)
+      else:
+        orders = self._sampler.orders(ids)
+      if goal_lims is not None:
+        lims = np.asarray(goal_lims, dtype='int64').reshape(n, 2, 2)
+      else:
+        lims = self._sampler.goals(ids)
+      self._sync_host()
+      self._order_h[ids] = orders[:, ::-1]     # the reference pops from the end (env.py:245)
+      self.set_goals(lims, None if env_ids is None else ids)
+      self.obs.begin(self._order_h, None if env_ids is None else ids)
     self._observe()
     return self.observation, self._zero_reward, self.obs.state.done.view(torch.bool)
 
@@ -210,8 +246,8 @@ class BatchedStackEnv(object):
   def _quats(self):
     return self.obs.state.hist_rest.cpu().numpy()[..., 3:]
 
-  def _observe(self):
-    self.obs.observe_walls()
+  def _observe(self, appended=False):
+    self.obs.observe_walls(appended)
     self.obs.observe_rocks()
 
   def _pack(self, out=None):
@@ -252,9 +288,11 @@ class BatchedStackEnv(object):
     return dev64(views), dev64(flat)
 
   def _step_device(self, views, flat):
-    """The kernel chain of one step (no host synchronisation when settle is None)."""
+    """The kernel chain of one step (no host synchronisation when settle is None):
+    -> (observation, reward)."""
     obs = self.obs
     obs.poses_device(views, flat)
+    appended = True
     if self._settle is None:
       obs.advance()
     else:
@@ -266,9 +304,22 @@ class BatchedStackEnv(object):
                              np.asarray(res[1], dtype='float64').reshape(self.E, 4)], axis=1)
       obs.advance(torch.from_numpy(np.ascontiguousarray(rest)).to(self.dev), obs.pose_buf)
       if len(res) > 2 and res[2] is not None:
-        obs.set_poses(res[2])
-    self._observe()
-    return self._reward()
+        obs.set_poses(res[2])            # earlier rocks moved: the whole scene is redrawn
+        appended = False
+    self._observe(appended)
+    return self._reward_and_pack()
+
+  def _reward_and_pack(self):
+    """Packed observation + reward of the step in one launch (a14 + a11/a12)."""
+    g = self.obs.geo
+    wall_goal, rock, r = capi.pack_rewards(
+      self.obs.state, self.obs.walls, self.goals, self.obs.rocks, self._goal_z_d, self._rects_d,
+      self.metric, self.scale, (g.pixel_h, g.pixel_w), self._pmax, self._pexp, self._oexp,
+      dtype=self._dtype, obs_scale=self._scale, repeat_wall=self.R > 1)
+    if self.metric == 'all':
+      # the reference returns the four metrics as the info dict (env.py:258-262)
+      r = {name: r[:, k] for k, name in enumerate(METRIC_NAMES)}
+    return (wall_goal, rock if self.R > 1 else rock[:, 0]), r
 
   def step(self, action):
     """action: [E] flat indices, or (views [E], flat indices [E]) when
@@ -284,8 +335,7 @@ class BatchedStackEnv(object):
       self._graph.replay()
       reward, observation = self._g_reward, self._g_obs
     else:
-      reward = self._step_device(views, flat)
-      observation = self.observation
+      observation, reward = self._step_device(views, flat)
     self._advance_host()
     return observation, reward, self.obs.state.done.view(torch.bool)
 
@@ -322,8 +372,7 @@ class BatchedStackEnv(object):
           self._g_action = action
         else:
           views, flat = self._g_views, self._g_flat
-        self._g_reward = self._step_device(views, flat)
-        self._g_obs = self._pack()
+        self._g_obs, self._g_reward = self._step_device(views, flat)
     torch.cuda.current_stream(dev).wait_stream(stream)
     self._graph, self._graph_policy = graph, policy
     return self

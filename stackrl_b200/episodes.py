@@ -73,19 +73,18 @@ class EpisodeSampler(object):
 
   def _orders_vector(self, n):
     rng, M, L = self._rng, self.M, self.L
-    order = rng.randint(M, size=(n, L))
-    if not self.replace:
-      # without replacement: redraw the rows that repeat a rock (rare when M >> L)
-      for _ in range(64):
-        srt = np.sort(order, axis=1)
-        bad = np.nonzero((srt[:, 1:] == srt[:, :-1]).any(axis=1))[0]
-        if len(bad) == 0:
-          break
-        if M < 4 * L:
-          order[bad] = np.stack([rng.permutation(M)[:L] for _ in bad])
-        else:
-          order[bad] = rng.randint(M, size=(len(bad), L))
-    return order.astype('int64')
+    if self.replace:
+      return rng.randint(M, size=(n, L)).astype('int64')
+    # without replacement: the first L steps of a Fisher-Yates shuffle, all rows at once
+    deck = np.tile(np.arange(M, dtype='int64'), (n, 1))
+    rows = np.arange(n)
+    u = rng.random_sample((L, n))
+    for k in range(L):
+      j = k + (u[k] * (M - k)).astype('int64')
+      picked = deck[rows, j]
+      deck[rows, j] = deck[rows, k]
+      deck[rows, k] = picked
+    return deck[:, :L].copy()
 
   # -- goal rectangles: [n, 2, 2] = ((u, v), (u + h, v + w)) = Rewarder._goal_lims ------- #
   def goals(self, ids):

@@ -411,6 +411,12 @@ class BatchedObserver(object):
                              device=self.dev)
     self.rocks = torch.zeros((E, R, g.object_h, g.object_w), dtype=torch.float32,
                              device=self.dev)
+    # GL depth image of the placed rocks of every environment, kept between steps:
+    # a step that only appends a rock draws that rock alone onto it (same bits as
+    # re-drawing the scene: the depth image is a minimum over triangles).
+    self._wall_depth = torch.ones((E, g.overhead_h, g.overhead_w), dtype=torch.float32,
+                                  device=self.dev)
+    self._wall_depth_valid = False
 
   # -- instance rows -------------------------------------------------------------- #
   def _rows(self, mesh_ids, positions, quaternions):
@@ -443,14 +449,16 @@ class BatchedObserver(object):
   # -- episodes --------------------------------------------------------------------- #
   def begin(self, orders, env_ids=None):
     """Start episodes (env.py:266-293): ``orders`` is the full [E, length] host table
-    of mesh ids in pop order (uploaded whole); ``env_ids``: the environments to
-    restart (None: all)."""
+    of mesh ids in pop order (uploaded whole; None: ``state.order`` was filled on the
+    device, srl_env_draw); ``env_ids``: the environments to restart (None: all)."""
     st = self.state
-    st.order.copy_(torch.from_numpy(np.ascontiguousarray(orders, dtype='int32')),
-                   non_blocking=True)
+    if orders is not None:
+      st.order.copy_(torch.from_numpy(np.ascontiguousarray(orders, dtype='int32')),
+                     non_blocking=True)
     ids = None if env_ids is None else torch.from_numpy(
       np.ascontiguousarray(env_ids, dtype='int32')).to(self.dev, non_blocking=True)
     capi.env_reset(st, ids)
+    self._wall_depth_valid = False
     if env_ids is None:
       self.status.copy_(self._status_zero, non_blocking=True)     # device memcpy
 
@@ -471,6 +479,7 @@ class BatchedObserver(object):
     inst_rows = self._inst.view(torch.float64).view(self.E * self.cap, -1)
     inst_rows.index_copy_(0, torch.clamp(slot, max=self.E * self.cap - 1), rows)
     self.counts[env_ids] = torch.clamp(self.counts[env_ids] + 1, max=self.cap)
+    self._wall_depth_valid = False
 
   def poses_device(self, views, flat):
     """Observer.pose for every environment on the device (observer.py:392-421):
@@ -492,16 +501,22 @@ class BatchedObserver(object):
     poses = torch.as_tensor(np.ascontiguousarray(poses, dtype='float64')) \
       if not isinstance(poses, torch.Tensor) else poses
     capi.env_set_poses(self.state, poses.to(self.dev).contiguous())
+    self._wall_depth_valid = False
 
   # -- capture -------------------------------------------------------------------- #
-  def observe_walls(self):
+  def observe_walls(self, appended=False):
     """Rasterise every environment's placed rocks into ``walls``
-    (observer.py:252-260)."""
+    (observer.py:252-260).  ``appended``: since the last call exactly one rock was
+    appended to every environment (``advance``) and nothing else moved -- only that
+    rock is drawn, onto the kept depth image; otherwise the whole scene."""
     g = self.geo
+    last = bool(appended) and self._wall_depth_valid
     capi.raster(self._verts, self._tris, self._inst, self._wall_jobs, g.overhead_h,
                 g.overhead_w, capi.RASTER_WALL, far_plane=FAR, out=self.walls,
-                inst_counts=self.counts,
-                max_cached_verts=min(2048, max(256, self._max_verts * self.cap)))
+                inst_counts=self.counts, depth_state=self._wall_depth, only_last=last,
+                max_cached_verts=max(256, self._max_verts) if last else
+                min(2048, max(256, self._max_verts * self.cap)))
+    self._wall_depth_valid = True
     return self.walls
 
   def observe_rocks(self, mesh_ids=None):

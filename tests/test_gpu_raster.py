@@ -582,3 +582,69 @@ def test_discounted_rewards_and_settle_hook_moving_every_rock(mods):
     walls = env.obs.walls.clone()
     env.obs.observe_walls()
     assert torch.equal(walls, env.obs.walls)
+
+
+def test_incremental_wall_image_equals_the_full_redraw(mods):
+  """A step draws only the appended rock onto the kept depth image
+  (srl_raster_incremental); re-drawing every placed rock gives the same bits."""
+  envs = mods['envs']
+  for dtype, freedom in (('float32', 0), ('uint8', 2)):
+    env = _synthetic_env(mods, 33, dtype, freedom, steps=7)
+    policy = envs.HeightPolicy()
+    env.reset()
+    for k in range(7):
+      env.step(policy(env))
+      walls = env.obs.walls.clone()
+      depth = env.obs._wall_depth.clone()
+      env.obs._wall_depth_valid = False
+      env.obs.observe_walls()                      # whole scene
+      assert torch.equal(walls, env.obs.walls), (dtype, k)
+      assert torch.equal(depth, env.obs._wall_depth)
+      assert int(env.obs.counts[0]) == k + 1
+    # a new episode starts from an empty image
+    env.reset()
+    assert float(env.obs.walls.abs().max()) == 0.
+
+
+def test_device_side_episode_draws(mods):
+  """vector_rng=True: rock lists and goal rectangles drawn by srl_env_draw obey the
+  constraints of env.py:268-272 / rewarder.py:211-250 and change per episode."""
+  for ratio in (.25, (.5, .25), None):
+    env = _synthetic_env(mods, 500, steps=6, vector_rng=True, goal_size_ratio=ratio, seed=9)
+    env.reset()
+    lims, order = env.goal_lims.copy(), env._order.copy()
+    h = lims[:, 1, 0] - lims[:, 0, 0]
+    w = lims[:, 1, 1] - lims[:, 0, 1]
+    assert (h >= 16).all() and (w >= 16).all() and (lims[:, 1] <= 64).all() and (lims >= 0).all()
+    u_max, v_max = 64 - h, 64 - w
+    assert (lims[:, 0, 0] >= u_max // 8).all() and (lims[:, 0, 0] <= 7 * u_max // 8).all()
+    assert (lims[:, 0, 1] >= v_max // 8).all() and (lims[:, 0, 1] <= 7 * v_max // 8).all()
+    if ratio == .25:
+      assert (np.abs(h * w - 1024) <= np.maximum(h, w)).all()
+      assert len(np.unique(h)) > 5                      # the beta draw spreads the aspect
+    if ratio == (.5, .25):
+      assert set(zip(h.tolist(), w.tolist())) == {(32, 16), (16, 32)}
+    if ratio is None:
+      assert (h == 16).all() and len(np.unique(w)) > 5  # quirk Q13
+    srt = np.sort(order, axis=1)
+    assert not (srt[:, 1:] == srt[:, :-1]).any()        # 16 rocks >= 6 per episode
+    assert order.min() >= 0 and order.max() < 16 and len(np.unique(order[:, 0])) == 16
+    goal = env.goals.cpu().numpy()
+    for e in (0, 17, 499):
+      (u0, v0), (u1, v1) = lims[e]
+      want = np.zeros((64, 64), 'float32')
+      want[u0:u1, v0:v1] = np.float32(0.25)
+      assert np.array_equal(goal[e], want)
+    env.step(mods['envs'].HeightPolicy()(env))
+    env.reset(env_ids=[3, 4])                           # partial reset: a new draw for two
+    lims2, order2 = env.goal_lims, env._order
+    keep = np.ones(500, bool)
+    keep[[3, 4]] = False
+    assert np.array_equal(lims2[keep], lims[keep]) and np.array_equal(order2[keep], order[keep])
+    assert not np.array_equal(order2[[3, 4]], order[[3, 4]])
+    assert env.obs.counts.cpu().numpy()[[3, 4, 5]].tolist() == [0, 0, 1]
+  # a bank smaller than the episode: drawn with replacement
+  from stackrl_b200 import capi
+  env = _synthetic_env(mods, 64, steps=40, vector_rng=True, seed=2)
+  env.reset()
+  assert env._order.max() < 16 and env._order.shape == (64, 40)

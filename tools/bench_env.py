@@ -38,10 +38,10 @@ def timeit(fn, reps=20):
 
 
 print('mode %s, E=%d' % (os.environ.get('SRL_RASTER_MODE', '0'), E))
-print('walls  %.3f ms' % timeit(env.obs.observe_walls))
+print('walls (full redraw) %.3f ms' % timeit(env.obs.observe_walls))
+print('walls (appended rock) %.3f ms' % timeit(lambda: env.obs.observe_walls(True)))
 print('rocks  %.3f ms' % timeit(env.obs.observe_rocks))
-print('reward %.3f ms' % timeit(env._reward))
-print('pack   %.3f ms' % timeit(lambda: env.observation))
+print('reward+pack %.3f ms' % timeit(env._reward_and_pack))
 print('policy %.3f ms' % timeit(lambda: policy(env)))
 view = torch.zeros(E, dtype=torch.int64, device=dev)
 print('poses+advance (state frozen: done envs skip) %.3f ms' % timeit(
