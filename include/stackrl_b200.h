@@ -194,13 +194,25 @@ SRL_API int srl_correlate_f32(const float* walls, const float* rocks, const floa
  *   tf.nn.conv2d(x[b][None], w[b][..., None], strides=1, padding='VALID'):
  *   out[b,i,j] = sum_{u,v,c} x[b,i+u,j+v,c] * w[b,u,v,c]
  * x [B,H,W,C], w [B,h,wd,C] float32 channels-last (the reference's tensor layout),
- * out [B,H-h+1,W-wd+1] (the reference's trailing unit channel is a view).  float32
- * products and accumulation (float64 across input rows); inputs must be finite.
+ * out [B,H-h+1,W-wd+1] (the reference's trailing unit channel is a view).  Shapes with
+ * C % 8 == 0 and h <= 32 that fit shared memory run on the tensor cores (tcgen05.mma,
+ * kind::tf32, every operand split hi + lo: three products, float32 accumulation in
+ * TMEM per filter row, float32 sum over the filter rows); everything else on the FP32
+ * FMA pipe.  Inputs must be finite.
  * Matched to a tolerance (1e-5 of the largest output): TensorFlow's own summation
  * order is outside the reference tree. */
 SRL_API int srl_siam_correlation_f32(const float* x, const float* w, float* out, int B,
                                      int H, int W, int C, int h, int wd,
                                      srl_stream_t stream);
+
+/* The two vector-Jacobian products of the layer (the DQN trains through it,
+ * nets/models.py:89, 182):  grad_w[b,u,v,c] = sum_{i,j} grad_out[b,i,j] x[b,i+u,j+v,c],
+ * grad_x[b,r,s,c] = sum_{u,v} grad_out[b,r-u,s-v] w[b,u,v,c].  grad_out [B,H-h+1,W-wd+1];
+ * either output may be NULL (then the matching input may be NULL too).  float32. */
+SRL_API int srl_siam_correlation_grad_f32(const float* x, const float* w,
+                                          const float* grad_out, float* grad_x, float* grad_w,
+                                          int B, int H, int W, int C, int h, int wd,
+                                          srl_stream_t stream);
 
 /* corrcoef(localized=True) (baselines.py:87-114): the masked variant, every sum in
  * numpy's pairwise order and in the observation's arithmetic type (float32, or

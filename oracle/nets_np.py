@@ -41,3 +41,23 @@ def correlation_loops(in0, in1):
       for j in range(W - w + 1):
         out[b, i, j, 0] = (in0[b, i:i + h, j:j + w, :] * in1[b]).sum()
   return out
+
+
+def correlation_grads(in0, in1, grad_out):
+  """Vector-Jacobian products of ``correlation`` by the definition (float64):
+  grad_in1[b,u,v,c] = sum_{i,j} g[b,i,j] in0[b,i+u,j+v,c];
+  grad_in0[b,r,s,c] = sum_{u,v} g[b,r-u,s-v] in1[b,u,v,c]."""
+  in0 = np.asarray(in0, dtype='float64')
+  in1 = np.asarray(in1, dtype='float64')
+  B, H, W, C = in0.shape
+  _, h, w, _ = in1.shape
+  g = np.asarray(grad_out, dtype='float64').reshape(B, H - h + 1, W - w + 1)
+  g0 = np.zeros_like(in0)
+  g1 = np.zeros_like(in1)
+  for b in range(B):
+    for u in range(h):
+      for v in range(w):
+        patch = in0[b, u:u + H - h + 1, v:v + W - w + 1, :]            # [Ph, Pw, C]
+        g1[b, u, v, :] = np.einsum('ij,ijc->c', g[b], patch)
+        g0[b, u:u + H - h + 1, v:v + W - w + 1, :] += g[b][:, :, None] * in1[b, u, v, :]
+  return g0, g1

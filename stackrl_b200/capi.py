@@ -57,6 +57,7 @@ _SIGNATURES = {
   'srl_corrcoef_localized_u8': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
   'srl_correlate_f32': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
   'srl_siam_correlation_f32': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+  'srl_siam_correlation_grad_f32': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
   'srl_raster': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _P]),
   'srl_raster_ex': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _I, _P]),
   'srl_raster_incremental': (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _c.c_double,
@@ -493,6 +494,25 @@ def siam_correlation_f32(x, w, out=None):
     _check(lib.srl_siam_correlation_f32(*args, _dev(out, torch.float32, 'out'),
                                         B, H, W, C, h, wd, _stream()))
   return out
+
+
+def siam_correlation_grad_f32(x, w, grad_out, want_x=True, want_w=True):
+  """Vector-Jacobian products of the correlation layer: grad_out [B,Ph,Pw(,1)] ->
+  (grad_x like x | None, grad_w like w | None)."""
+  B, H, W, C = x.shape
+  h, wd = w.shape[1], w.shape[2]
+  if grad_out.numel() != B * (H - h + 1) * (W - wd + 1):
+    raise ValueError('grad_out must hold [B, H-h+1, W-w+1] values, got {}'.format(
+      tuple(grad_out.shape)))
+  _same_device(x, w, grad_out)
+  gx = torch.empty_like(x) if want_x else None
+  gw = torch.empty_like(w) if want_w else None
+  with torch.cuda.device(x.device):
+    _check(lib.srl_siam_correlation_grad_f32(
+      _dev(x, torch.float32, 'x'), _dev(w, torch.float32, 'w'),
+      _dev(grad_out, torch.float32, 'grad_out'), _opt(gx, torch.float32, 'grad_x'),
+      _opt(gw, torch.float32, 'grad_w'), B, H, W, C, h, wd, _stream()))
+  return gx, gw
 
 
 def correlate_f32(walls, rocks, level=None, want_corr=True, want_coef=True):

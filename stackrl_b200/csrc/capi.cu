@@ -315,6 +315,13 @@ int srl_quantise_planes_u8(const float* walls, const float* goals, const float* 
                                  scale, (cudaStream_t)stream);
 }
 
+int srl_siam_correlation_grad_f32(const float* x, const float* w, const float* grad_out,
+                                  float* grad_x, float* grad_w, int B, int H, int W, int C,
+                                  int h, int wd, srl_stream_t stream) {
+  return srl::siam_correlation_grad_f32(x, w, grad_out, grad_x, grad_w, B, H, W, C, h, wd,
+                                        (cudaStream_t)stream);
+}
+
 int srl_microbench_addmax(int variant, int iters, double* host_cells_per_s) {
   return srl::microbench_addmax(variant, iters, host_cells_per_s);
 }

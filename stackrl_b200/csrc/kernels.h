@@ -118,6 +118,13 @@ int quantise_planes_u8(const float* walls, const float* goals, const float* rock
                        uint8_t* walls8, uint8_t* goals8, uint8_t* rocks8, int E, int R, int H,
                        int W, int h, float scale, cudaStream_t stream);
 
+int siam_correlation_tc(const float* x, const float* f, float* out, int B, int H, int W, int C,
+                        int h, int wd, cudaStream_t stream);
+
+int siam_correlation_grad_f32(const float* x, const float* f, const float* g, float* grad_x,
+                              float* grad_f, int B, int H, int W, int C, int h, int wd,
+                              cudaStream_t stream);
+
 int microbench_addmax(int variant, int iters, double* host_cells_per_s);
 
 int microbench_fma(int variant, int iters, double* host_fma_per_s);

@@ -5,18 +5,41 @@ of the rock features over the wall features inside the DQN.
 Reference: ``stackrl.nets.correlation`` (stackrl/nets/layers.py:21-38), a Keras
 Lambda around ``tf.map_fn`` of one ``tf.nn.conv2d`` per sample, called from
 PseudoSiamFCN / DeepQSiamFCN (stackrl/nets/models.py:89, 182).  Here it is one
-launch of ``srl_siam_correlation_f32`` over the whole batch.  The rest of the
-networks (U-Nets, position layers, dueling head) stays the reference's.
+launch of ``srl_siam_correlation_f32`` over the whole batch (tensor cores: tcgen05,
+3xTF32) and, for training, ``srl_siam_correlation_grad_f32`` behind
+torch.autograd.  The rest of the networks (U-Nets, position layers, dueling head)
+stays the reference's.
 """
 import torch
 
 from stackrl_b200 import capi
 
 
+class _Correlation(torch.autograd.Function):
+  """The layer with its two vector-Jacobian products, so that a network trains
+  through it like through the reference's Lambda(tf.map_fn(conv2d)) (the DQN's
+  gradient tape, stackrl/agents/dqn.py, differentiates nets/models.py:89, 182)."""
+
+  @staticmethod
+  def forward(ctx, in0, in1):
+    in0, in1 = in0.contiguous(), in1.contiguous()
+    ctx.save_for_backward(in0, in1)
+    return capi.siam_correlation_f32(in0, in1)
+
+  @staticmethod
+  def backward(ctx, grad_out):
+    in0, in1 = ctx.saved_tensors
+    g0, g1 = capi.siam_correlation_grad_f32(
+      in0, in1, grad_out.contiguous(), want_x=ctx.needs_input_grad[0],
+      want_w=ctx.needs_input_grad[1])
+    return g0, g1
+
+
 def correlation(in0, in1, parallel_iterations=None):
   """``in0`` [B,H,W,C], ``in1`` [B,h,w,C] (float32 CUDA tensors, channels-last
   like the reference's) -> [B,H-h+1,W-w+1,1]: for every sample the VALID
   cross-correlation of in0 with in1 used as the filter, summed over channels.
+  Differentiable with respect to both inputs (torch.autograd).
 
   ``parallel_iterations`` is the reference's ``tf.map_fn`` knob; the batch is
   always one launch here, the argument is accepted and ignored."""
@@ -26,6 +49,8 @@ def correlation(in0, in1, parallel_iterations=None):
   if in0.dtype != torch.float32 or in1.dtype != torch.float32:
     raise TypeError('correlation is float32 like the reference layer, got {} and {}'.format(
       in0.dtype, in1.dtype))
+  if in0.requires_grad or in1.requires_grad:
+    return _Correlation.apply(in0, in1)
   return capi.siam_correlation_f32(in0.contiguous(), in1.contiguous())
 
 

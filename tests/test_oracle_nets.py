@@ -49,3 +49,22 @@ def test_mirror_has_no_cpu_path():
     nets.correlation(torch.from_numpy(x), torch.from_numpy(f))
   with pytest.raises(TypeError):
     nets.correlation(torch.from_numpy(x).double(), torch.from_numpy(f).double())
+
+
+def test_gradients_match_finite_differences():
+  """The oracle's vector-Jacobian products against central differences of the oracle's
+  forward (the layer is bilinear, so the difference quotient is exact up to rounding)."""
+  rng = np.random.default_rng(3)
+  x = rng.standard_normal((2, 7, 9, 3))
+  f = rng.standard_normal((2, 3, 4, 3))
+  g = rng.standard_normal((2, 5, 6))
+  g0, g1 = nets_np.correlation_grads(x, f, g)
+  loss = lambda a, b: float((nets_np.correlation(a, b)[..., 0] * g).sum())
+  for idx in [(0, 0, 0, 0), (1, 6, 8, 2), (0, 3, 4, 1)]:
+    d = np.zeros_like(x)
+    d[idx] = 1e-3
+    assert abs((loss(x + d, f) - loss(x - d, f)) / 2e-3 - g0[idx]) < 1e-9
+  for idx in [(0, 0, 0, 0), (1, 2, 3, 2), (0, 1, 2, 1)]:
+    d = np.zeros_like(f)
+    d[idx] = 1e-3
+    assert abs((loss(x, f + d) - loss(x, f - d)) / 2e-3 - g1[idx]) < 1e-9
