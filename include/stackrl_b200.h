@@ -329,6 +329,24 @@ SRL_API int srl_place_poses_f32(const float* walls, const float* rocks, const in
                                 double object_x, double object_y, double object_z,
                                 float threshold, srl_stream_t stream);
 
+/* ---- contact pre-check of a placement from the heightmaps ----------
+ * The reference learns whether a dropped rock rests by stepping physics until it
+ * has >= 3 contact points (Simulator._drop, simulator.py:337-341).  The maps answer a
+ * cheaper version of the question before any physics: with h0 = max((walls[e, window]
+ * + rocks[e, r])[rocks > threshold]) (a4 / a5), the cells with h0 - (wall + rock) <=
+ * eps -- difference()'s residual field (baselines.py:64-72) thresholded -- are where
+ * the rock touches.  contacts [E] i32: their number; octants [E] i32: bit k set when a
+ * touching cell lies in octant k (45 degree sectors, counter-clockwise from +row)
+ * around the map centre (= the centre of mass in x, y: the object camera looks at the
+ * inertial frame, observer.py:148-164); supported [E] u8: contacts >= 3 and no four
+ * consecutive empty octants (no empty half-plane through the centre).  Actions as in
+ * srl_place_poses_f32; an invalid action gives (0, 0, 0). */
+SRL_API int srl_contact_precheck_f32(const float* walls, const float* rocks,
+                                     const int64_t* views, const int64_t* flat,
+                                     int32_t* contacts, int32_t* octants, uint8_t* supported,
+                                     int E, int R, int H, int W, int h, int action_stride,
+                                     float threshold, float eps, srl_stream_t stream);
+
 /* ---- a15: episode bookkeeping of StackEnv.step / reset on the device --------------
  * (env.py:233-293 around the physics call; Simulator.positions /
  * distances_from_place, simulator.py:86-127, for the discounted rewards).

@@ -80,3 +80,37 @@ def reward(wall, goal, goal_z, metric, memory=0., scale=1.):
   else:
     raise ValueError(metric)
   return (r - memory) * scale, r
+
+
+def contact_precheck(wall, rock, pixel, eps=2. ** -13, threshold=1e-4):
+  """Restatement of the heightmap contact pre-check (srl_contact_precheck_f32): the
+  residual field h0 - (wall_window + rock) of baselines.py:64-72 at ``pixel``, cells
+  within ``eps`` of the contact height counted and sorted into the 8 octants around
+  the map centre; supported = at least 3 contacts and no 4 consecutive empty octants
+  (the heightmap analogue of Simulator._drop's contact-point count,
+  simulator.py:337-341).  -> (contacts, octant mask, supported)."""
+  wall = np.asarray(wall, dtype='float32')
+  rock = np.asarray(rock, dtype='float32')
+  h = rock.shape[0]
+  i, j = pixel
+  lift = wall[i:i + h, j:j + h] + rock
+  live = rock > np.float32(threshold)
+  top = lift[live].max()
+  touch = live & ((top - lift) <= np.float32(eps))
+  mask = 0
+  for u, v in zip(*np.nonzero(touch)):
+    dx, dy = 2 * int(u) + 1 - h, 2 * int(v) + 1 - h
+    ax, ay = abs(dx), abs(dy)
+    if dx >= 0 and dy >= 0:
+      o = 0 if ax >= ay else 1
+    elif dx < 0 and dy >= 0:
+      o = 2 if ay > ax else 3
+    elif dx < 0 and dy < 0:
+      o = 4 if ax >= ay else 5
+    else:
+      o = 6 if ay > ax else 7
+    mask |= 1 << o
+  m2 = mask | (mask << 8)
+  gap = any(((m2 >> s) & 0xf) == 0 for s in range(8))
+  count = int(touch.sum())
+  return count, mask, bool(count >= 3 and not gap)

@@ -67,6 +67,7 @@ _SIGNATURES = {
   'srl_place_poses_f32': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_double,
                                 _c.c_double, _c.c_double, _c.c_double, _c.c_double,
                                 _c.c_float, _P]),
+  'srl_contact_precheck_f32': (_I, [_P] * 7 + [_I] * 6 + [_c.c_float, _c.c_float, _P]),
   'srl_env_reset': (_I, [_P, _P, _I, _P]),
   'srl_env_advance': (_I, [_P, _P, _P, _P]),
   'srl_env_set_poses': (_I, [_P, _P, _I, _P]),
@@ -610,6 +611,28 @@ def place_poses(walls, rocks, views, flat, orientations, geometry, threshold=1e-
       _out(status, torch.int32, (E,), walls, 'status'), E, R, H, W, h, int(stride),
       *[float(x) for x in geometry], float(threshold), _stream()))
   return poses, status
+
+
+def contact_precheck(walls, rocks, views, flat, eps=2. ** -13, threshold=1e-4):
+  """Heightmap contact pre-check of the chosen placements (srl_contact_precheck_f32):
+  -> (contacts [E] int32, octants [E] int32 bit mask, supported [E] bool)."""
+  E, R, H, W, h = _batch_dims(walls, rocks)
+  dev = walls.device
+  stride = flat.stride(0) if E > 1 else 1
+  for name, t in (('views', views), ('flat', flat)):
+    if t is not None and (not t.is_cuda or t.dtype != torch.int64 or
+                          (E > 1 and t.stride(0) != stride)):
+      raise TypeError('{} must be an int64 CUDA tensor of the common stride'.format(name))
+  contacts = torch.empty((E,), dtype=torch.int32, device=dev)
+  octants = torch.empty((E,), dtype=torch.int32, device=dev)
+  supported = torch.empty((E,), dtype=torch.uint8, device=dev)
+  with torch.cuda.device(dev):
+    _check(lib.srl_contact_precheck_f32(
+      _dev(walls, torch.float32, 'walls'), _dev(rocks, torch.float32, 'rocks'),
+      _P(None) if views is None else _P(views.data_ptr()), _P(flat.data_ptr()),
+      _P(contacts.data_ptr()), _P(octants.data_ptr()), _P(supported.data_ptr()), E, R, H, W, h,
+      int(stride), float(threshold), float(eps), _stream()))
+  return contacts, octants, supported.view(torch.bool)
 
 
 def env_reset(state, env_ids=None):

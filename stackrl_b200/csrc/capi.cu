@@ -249,6 +249,16 @@ int srl_place_poses_f32(const float* walls, const float* rocks, const int64_t* v
                               object_z, threshold, (cudaStream_t)stream);
 }
 
+int srl_contact_precheck_f32(const float* walls, const float* rocks, const int64_t* views,
+                             const int64_t* flat, int32_t* contacts, int32_t* octants,
+                             uint8_t* supported, int E, int R, int H, int W, int h,
+                             int action_stride, float threshold, float eps,
+                             srl_stream_t stream) {
+  return srl::contact_precheck_f32(walls, rocks, views, flat, contacts, octants, supported, E, R,
+                                   H, W, h, action_stride, threshold, eps,
+                                   (cudaStream_t)stream);
+}
+
 int srl_env_reset(const srl_env_state* host_state, const int32_t* env_ids, int n,
                   srl_stream_t stream) {
   return srl::env_reset(host_state, env_ids, n, (cudaStream_t)stream);

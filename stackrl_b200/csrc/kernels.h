@@ -91,6 +91,10 @@ int place_poses_f32(const float* walls, const float* rocks, const int64_t* views
                     int32_t* status, int E, int R, int H, int W, int h, int action_stride,
                     double pixel_h, double pixel_w, double object_x, double object_y,
                     double object_z, float threshold, cudaStream_t stream);
+int contact_precheck_f32(const float* walls, const float* rocks, const int64_t* views,
+                         const int64_t* flat, int32_t* contacts, int32_t* octants,
+                         uint8_t* supported, int E, int R, int H, int W, int h,
+                         int action_stride, float threshold, float eps, cudaStream_t stream);
 int env_advance(const srl_env_state* st, const double* rest, const double* placed,
                 cudaStream_t stream);
 int env_reset(const srl_env_state* st, const int32_t* env_ids, int n, cudaStream_t stream);

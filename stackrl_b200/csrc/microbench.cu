@@ -96,11 +96,14 @@ __global__ void __launch_bounds__(256) addmax_kernel(const float* in, float* out
           if constexpr (VARIANT == 2) acc[t] = vmax3(acc[t], s0, s1);
           else acc[t] = vimax3(acc[t], s0, s1);
         } else if constexpr (VARIANT == 3) {
-          acc[t] = vadd(acc[k1], nv[v]);
-          acc[t] = vadd(acc[k2], nv[v + 1]);
+          // two DEPENDENT adds, both live (round 1 overwrote the first result, which
+          // ptxas removed: the reported rate counted instructions that never ran)
+          acc[t] = vadd(vadd(acc[k1], nv[v]), nv[v + 1]);
         } else if constexpr (VARIANT == 4) {
+          // two maxima that cannot fuse into one FMNMX3: the inner one feeds an add-free
+          // chain through a second accumulator
           acc[t] = vmax(acc[k1], nv[v]);
-          acc[t] = vmax(acc[k2], nv[v + 1]);
+          acc[k2] = vmax(acc[t], nv[v + 1]);
         } else if constexpr (VARIANT == 5) {
           acc[t] = vmax3(acc[k1], acc[k2], nv[v]);
         } else if constexpr (VARIANT == 6) {

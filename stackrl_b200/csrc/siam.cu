@@ -219,15 +219,19 @@ int siam_correlation_f32(const float* x, const float* w, float* out, int B, int 
               "siam_correlation: bad shape B=%d H=%d W=%d C=%d h=%d w=%d", B, H, W, C, h, wd);
   if (B == 0) return SRL_OK;
   SRL_REQUIRE(x && w && out, SRL_E_INVALID, "siam_correlation: null pointer");
-  // Tensor-core path (siam_tc.cu: tcgen05, 3xTF32) for the shapes it covers; the
-  // FP32 FFMA2 kernel below for the rest, and as the A/B reference (SRL_SIAM_MODE=0).
+  // Tensor-core path (siam_tc.cu: tcgen05, 3xTF32) for the shapes it covers and batches
+  // that fill the GPU with whole samples (one CTA per sample: a band split re-stages
+  // the filter and h - 1 image rows per band, which the FP32 kernel does not pay);
+  // the FP32 FFMA2 kernel below for the rest.  SRL_SIAM_MODE: 0 FP32 only, 1 automatic
+  // (default), 2 tensor cores whenever the shape allows (tests, A/B).
+  const int sms = sm_count();
   int mode = 1;
   if (const char* m = getenv("SRL_SIAM_MODE")) mode = atoi(m);
-  if (mode != 0) {
+  const long long whole = (long long)B * ((W - wd + 1 + 127) / 128);
+  if (mode == 2 || (mode == 1 && 4 * whole >= 3ll * sms)) {
     const int rc = siam_correlation_tc(x, w, out, B, H, W, C, h, wd, stream);
     if (rc != SRL_E_UNSUPPORTED) return rc;
   }
-  const int sms = sm_count();
   SRL_REQUIRE(sms > 0, SRL_E_CUDA, "siam_correlation: no CUDA device");
   SiamParams p;
   p.x = x; p.w = w; p.out = out;

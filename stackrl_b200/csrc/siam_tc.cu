@@ -83,22 +83,33 @@ __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], TF32 operands, float32 accumulate.
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                          uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                          uint32_t accumulate) {
+  // executed by the whole (converged) warp with warp-uniform operands; one elected
+  // lane issues -- the operands then stay on the uniform datapath
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
       "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// mbarrier arrive once every tcgen05.mma issued so far by this thread has completed.
+// mbarrier arrive once every tcgen05.mma issued so far by the elected lane has completed
+// (elect.sync picks the same lane every time for a full mask).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-          smem_u32(bar))
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar))
       : "memory");
 }
 // 32 consecutive accumulator columns of this thread's TMEM lane.
@@ -140,7 +151,10 @@ __device__ __forceinline__ float tf32_hi(float x) {
 
 __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // (shuffled so that the compiler knows the warp index is warp-uniform: the role
+  // branches and everything the MMA issuer computes then stay on the uniform datapath)
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int Q = p.Q, N = p.N, wd = p.wd;
   // ---- shared memory ----------------------------------------------------------------- //
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -200,7 +214,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcPara
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // =============================== MMA issuer ========================================= //
@@ -214,23 +228,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcPara
       mbar_wait(full + s, (k / kTcStages) & 1);
       if (k >= 2) mbar_wait(acc_empty + b, ((k >> 1) - 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      {
         const uint32_t d = tmem + (uint32_t)(b * 32);
+        // Descriptors differ only in their start-address field (low 14 bits, 16-byte
+        // units): one add per operand and MMA instead of rebuilding 64-bit words.
         const uint32_t a_hi = a_base + (uint32_t)(s * stage_bytes);
-        const uint32_t a_lo = a_hi + (uint32_t)(Q * p.plane);
+        const uint64_t a_tmpl = smem_desc(0, p.plane, 128), b_tmpl = smem_desc(0, p.bplane, 128);
+        const uint32_t a_top = (uint32_t)(a_tmpl >> 32), b_top = (uint32_t)(b_tmpl >> 32);
+        const uint32_t a_mid = (uint32_t)a_tmpl, b_mid = (uint32_t)b_tmpl;   // LBO field, bits 16..29
+        const uint32_t a_hi0 = a_mid | (a_hi >> 4), a_lo0 = a_mid | ((a_hi + (uint32_t)(Q * p.plane)) >> 4);
+        const uint32_t qstep = (uint32_t)(2 * p.plane) >> 4, bstep = (uint32_t)(2 * p.bplane) >> 4;
+        uint32_t bh = b_mid | (b_base >> 4), bl = b_mid | ((b_base + b_lo) >> 4);
         uint32_t first = 0;
         for (int v = 0; v < wd; ++v) {
+          uint32_t ah = a_hi0 + (uint32_t)v, al = a_lo0 + (uint32_t)v;
+#pragma unroll 2
           for (int q = 0; q < Q; q += 2) {
-            const uint32_t ao = (uint32_t)(q * p.plane + 16 * v);
-            const uint32_t bo = (uint32_t)((v * Q + q) * p.bplane);
-            const uint64_t ah = smem_desc(a_hi + ao, p.plane, 128);
-            const uint64_t al = smem_desc(a_lo + ao, p.plane, 128);
-            const uint64_t bh = smem_desc(b_base + bo, p.bplane, 128);
-            const uint64_t bl = smem_desc(b_base + b_lo + bo, p.bplane, 128);
-            umma_tf32(d, al, bh, idesc, first);     // small terms first
-            umma_tf32(d, ah, bl, idesc, 1u);
-            umma_tf32(d, ah, bh, idesc, 1u);
+            umma_tf32(d, al, a_top, bh, b_top, idesc, first);     // small terms first
+            umma_tf32(d, ah, a_top, bl, b_top, idesc, 1u);
+            umma_tf32(d, ah, a_top, bh, b_top, idesc, 1u);
             first = 1u;
+            ah += qstep; al += qstep; bh += bstep; bl += bstep;
           }
         }
         umma_commit(freeb + s);        // the stage may be overwritten

@@ -344,6 +344,13 @@ class BatchedStackEnv(object):
     self._cursor += more
     self._done = ~more
 
+  def contact_precheck(self, action, eps=2. ** -13):
+    """Heightmap contact pre-check of ``action`` BEFORE stepping (the
+    map analogue of Simulator._drop's contact count, simulator.py:337-341):
+    -> (contact cells [E] int32, octant mask [E] int32, supported [E] bool)."""
+    views, flat = self._as_action(action)
+    return capi.contact_precheck(self.obs.walls, self.obs.rocks, views, flat, eps=eps)
+
   def check_actions(self):
     """Synchronises and raises like env.py:237 if any action of the steps so far
     was outside the action space (such actions place nothing valid: NaN pose)."""

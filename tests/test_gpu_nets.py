@@ -109,7 +109,7 @@ def test_tensor_core_path_matches_oracle_and_fp32_path(mods, monkeypatch, shape)
   x = rng.standard_normal((B, H, W, C)).astype('float32')
   f = rng.standard_normal((B, h, w, C)).astype('float32')
   xd, fd = torch.from_numpy(x).cuda(), torch.from_numpy(f).cuda()
-  monkeypatch.setenv('SRL_SIAM_MODE', '1')
+  monkeypatch.setenv('SRL_SIAM_MODE', '2')
   tc = nets.correlation(xd, fd).cpu().numpy().astype('float64')
   monkeypatch.setenv('SRL_SIAM_MODE', '0')
   fp = nets.correlation(xd, fd).cpu().numpy().astype('float64')
@@ -119,7 +119,7 @@ def test_tensor_core_path_matches_oracle_and_fp32_path(mods, monkeypatch, shape)
   assert np.abs(fp - want).max() <= TOL * scale
   assert np.abs(tc - fp).max() <= TOL * scale
   # second launch: the pipeline leaves no state behind
-  monkeypatch.setenv('SRL_SIAM_MODE', '1')
+  monkeypatch.setenv('SRL_SIAM_MODE', '2')
   assert np.array_equal(nets.correlation(xd, fd).cpu().numpy().astype('float64'), tc)
 
 
@@ -128,7 +128,7 @@ def test_tensor_core_path_exact_on_small_integers(mods, monkeypatch):
   tensor-core result must equal the oracle bit for bit (catches layout / descriptor
   errors that a tolerance could hide)."""
   torch, nets, capi, nets_np = mods
-  monkeypatch.setenv('SRL_SIAM_MODE', '1')
+  monkeypatch.setenv('SRL_SIAM_MODE', '2')
   rng = np.random.default_rng(1)
   for shape in [(2, 128, 128, 16, 32, 32), (1, 40, 300, 8, 9, 12), (3, 24, 24, 8, 5, 5)]:
     B, H, W, C, h, w = shape

@@ -648,3 +648,33 @@ def test_device_side_episode_draws(mods):
   env = _synthetic_env(mods, 64, steps=40, vector_rng=True, seed=2)
   env.reset()
   assert env._order.max() < 16 and env._order.shape == (64, 40)
+
+
+def test_contact_precheck_matches_oracle(mods):
+  """contact cells / octants / support verdict of the chosen
+  placements against the numpy restatement (exact: counts and integer octants)."""
+  capi = mods['capi']
+  dev = torch.device('cuda')
+  E, R_, H, W, h = 40, 3, 48, 40, 16
+  walls, rocks, _ = synth.placement_batch(12, E, R_, H, W, h)
+  q = np.float32(2.0 ** -14)
+  walls = (np.round(walls / q) * q).astype('float32')       # heights as the rasteriser leaves them
+  rocks = (np.round(rocks / q) * q).astype('float32')
+  walls[:8] = 0.                                            # flat floor: wide contact patch
+  walls[8:12, 20:, :] += np.float32(0.05)                   # a step: contacts on one side only
+  rng = np.random.default_rng(3)
+  Ph, Pw = H - h + 1, W - h + 1
+  best = np.stack([rng.integers(0, R_, E), rng.integers(0, Ph * Pw, E)], 1).astype('int64')
+  best[-1] = (R_, 0)                                        # invalid action
+  bd = torch.from_numpy(best).to(dev)
+  for eps in (0., 2.0 ** -13, 2e-3):
+    c, o, s = capi.contact_precheck(torch.from_numpy(walls).to(dev), torch.from_numpy(rocks).to(dev),
+                                    bd[:, 0], bd[:, 1], eps=eps)
+    c, o, s = c.cpu().numpy(), o.cpu().numpy(), s.cpu().numpy()
+    assert (c[-1], o[-1], bool(s[-1])) == (0, 0, False)
+    for e in range(E - 1):
+      r, a = best[e]
+      want = O.contact_precheck(walls[e], rocks[e, r], (a // Pw, a % Pw), eps=eps)
+      assert (int(c[e]), int(o[e]), bool(s[e])) == want, (eps, e)
+    assert c[:-1].min() >= 1                                # the maximum itself always touches
+  assert s[:8].all()                                        # flat floor under a convex underside

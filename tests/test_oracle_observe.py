@@ -74,3 +74,23 @@ def test_iou_and_or_rewards(observe_golden, name):
     for col, metric in ((0, 'iou'), (1, 'or')):
       r, memory[metric] = O.reward(wall, goal, GEOM['goal_z'], metric, memory[metric])
       assert r == want[col], (k, metric)
+
+
+def test_contact_precheck_known_cases():
+  """The heightmap contact pre-check on configurations with a known answer."""
+  h = 8
+  rock = np.full((h, h), 0.05, 'float32')                  # flat underside
+  wall = np.zeros((20, 20), 'float32')
+  count, mask, ok = O.contact_precheck(wall, rock, (3, 4))
+  assert (count, mask, ok) == (64, 0xff, True)             # rests on all of it
+  wall[3:7, :] = np.float32(0.02)                          # a ledge under the first rows only
+  count, mask, ok = O.contact_precheck(wall, rock, (3, 4))
+  assert count == 32 and not ok and mask == 0b00111100     # one half-plane only: tips over
+  rock2 = rock.copy()
+  rock2[0, 0] = np.float32(0.08)                           # a single spike
+  wall[:] = 0
+  assert O.contact_precheck(wall, rock2, (0, 0)) == (1, 1 << 4, False)
+  # background cells (rock <= 1e-4) never touch
+  rock3 = np.zeros((h, h), 'float32')
+  rock3[2:6, 2:6] = np.float32(0.03)
+  assert O.contact_precheck(wall, rock3, (5, 5))[0] == 16
