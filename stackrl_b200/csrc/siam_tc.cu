@@ -24,6 +24,13 @@
 // lo = value - hi (exact), and three tensor-core products hi*hi + hi*lo + lo*hi
 // are accumulated in float32 (3xTF32); a TMEM accumulator only sums the (v, c) of
 // one filter row (K = w*C), the 32-term sum over u runs in the epilogue in float32.
+// Both operands come from shared memory and N is only the filter height, so the tensor
+// core's operand reads (128 x 32 B of image per MMA), not its arithmetic, bound the
+// kernel (ncu: tensor pipe 22 % busy, its shared-memory wavefronts at 67 % of peak).  The
+// two products that share the image's hi part are therefore ONE MMA: the filter's hi and
+// lo planes are stacked along N (columns [0, N) = hi*hi, [N, 2N) = hi*lo), the image's lo
+// part multiplies the hi planes alone into columns [0, N), and the epilogue adds the two
+// column groups: 11 KB of operand reads per K step instead of 15.
 //
 // Warp roles (160 threads, one CTA = one band of output rows of one sample):
 //   warp 0        allocates TMEM, then one elected lane issues every tcgen05.mma
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcPara
   uint64_t* acc_empty = acc_full + 2;           // [2] accumulator read back
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   unsigned char* at = smem_raw + 128;
-  unsigned char* bmat = at;                                   // [2 parts][wd * Q planes][N * 16 B]
+  unsigned char* bmat = at;                                   // [wd * Q planes][hi, lo][N * 16 B]
   at += (size_t)2 * wd * Q * p.bplane;
   unsigned char* amat = at;                                   // [stages][2 parts][Q planes]
   const int stage_bytes = 2 * Q * p.plane;
@@ -193,11 +200,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcPara
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 64);
+    tmem_alloc(tmem_slot, 128);
     tmem_relinquish();
   }
   // ---- filter planes, hi and lo (all threads; resident for the whole CTA) ------------- //
-  // plane (v, q) holds f[u, v, 4q .. 4q+4) for u = 0 .. N-1 (zero rows beyond h)
+  // plane (v, q) holds f[u, v, 4q .. 4q+4) for u = 0 .. N-1 (zero rows beyond h), its lo
+  // part right behind its hi part: together they are one K-major operand of 2N rows
   for (int k = tid; k < wd * Q * N; k += kTcThreads) {
     const int u = k % N, vq = k / N;
     const int v = vq / Q, q = vq - v * Q;
@@ -206,8 +214,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcPara
       val = __ldg(reinterpret_cast<const float4*>(fs + ((size_t)u * wd + v) * p.C + 4 * q));
     const float4 hi = make_float4(tf32_hi(val.x), tf32_hi(val.y), tf32_hi(val.z), tf32_hi(val.w));
     const float4 lo = make_float4(val.x - hi.x, val.y - hi.y, val.z - hi.z, val.w - hi.w);
-    *reinterpret_cast<float4*>(bmat + (size_t)vq * p.bplane + 16 * u) = hi;
-    *reinterpret_cast<float4*>(bmat + (size_t)(wd * Q + vq) * p.bplane + 16 * u) = lo;
+    *reinterpret_cast<float4*>(bmat + (size_t)(2 * vq) * p.bplane + 16 * u) = hi;
+    *reinterpret_cast<float4*>(bmat + (size_t)(2 * vq + 1) * p.bplane + 16 * u) = lo;
   }
   for (int k = tid; k < 32 * kTileM; k += kTcThreads) ring[k] = 0.f;
   fence_proxy_async();            // generic-proxy writes of the filter -> tensor-core reads
@@ -220,35 +228,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcPara
     // =============================== MMA issuer ========================================= //
     // every lane follows the barriers (cheap, keeps the warp converged for the final
     // block barrier); one lane issues
-    const uint32_t idesc = instr_desc(N);
+    const uint32_t idesc = instr_desc(N), idesc2 = instr_desc(2 * N);
     const uint32_t a_base = smem_u32(amat), b_base = smem_u32(bmat);
-    const uint32_t b_lo = (uint32_t)(wd * Q * p.bplane);
     for (int k = 0; k < nrows; ++k) {
       const int s = k % kTcStages, b = k & 1;
       mbar_wait(full + s, (k / kTcStages) & 1);
       if (k >= 2) mbar_wait(acc_empty + b, ((k >> 1) - 1) & 1);
       tc_fence_after();
       {
-        const uint32_t d = tmem + (uint32_t)(b * 32);
+        const uint32_t d = tmem + (uint32_t)(b * 64);
         // Descriptors differ only in their start-address field (low 14 bits, 16-byte
         // units): one add per operand and MMA instead of rebuilding 64-bit words.
         const uint32_t a_hi = a_base + (uint32_t)(s * stage_bytes);
-        const uint64_t a_tmpl = smem_desc(0, p.plane, 128), b_tmpl = smem_desc(0, p.bplane, 128);
+        const uint64_t a_tmpl = smem_desc(0, p.plane, 128), b_tmpl = smem_desc(0, 2 * p.bplane, 128);
         const uint32_t a_top = (uint32_t)(a_tmpl >> 32), b_top = (uint32_t)(b_tmpl >> 32);
         const uint32_t a_mid = (uint32_t)a_tmpl, b_mid = (uint32_t)b_tmpl;   // LBO field, bits 16..29
         const uint32_t a_hi0 = a_mid | (a_hi >> 4), a_lo0 = a_mid | ((a_hi + (uint32_t)(Q * p.plane)) >> 4);
-        const uint32_t qstep = (uint32_t)(2 * p.plane) >> 4, bstep = (uint32_t)(2 * p.bplane) >> 4;
-        uint32_t bh = b_mid | (b_base >> 4), bl = b_mid | ((b_base + b_lo) >> 4);
+        const uint32_t qstep = (uint32_t)(2 * p.plane) >> 4, bstep = (uint32_t)(4 * p.bplane) >> 4;
+        uint32_t bh = b_mid | (b_base >> 4);
         uint32_t first = 0;
         for (int v = 0; v < wd; ++v) {
           uint32_t ah = a_hi0 + (uint32_t)v, al = a_lo0 + (uint32_t)v;
 #pragma unroll 2
           for (int q = 0; q < Q; q += 2) {
-            umma_tf32(d, al, a_top, bh, b_top, idesc, first);     // small terms first
-            umma_tf32(d, ah, a_top, bl, b_top, idesc, 1u);
-            umma_tf32(d, ah, a_top, bh, b_top, idesc, 1u);
+            umma_tf32(d, ah, a_top, bh, b_top, idesc2, first);    // hi * [hi | lo]
+            umma_tf32(d, al, a_top, bh, b_top, idesc, 1u);        // lo * hi
             first = 1u;
-            ah += qstep; al += qstep; bh += bstep; bl += bstep;
+            ah += qstep; al += qstep; bh += bstep;
           }
         }
         umma_commit(freeb + s);        // the stage may be overwritten
@@ -289,7 +295,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcPara
       const int quarter = warp & 3;
       const int pix = quarter * 32 + lane;
       float g[32];
-      tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 32), g);
+      {
+        const uint32_t t0 = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 64);
+        tmem_ld32(t0, g);
+        if (N == 32) {
+          float g2[32];
+          tmem_ld32(t0 + 32u, g2);
+#pragma unroll
+          for (int u = 0; u < 32; ++u) g[u] += g2[u];
+        } else {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) g[u] += g[16 + u];
+        }
+      }
       tc_fence_before();
       mbar_arrive(acc_empty + b);
       // diagonal sum: G[(r, j), u] belongs to output row r - u
@@ -317,7 +335,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcPara
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 64);
+  if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
 }  // namespace
