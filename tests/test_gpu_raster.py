@@ -678,3 +678,46 @@ def test_contact_precheck_matches_oracle(mods):
       assert (int(c[e]), int(o[e]), bool(s[e])) == want, (eps, e)
     assert c[:-1].min() >= 1                                # the maximum itself always touches
   assert s[:8].all()                                        # flat floor under a convex underside
+
+
+def test_gpu_camera_returns_the_recorded_depth_images(mods, observe_golden):
+  """Seam b2: GpuCamera.getCameraImage(width, height, viewMatrix, projectionMatrix) --
+  the call the reference's unmodified Observer makes (observer.py:252-257, 267-272) --
+  returns, bit for bit, the depth images the reference env recorded on the fake
+  backend (overhead camera first, then the eight object views)."""
+  g = observe_golden
+  name = 'test_f32_rot8'
+  order = [str(n) for n in g[name + '/urdf_order']]
+  spawn = ((0., 0., 0.375 + 0.125), (0., 0., 0., 1.))
+  geo = mods['camera'].ObserverGeometry(128, 32, 0.125 / 32, 0.375, orientation_freedom=3)
+
+  class Sim(object):
+    def __init__(self):
+      self.bodies = []
+    def scene(self):
+      return list(self.bodies)
+
+  def body(mesh, pos, quat):
+    v, t, com = (g['mesh/{}/{}'.format(mesh, k)] for k in ('verts', 'tris', 'com'))
+    rot = R.quat_matrix(quat)
+    return (v, t, rot, np.asarray(pos, dtype='float64') - rot.dot(com))
+
+  sim = Sim()
+  cam = mods['observer'].GpuCamera(sim)
+  placed = []
+  for k in range(3):
+    key = '{}/s{}'.format(name, k)
+    depths = split_depths(g, key)
+    assert len(depths) == 9
+    sim.bodies = placed + [body(order[k], *spawn)]
+    w, h, rgb, depth, seg = cam.getCameraImage(
+      width=128, height=128, viewMatrix=geo.overhead_view,
+      projectionMatrix=geo.overhead_projection)
+    assert (w, h, rgb, seg) == (128, 128, None, None)
+    assert depth.dtype == np.float32 and np.array_equal(depth, depths[0])
+    for r in range(8):
+      _, _, _, depth, _ = cam.getCameraImage(
+        width=32, height=32, viewMatrix=geo.object_view(spawn, r),
+        projectionMatrix=geo.object_projection)
+      assert np.array_equal(depth, depths[1 + r])
+    placed.append(body(order[k], g[key + '/pose_position'], g[key + '/pose_orientation']))
