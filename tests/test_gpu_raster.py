@@ -704,7 +704,10 @@ def test_gpu_camera_returns_the_recorded_depth_images(mods, observe_golden):
 
   sim = Sim()
   cam = mods['observer'].GpuCamera(sim)
-  placed = []
+  # the reference Simulator's floor (simulator.py:167-179): a 20 m x 20 m box of height 0
+  from oracle.fake_pybullet import box_mesh
+  fv, ft = box_mesh((10, 10, 0))
+  placed = [(fv, ft, np.eye(3), np.zeros(3))]
   for k in range(3):
     key = '{}/s{}'.format(name, k)
     depths = split_depths(g, key)
