@@ -39,12 +39,14 @@
 // part multiplies the hi planes alone into its own columns [64, 64 + N), and the epilogue
 // adds the three column groups: 11 KB of operand reads per K step instead of 15.
 //
-// Warp roles (160 threads, one CTA = one band of output rows of one sample):
+// Warp roles (288 threads, one CTA = one band of output rows of one sample):
 //   warp 0        allocates TMEM, then one elected lane issues every tcgen05.mma
-//   warps 1..4    (a) stage image rows: coalesced loads -> hi / lo planes, three rows
-//                 ahead of the MMAs; (b) epilogue: tcgen05.ld of a finished row tile,
-//                 diagonal accumulation into a 32-row ring in shared memory, finished
-//                 output rows to global memory.
+//   warps 1..4    epilogue: tcgen05.ld of a finished row tile, diagonal accumulation into
+//                 a 32-row ring in shared memory, finished output rows to global memory
+//   warps 5..8    stage image rows: coalesced loads -> hi / lo planes, up to three rows
+//                 ahead of the MMAs
+// (staging and epilogue in the same warps put load latency + epilogue on one critical
+// path per row: 3.7 us against 2.5 us of MMAs.)
 // Synchronisation is mbarriers only (stage full / stage free via tcgen05.commit /
 // accumulator full / accumulator empty); the two TMEM accumulators alternate.
 #include <algorithm>
@@ -58,8 +60,8 @@ namespace srl {
 
 namespace {
 
-constexpr int kTcThreads = 160;
-constexpr int kTcWorkers = 128;       // warps 1..4
+constexpr int kTcThreads = 288;
+constexpr int kTcWorkers = 128;       // warps 1..4 (epilogue) and warps 5..8 (staging)
 constexpr int kTcStages = 3;          // image rows in flight
 constexpr int kTileM = 128;           // pixels per tile (UMMA M)
 
@@ -131,6 +133,35 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
   }
+}
+// The two MMAs of one K step under ONE election: D1 (+)= A1 * B with descriptor i1,
+// D2 (+)= A2 * B with descriptor i2 (A1, A2 share the high descriptor word).
+template <bool kHalf>
+__device__ __forceinline__ void umma_pair(uint32_t d1, uint32_t d2, uint32_t a1_lo, uint32_t a2_lo,
+                                          uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t i1,
+                                          uint32_t i2, uint32_t accumulate) {
+#define SRL_UMMA_PAIR(KIND)                                                              \
+  asm volatile(                                                                          \
+      "{\n\t"                                                                            \
+      ".reg .pred p, e;\n\t"                                                             \
+      ".reg .b64 da1, da2, db;\n\t"                                                      \
+      "mov.b64 da1, {%2, %4};\n\t"                                                       \
+      "mov.b64 da2, {%3, %4};\n\t"                                                       \
+      "mov.b64 db, {%5, %6};\n\t"                                                        \
+      "elect.sync _|e, 0xffffffff;\n\t"                                                  \
+      "setp.ne.b32 p, %9, 0;\n\t"                                                        \
+      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%0], da1, db, %7, p;\n\t"             \
+      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%1], da2, db, %8, p;\n\t"             \
+      "}\n" ::"r"(d1),                                                                   \
+      "r"(d2), "r"(a1_lo), "r"(a2_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(i1), "r"(i2), \
+      "r"(accumulate)                                                                    \
+      : "memory")
+  if (kHalf) {
+    SRL_UMMA_PAIR("f16");
+  } else {
+    SRL_UMMA_PAIR("tf32");
+  }
+#undef SRL_UMMA_PAIR
 }
 // mbarrier arrive once every tcgen05.mma issued so far by the elected lane has completed
 // (elect.sync picks the same lane every time for a full mask).
@@ -221,7 +252,7 @@ struct Chunk {
 };
 
 // Largest |value| of n floats (n a multiple of 4, 16-byte aligned), over the CTA; NaNs
-// are ignored.  `red` is shared scratch of 8 floats.
+// are ignored.  `red` is shared scratch of one float per warp.
 __device__ __forceinline__ float cta_abs_max(const float* src, int n, float* red) {
   float m = 0.f;
   for (int k = threadIdx.x; k < n / 4; k += kTcThreads) {
@@ -261,9 +292,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcPara
   uint64_t* acc_full = bars + 2 * kTcStages;    // [2] accumulator written
   uint64_t* acc_empty = acc_full + 2;           // [2] accumulator read back
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* red = reinterpret_cast<float*>(tmem_slot + 2);        // [8] reduction scratch
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);        // [16] reduction scratch
   constexpr int kCw = kHalf ? 8 : 4;                           // channels per 16-byte chunk
-  unsigned char* at = smem_raw + 128;
+  unsigned char* at = smem_raw + 256;
   unsigned char* bmat = at;                                   // [wd * Q planes][hi, lo][N * 16 B]
   at += (size_t)2 * wd * Q * p.bplane;
   unsigned char* amat = at;                                   // [stages][2 parts][Q planes]
@@ -332,16 +363,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcPara
     // MMAs this small (16-32 clocks of tensor work) the single issuing warp, not the tensor
     // core, sets the pace.  redux.sync returns in a uniform register; the descriptors are
     // rebuilt from the (uniform) loop counters instead of being carried in registers.
-    const uint32_t idesc = __reduce_or_sync(0xffffffffu, instr_desc<kHalf>(N));
-    const uint32_t idesc2 = __reduce_or_sync(0xffffffffu, instr_desc<kHalf>(2 * N));
-    const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);
+    auto uni = [](uint32_t v) { return __reduce_or_sync(0xffffffffu, v); };
+    const uint32_t idesc = uni(instr_desc<kHalf>(N)), idesc2 = uni(instr_desc<kHalf>(2 * N));
+    const uint32_t tmem_u = uni(tmem);
     const uint32_t a_base = smem_u32(amat), b_base = smem_u32(bmat);
     const uint64_t a_tmpl = smem_desc(0, p.plane, 128), b_tmpl = smem_desc(0, 2 * p.bplane, 128);
-    const uint32_t a_top = (uint32_t)(a_tmpl >> 32), b_top = (uint32_t)(b_tmpl >> 32);
+    const uint32_t a_top = uni((uint32_t)(a_tmpl >> 32)), b_top = uni((uint32_t)(b_tmpl >> 32));
     const uint32_t a_mid = (uint32_t)a_tmpl, b_mid = (uint32_t)b_tmpl;     // LBO field, bits 16..29
-    const uint32_t qstep = (uint32_t)(2 * p.plane) >> 4, bstep = (uint32_t)(4 * p.bplane) >> 4;
-    const uint32_t lo_off = (uint32_t)(Q * p.plane) >> 4;
-    const uint32_t bh0 = b_mid | (b_base >> 4);
+    const uint32_t qstep = uni((uint32_t)(2 * p.plane) >> 4), bstep = uni((uint32_t)(4 * p.bplane) >> 4);
+    const uint32_t lo_off = uni((uint32_t)(Q * p.plane) >> 4);
+    const uint32_t bh0 = uni(b_mid | (b_base >> 4));
+    const uint32_t a_first = uni(a_mid | (a_base >> 4)), a_stage = uni((uint32_t)stage_bytes >> 4);
     const int Q2 = Q >> 1;
     for (int k = 0; k < nrows; ++k) {
       const int s = k % kTcStages, b = k & 1;
@@ -353,14 +385,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcPara
         // [64, 64 + N) -- MMAs into different columns do not wait for each other
         const uint32_t d = tmem_u + (uint32_t)(b * 128);
         // Descriptors differ only in their start-address field (low 14 bits, 16-byte units).
-        const uint32_t a_hi0 = a_mid | ((a_base + (uint32_t)(s * stage_bytes)) >> 4);
-        for (int v = 0; v < wd; ++v) {
+        const uint32_t a_hi0 = a_first + (uint32_t)s * a_stage;
+        if (Q2 == 1) {
+          // one K step per tap: tap v moves the image operand by one 16-byte row and the
+          // filter operand by one pair of planes
+#pragma unroll 4
+          for (int v = 0; v < wd; ++v) {
+            const uint32_t ah = a_hi0 + (uint32_t)v, bh = bh0 + (uint32_t)v * bstep;
+            umma_pair<kHalf>(d, d + 64u, ah, ah + lo_off, a_top, bh, b_top, idesc2, idesc,
+                             (uint32_t)v);
+          }
+        } else {
+          for (int v = 0; v < wd; ++v) {
 #pragma unroll 2
-          for (int q2 = 0; q2 < Q2; ++q2) {
-            const uint32_t ah = a_hi0 + (uint32_t)v + (uint32_t)q2 * qstep;
-            const uint32_t bh = bh0 + (uint32_t)(v * Q2 + q2) * bstep;
-            umma<kHalf>(d, ah, a_top, bh, b_top, idesc2, (uint32_t)(v | q2));            // hi * [hi | lo]
-            umma<kHalf>(d + 64u, ah + lo_off, a_top, bh, b_top, idesc, (uint32_t)(v | q2));  // lo * hi
+            for (int q2 = 0; q2 < Q2; ++q2) {
+              const uint32_t ah = a_hi0 + (uint32_t)v + (uint32_t)q2 * qstep;
+              const uint32_t bh = bh0 + (uint32_t)(v * Q2 + q2) * bstep;
+              umma_pair<kHalf>(d, d + 64u, ah, ah + lo_off, a_top, bh, b_top, idesc2, idesc,
+                               (uint32_t)(v | q2));
+            }
           }
         }
         umma_commit(freeb + s);        // the stage may be overwritten
@@ -369,8 +412,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcPara
       __syncwarp();
     }
   } else {
-    // =============================== workers ============================================= //
-    const int wt = tid - 32;                      // 0 .. 127
+    // ====================== workers: warps 1..4 epilogue, warps 5..8 staging ============== //
+    const bool stager = warp >= 5;
+    const int wt = stager ? tid - 160 : tid - 32;          // 0 .. 127 within the group
     const int npx = p.npx;
     auto stage_row = [&](int k) {
       const int s = k % kTcStages;
@@ -451,9 +495,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) siam_tc_kernel(const SiamTcPara
       }
       named_bar_sync(1, kTcWorkers);
     };
-    for (int k = 0; k < nrows + 2; ++k) {
-      if (k < nrows) stage_row(k);
-      if (k >= 2) epilogue(k - 2);
+    if (stager) {
+      for (int k = 0; k < nrows; ++k) stage_row(k);
+    } else {
+      for (int k = 0; k < nrows; ++k) epilogue(k);
     }
   }
   tc_fence_before();
@@ -486,7 +531,7 @@ int siam_correlation_tc(const float* x, const float* f, float* out, int B, int H
   p.plane = 16 * (p.npx | 1);                  // odd number of 16-byte slots: no bank conflicts
   p.bplane = 16 * p.N;
   p.jblocks = (Pw + kTileM - 1) / kTileM;
-  const size_t smem = 128 + (size_t)2 * wd * p.Q * p.bplane +
+  const size_t smem = 256 + (size_t)2 * wd * p.Q * p.bplane +
                       (size_t)kTcStages * 2 * p.Q * p.plane + (size_t)32 * kTileM * 4;
   if (smem > 227 * 1024 || p.plane >= (1 << 18) || p.bplane >= (1 << 18)) return SRL_E_UNSUPPORTED;
   // bands of output rows: enough CTAs for every SM, not more rows re-staged than needed
