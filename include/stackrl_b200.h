@@ -277,7 +277,9 @@ SRL_API int srl_raster_ex(const float* verts, const int32_t* tris,
  * depth_state [njobs, rows, cols] f32 is the GL depth image kept between calls.
  * only_last == 0: draw every instance (like srl_raster_ex) and leave the depth image
  * in depth_state; only_last != 0: start from depth_state and draw ONLY the last
- * instance of each job.  The depth image is a minimum over triangles, so the result
+ * instance of each job; only_last == 2 additionally promises that `out` still holds
+ * the image this function wrote for the current depth_state: only the pixels the new
+ * instance changes are then read and written (in place).  The depth image is a minimum over triangles, so the result
  * is bit-identical to re-drawing all instances (the reference re-renders the whole
  * scene every step, observer.py:252-257, because pybullet's renderer has no such
  * mode); the wall image of a 30-rock episode costs one rock per step instead of 15 on

@@ -349,7 +349,8 @@ def raster(verts, tris, instances, jobs, rows, cols, mode, far_plane=1000., out=
   ``max_cached_verts`` sizes the shared-memory vertex cache (srl_raster_ex).
   ``depth_state`` [njobs, rows, cols] float32: the GL depth image kept between calls
   (srl_raster_incremental); with ``only_last`` only the last instance of every job
-  is drawn onto it -- same bits as re-drawing the whole scene."""
+  is drawn onto it -- same bits as re-drawing the whole scene; ``only_last=2``: ``out``
+  still holds the image of ``depth_state`` and is updated in place."""
   dev = verts.device
   def as_bytes(a, dtype):
     if isinstance(a, torch.Tensor):
@@ -377,7 +378,7 @@ def raster(verts, tris, instances, jobs, rows, cols, mode, far_plane=1000., out=
       _check(lib.srl_raster_incremental(
         *args[:4], _opt(inst_counts, torch.int32, 'inst_counts'),
         _out(depth_state, torch.float32, (njobs, rows, cols), verts, 'depth_state'),
-        int(bool(only_last)), args[4], int(njobs), int(rows), int(cols), int(mode),
+        int(only_last), args[4], int(njobs), int(rows), int(cols), int(mode),
         float(far_plane), int(max_cached_verts), _stream()))
     else:
       _check(lib.srl_raster_ex(*args[:4], _opt(inst_counts, torch.int32, 'inst_counts'), args[4],

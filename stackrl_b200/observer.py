@@ -513,7 +513,8 @@ class BatchedObserver(object):
     last = bool(appended) and self._wall_depth_valid
     capi.raster(self._verts, self._tris, self._inst, self._wall_jobs, g.overhead_h,
                 g.overhead_w, capi.RASTER_WALL, far_plane=FAR, out=self.walls,
-                inst_counts=self.counts, depth_state=self._wall_depth, only_last=last,
+                inst_counts=self.counts, depth_state=self._wall_depth,
+                only_last=2 if last else 0,       # walls still holds the kept image
                 max_cached_verts=max(256, self._max_verts) if last else
                 min(2048, max(256, self._max_verts * self.cap)))
     self._wall_depth_valid = True
