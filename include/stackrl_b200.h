@@ -440,7 +440,10 @@ SRL_API int srl_rewards_f32(const srl_env_state* host_state, const float* walls,
 /* a14 + a11/a12 in one pass over the wall and goal maps: srl_pack_obs and
  * srl_rewards_f32 of the same step (what StackEnv.step returns, env.py:255-264) --
  * the observation is packed while the reward sums are taken, so the maps are read
- * once.  Arguments as in those two; obs_scale is srl_pack_obs's `scale`. */
+ * once.  Arguments as in those two; obs_scale is srl_pack_obs's `scale`.  `goals` may be
+ * NULL when `rects` is given: the goal map of environment e then IS the rectangle
+ * rects[e] at height goal_z[e] (Rewarder._reset_goal, rewarder.py:252-258 -- what
+ * srl_fill_goals_f32 writes) and is not read from memory. */
 SRL_API int srl_pack_rewards_f32(const srl_env_state* host_state, const float* walls,
                                  const float* goals, const float* rocks, const float* goal_z,
                                  const int32_t* rects, void* wall_goal, void* rock,

@@ -735,7 +735,9 @@ def rewards(state, walls, goals, goal_z, rects, metric, scale, pixel, pmax, pexp
 
 def pack_rewards(state, walls, goals, rocks, goal_z, rects, metric, scale, pixel, pmax, pexp,
                  oexp, dtype='float32', obs_scale=1., repeat_wall=False, out=None):
-  """pack_obs + rewards of one step in one launch -> (wall_goal, rock, reward)."""
+  """pack_obs + rewards of one step in one launch -> (wall_goal, rock, reward).
+  ``goals=None``: the goal maps are the rectangles ``rects`` at ``goal_z`` (what
+  ``fill_goals`` writes) and are not read from memory."""
   E, R, H, W, h = _batch_dims(walls, rocks)
   dev = walls.device
   m = METRICS[metric]
@@ -751,7 +753,8 @@ def pack_rewards(state, walls, goals, rocks, goal_z, rects, metric, scale, pixel
   reward = torch.empty((E, 4) if m == 4 else (E,), dtype=torch.float32, device=dev)
   with torch.cuda.device(dev):
     _check(lib.srl_pack_rewards_f32(
-      state.ref(), _dev(walls, torch.float32, 'walls'), _dev(goals, torch.float32, 'goals'),
+      state.ref(), _dev(walls, torch.float32, 'walls'),
+      _P(None) if goals is None else _dev(goals, torch.float32, 'goals'),
       _dev(rocks, torch.float32, 'rocks'), _dev(goal_z, torch.float32, 'goal_z'),
       _dev(rects, torch.int32, 'rects'), _P(wall_goal.data_ptr()), _P(rock.data_ptr()),
       _P(reward.data_ptr()), _P(None), R, H, W, h, 0 if tdt == torch.float32 else 1,

@@ -206,6 +206,28 @@ __device__ __forceinline__ void stage_bytes(void* dst, const void* src, size_t n
   }
 }
 
+// Copy `count` elements with the destination at the source's 16-byte phase
+// (dst = base16 + (src & 15)): head and tail element-wise, the body as 16-byte vectors
+// whatever the alignment of src (a [E, P] map with odd P starts 4, 8 or 12 bytes off
+// for three environments in four).  base16 must have 16 spare bytes.  Returns dst.
+template <typename T>
+__device__ __forceinline__ T* stage_phased(void* base16, const T* src, size_t count, int tid,
+                                           int nthreads) {
+  const int phase = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+  T* dst = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(base16) + phase);
+  size_t head = (size_t)((16 - phase) & 15) / sizeof(T);
+  if (head > count) head = count;
+  const size_t n4 = ((count - head) * sizeof(T)) >> 4;
+  const size_t body = n4 * (16 / sizeof(T));
+  for (size_t k = tid; k < head; k += nthreads) dst[k] = src[k];
+  const int4* s4 = reinterpret_cast<const int4*>(src + head);
+  int4* d4 = reinterpret_cast<int4*>(dst + head);
+#pragma unroll 4
+  for (int k = tid; k < (int)n4; k += nthreads) d4[k] = __ldg(s4 + k);
+  for (size_t k = head + body + tid; k < count; k += nthreads) dst[k] = src[k];
+  return dst;
+}
+
 struct MaskSelectParams {
   int staged;                  // inputs + score maps of one environment fit shared memory
   int R, H, W, h, Ph, Pw, minorder;
@@ -559,8 +581,7 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
     // packed word; only the score maps are staged in shared memory.
     for (int k = tid; k < H * g_nW + R * g_ng; k += kSelThreads) below[k] = 0u;
     if (q.stage_values)
-      stage_bytes(vals, values + (size_t)e * R * P, (size_t)R * P * sizeof(V), tid,
-                  kSelThreads);
+      vals = stage_phased(vals, values + (size_t)e * R * P, (size_t)R * P, tid, kSelThreads);
     if (tid < 32) s_cmax[tid] = 0;
     __syncthreads();
     const In* wsrc = walls + (size_t)e * H * W;
@@ -809,10 +830,10 @@ int launch_mask_select(const V* values, const In* walls, const In* goals, const 
   const size_t packed_base =
       4 * ((size_t)H * q.nW + (size_t)R * q.ng + (size_t)H * q.Pw) + 2 * (size_t)rch * P;
   // stage the score maps while that keeps >= 4 CTAs per SM
-  q.stage_values = !q.vec4 || packed_base + 16 + pad16((size_t)R * P * sizeof(V)) <= 52 * 1024;
+  q.stage_values = !q.vec4 || packed_base + 32 + pad16((size_t)R * P * sizeof(V)) <= 52 * 1024;
   const size_t packed_smem =
       packed_base + (!q.vec4 ? staged
-                             : (q.stage_values ? 16 + pad16((size_t)R * P * sizeof(V)) : 32));
+                             : (q.stage_values ? 32 + pad16((size_t)R * P * sizeof(V)) : 32));
   if (pow2 && packed_smem <= 200 * 1024 && minorder <= 1) {     // one CTA per SM at worst
 #define SRL_MSP_LAUNCH(MM, NGG)                                                            \
   do {                                                                                     \

@@ -312,8 +312,10 @@ class BatchedStackEnv(object):
   def _reward_and_pack(self):
     """Packed observation + reward of the step in one launch (a14 + a11/a12)."""
     g = self.obs.geo
+    # self.goals is always fill_goals(self._rects_d, self._goal_z_d): the kernel takes the
+    # rectangle instead of reading the map
     wall_goal, rock, r = capi.pack_rewards(
-      self.obs.state, self.obs.walls, self.goals, self.obs.rocks, self._goal_z_d, self._rects_d,
+      self.obs.state, self.obs.walls, None, self.obs.rocks, self._goal_z_d, self._rects_d,
       self.metric, self.scale, (g.pixel_h, g.pixel_w), self._pmax, self._pexp, self._oexp,
       dtype=self._dtype, obs_scale=self._scale, repeat_wall=self.R > 1)
     if self.metric == 'all':

@@ -650,6 +650,29 @@ def test_device_side_episode_draws(mods):
   assert env._order.max() < 16 and env._order.shape == (64, 40)
 
 
+@pytest.mark.parametrize('dtype,freedom', [('float32', 0), ('uint8', 0), ('float32', 2)])
+def test_pack_rewards_goal_rectangle_equals_goal_plane(mods, dtype, freedom):
+  """srl_pack_rewards_f32 with goals == NULL derives the goal map from the goal
+  limits (what the environment step does): same observation and rewards, bit for bit,
+  as reading the filled goal plane."""
+  from stackrl_b200 import capi
+  outs = []
+  for plane in (False, True):
+    env = _synthetic_env(mods, 12, dtype=dtype, freedom=freedom, steps=4, rewarder='all')
+    env.reset()
+    for _ in range(2):
+      env.step(env.sample())
+    g = env.obs.geo
+    wall_goal, rock, r = capi.pack_rewards(
+      env.obs.state, env.obs.walls, env.goals if plane else None, env.obs.rocks, env._goal_z_d,
+      env._rects_d, env.metric, env.scale, (g.pixel_h, g.pixel_w), env._pmax, env._pexp,
+      env._oexp, dtype=env._dtype, obs_scale=env._scale, repeat_wall=env.R > 1)
+    outs.append((wall_goal, rock, r))
+  for a, b in zip(*outs):
+    assert torch.equal(a, b)
+  assert outs[0][0][..., 1].any()
+
+
 def test_contact_precheck_matches_oracle(mods):
   """contact cells / octants / support verdict of the chosen
   placements against the numpy restatement (exact: counts and integer octants)."""

@@ -112,6 +112,32 @@ def test_placement_scorer_batched(B, shape, goal, minorder):
     assert np.array_equal(shown[e].reshape(R, -1), v)
 
 
+@pytest.mark.parametrize('shape', [(37, 64, 64, 16), (5, 32, 48, 16), (9, 44, 36, 16),
+                                   (3, 96, 80, 16)])
+@pytest.mark.parametrize('minorder', [0, 1])
+@pytest.mark.parametrize('dtype', ['float32', 'uint8'])
+def test_single_view_maps_off_a_16_byte_boundary(B, shape, minorder, dtype):
+  """R == 1 with odd P: the score map of three environments in four starts 4, 8 or 12
+  bytes off a 16-byte boundary (staged at the source's phase): actions and value maps
+  equal the oracle's for environments of every phase."""
+  from stackrl_b200 import capi
+  E, H, W, h = shape
+  walls, rocks, _ = synth.placement_batch(41, E, 1, H, W, h)
+  goals = synth.goals(42, E, H, W)
+  dev = torch.device('cuda')
+  if dtype == 'uint8':
+    walls, goals, rocks = (synth.to_dtype(x, 'uint8') for x in (walls, goals, rocks))
+  wd, gd, rd = (torch.from_numpy(x).to(dev) for x in (walls, goals, rocks))
+  run = capi.maxplus_u8 if dtype == 'uint8' else capi.maxplus_f32
+  values = run(wd, rd, capi.goal_level(gd))
+  got = capi.mask_select(values, wd, gd, rd, minorder=minorder)
+  for e in list(range(min(E, 4))) + [E - 1]:
+    obs = (np.stack([walls[e], goals[e]], -1), rocks[e, 0][..., None])
+    a, v = S.baseline_call(obs, goal=True, minorder=minorder)
+    assert int(got[0][e, 0]) == a
+    assert np.array_equal(got[1][e, 0].cpu().numpy().ravel(), np.asarray(v).ravel())
+
+
 def test_select_first_index_ties():
   """All-equal scores: np.argmin's first index, on a goal mask whose first
   member is not position 0."""
