@@ -324,6 +324,7 @@ class HostPipeline(object):
     self.actions = torch.empty((self.E, self.R), dtype=torch.int64).pin_memory()
     self.best = torch.empty((self.E, 2), dtype=torch.int64).pin_memory()
     self.copy_stream = torch.cuda.Stream(device=self.dev)
+    self.back_stream = torch.cuda.Stream(device=self.dev)
     self.graph = None
     self.d2h_bytes = (self.actions.numel() + self.best.numel()) * 8
 
@@ -351,6 +352,7 @@ class HostPipeline(object):
         ev = torch.cuda.Event()
         ev.record(self.copy_stream)
         ready.append(ev)
+    self._keep = []          # chunk outputs stay alive until their device->host copies ran
     for k, ((lo, hi), ev, dev_in) in enumerate(zip(self.bounds, ready, self.dev_in)):
       main.wait_event(ev)
       if self.rects:
@@ -358,8 +360,16 @@ class HostPipeline(object):
         out = self.scorer(dev_in['walls'], goals, dev_in['rocks'], level=dev_in['levels'])
       else:
         out = self.scorer(dev_in['walls'], dev_in['goals'], dev_in['rocks'])
-      self.actions[lo:hi].copy_(out['actions'], non_blocking=True)
-      self.best[lo:hi].copy_(out['best'], non_blocking=True)
+      # results travel back on their own stream: a device->host copy queued on `main`
+      # would hold the next chunk's kernels behind the copy engine's round trip
+      done = torch.cuda.Event()
+      done.record(main)
+      self.back_stream.wait_event(done)
+      with torch.cuda.stream(self.back_stream):
+        self.actions[lo:hi].copy_(out['actions'], non_blocking=True)
+        self.best[lo:hi].copy_(out['best'], non_blocking=True)
+      self._keep.append(out)
+    main.wait_stream(self.back_stream)
 
   def capture(self):
     """Record one step (every copy and kernel of ``run``) into a CUDA graph; later

@@ -33,7 +33,7 @@ def timed(fn, n=30):
 
 for dtype_name, rects in (('float32', True), ('uint8', False)):
   dt = {'float32': torch.float32, 'uint8': torch.uint8}[dtype_name]
-  for chunks in (1, 2, 4, 8, 16):
+  for chunks in (1, 2, 3, 4, 6, 8):
     scorer = baselines.PlacementScorer('height')
     pipe = baselines.HostPipeline(scorer, E, R, H, W, h, chunks=chunks, device=dev, dtype=dt,
                                   goal_rects=rects)
