@@ -588,12 +588,23 @@ def run_c4(args, su):
   env, policy = make('float32')
   env.reset()
   state = {'left': L}
+  # The public call of a rollout: BatchedStackEnv.capture(policy) records policy + step
+  # as ONE CUDA graph and step_policy() replays it (--eager: the same chain launch by
+  # launch).  Resets (every L steps, inside the timed region) are eager launches.
+  for _ in range(2):
+    env.step(policy(env))
+    state['left'] -= 1
+  if not args.eager:
+    env.capture(policy)
 
   def step(k, timed):
     if state['left'] == 0:
       env.reset()
       state['left'] = L
-    env.step(policy(env))
+    if args.eager:
+      env.step(policy(env))
+    else:
+      env.step_policy()
     state['left'] -= 1
   warmup = max(args.warmup, 3)
   elapsed_ms, sampler, clocks_how = timed_region(su, step, args.steps, warmup)
@@ -639,12 +650,15 @@ def run_c4(args, su):
   act_pin.copy_(policy(env))
   torch.cuda.synchronize()
   obs_pin = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in env.observation]
-  def e2e_loop(with_obs):
+  def e2e_loop(with_obs, steps=None):
+    timed = steps is None
+    if timed:
+      e2e_loop(with_obs, 3)       # untimed warm-up of this exact loop (allocator, pinned copies)
     env.reset()
     su.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(e2e_steps):
+    for _ in range(e2e_steps if timed else steps):
       action = act_pin.to(dev, non_blocking=True)           # the agent's action, from the host
       o, r, t_ = env.step(action)
       rew_pin.copy_(r, non_blocking=True)
@@ -671,7 +685,7 @@ def run_c4(args, su):
   peaks, peak_src = measured_peaks()
   V, F = v.shape[1], len(t)
   alg = {'packed_observation_write': 4 * (2 * H * H + h * h),
-         'reward_read': 8 * H * H,
+         'reward_read': 4 * H * H,        # the wall map (the goal is its rectangle)
          'maps_write': 4 * (H * H + h * h),
          'mesh_read': int(n_inst * (12 * V + 12 * F) + 12 * V + 12 * F)}
   alg_bytes = sum(alg.values())
@@ -703,6 +717,8 @@ def run_c4(args, su):
       'bytes_per_obs': alg, 'peak_source': peak_src,
       'breakdown_ms': breakdown, 'mean_placed_rocks': n_inst},
     'notes': {'envs_per_gpu': E, 'resets_in_timed_region': args.steps // L,
+              'launch': 'eager' if args.eager else 'one CUDA graph per step (capture(policy) + '
+                                                   'step_policy())',
               'rng': 'vector_rng=True (episode draws on the device, srl_env_draw)',
               'rocks': '{} synthetic rocks of {} triangles / {} vertices'.format(w['bank'], F, V)},
   }
@@ -1031,6 +1047,8 @@ def main():
   ap.add_argument('--envs', type=int, default=0,
                   help='override the TOTAL number of environments / walls of c4 / c5')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--eager', action='store_true',
+                  help='c4: launch the step kernel by kernel instead of replaying its CUDA graph')
   ap.add_argument('--no-extra', action='store_true')
   ap.add_argument('--no-bind', action='store_true', help='do not pin ranks to core slices')
   ap.add_argument('--fused', action='store_true',
