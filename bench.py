@@ -630,7 +630,7 @@ def run_c4(args, su):
     obs.observe_walls(True)
     mark('wall raster (the appended rock onto the kept depth image)')
     obs.observe_rocks()
-    mark('rock raster')
+    mark('rock images (per-bank table, rasterised once)')
     env._reward_and_pack()
     mark('reward + pack')
     env._advance_host()
@@ -684,10 +684,14 @@ def run_c4(args, su):
   value = total_E / (ms_per_step * 1e-3)
   peaks, peak_src = measured_peaks()
   V, F = v.shape[1], len(t)
+  # what one observation has to move at least: the packed observation out, the wall map in
+  # for the reward sums, the appended rock's mesh, the spawned rock's image in (per-bank
+  # table) and out (planar map for the scorer); the pixels the rock changes in the kept
+  # wall image are not counted
   alg = {'packed_observation_write': 4 * (2 * H * H + h * h),
-         'reward_read': 4 * H * H,        # the wall map (the goal is its rectangle)
-         'maps_write': 4 * (H * H + h * h),
-         'mesh_read': int(n_inst * (12 * V + 12 * F) + 12 * V + 12 * F)}
+         'reward_read': 4 * H * H,
+         'rock_image_read_write': 8 * h * h,
+         'mesh_read': 12 * V + 12 * F}
   alg_bytes = sum(alg.values())
   step_s = sum(breakdown.values()) * 1e-3
   obs_s = (step_s - breakdown['policy (max-plus + goal mask + arg-min)'] * 1e-3)
@@ -707,7 +711,7 @@ def run_c4(args, su):
     'gpu_launches': 7 * args.steps,
     'kernels_per_step': ['maxplus_stream_kernel', 'mask_select_packed_kernel',
                          'place_poses_kernel', 'env_advance_kernel', 'raster_kernel (walls)',
-                         'raster_kernel (rocks)', 'pack_rewards_kernel'],
+                         'gather_rows_kernel (rock images)', 'pack_rewards_kernel'],
     'roofline': {
       'bound': 'hbm', 'kernel': 'env observation chain (pose, append, wall raster, rock '
                                 'raster, reward, pack) of one mid-episode step',

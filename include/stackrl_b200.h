@@ -459,6 +459,16 @@ SRL_API int srl_quantise_planes_u8(const float* walls, const float* goals,
                                    uint8_t* rocks8, int E, int R, int H, int W, int h,
                                    float scale, srl_stream_t stream);
 
+/* Rock images by mesh id: out[e, :] = table[index[e], :] (rows of row_floats float32).
+ * The image Observer.__call__ renders of the spawned rock (observer.py:262-293) depends
+ * only on the mesh and the fixed spawn pose / orientation list, so a batched environment
+ * rasterises every mesh of its bank once (srl_raster) and a step fetches the images of the
+ * rocks spawned by srl_env_advance (state->current) with this call.  An index outside
+ * [0, table_rows) fills the row with NaN. */
+SRL_API int srl_gather_rows_f32(const float* table, const int32_t* index, float* out,
+                                int rows_out, int row_floats, int table_rows,
+                                srl_stream_t stream);
+
 /* ---- measurement helpers (not part of the reference's surface) --------------
  * Issue-rate micro-benchmark used to fix the FP32 roofline of the max-plus
  * kernel: runs `iters` dependent rounds of (add, max) cells on every lane of a

@@ -80,6 +80,7 @@ _SIGNATURES = {
   'srl_pack_rewards_f32': (_I, [_P] * 10 + [_I, _I, _I, _I, _I, _c.c_float, _I, _I] +
                            [_c.c_double] * 6 + [_P]),
   'srl_quantise_planes_u8': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_float, _P]),
+  'srl_gather_rows_f32': (_I, [_P, _P, _P, _I, _I, _I, _P]),
   'srl_microbench_addmax': (_I, [_I, _I, _c.POINTER(_c.c_double)]),
   'srl_microbench_fma': (_I, [_I, _I, _c.POINTER(_c.c_double)]),
 }
@@ -762,6 +763,20 @@ def pack_rewards(state, walls, goals, rocks, goal_z, rects, metric, scale, pixel
       float(pixel[1]), float(pmax), -1.0 if pexp is None else float(pexp),
       -1.0 if oexp is None else float(oexp), _stream()))
   return wall_goal, rock, reward
+
+
+def gather_rows(table, index, out):
+  """out[e] = table[index[e]] (float32 rows; int32 index on the device): the cached image
+  of the rock every environment spawned."""
+  n = int(table.shape[0])
+  row = table[0].numel()
+  E = int(index.numel())
+  _same_device(table, index, out)
+  with torch.cuda.device(table.device):
+    _check(lib.srl_gather_rows_f32(
+      _dev(table, torch.float32, 'table'), _dev(index, torch.int32, 'index'),
+      _out(out, torch.float32, (E, row), table), E, row, n, _stream()))
+  return out
 
 
 def quantise_planes(walls, goals, rocks, scale, out=None):

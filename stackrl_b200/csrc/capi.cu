@@ -325,6 +325,12 @@ int srl_quantise_planes_u8(const float* walls, const float* goals, const float* 
                                  scale, (cudaStream_t)stream);
 }
 
+int srl_gather_rows_f32(const float* table, const int32_t* index, float* out, int rows_out,
+                        int row_floats, int table_rows, srl_stream_t stream) {
+  return srl::gather_rows_f32(table, index, out, rows_out, row_floats, table_rows,
+                              (cudaStream_t)stream);
+}
+
 int srl_siam_correlation_grad_f32(const float* x, const float* w, const float* grad_out,
                                   float* grad_x, float* grad_w, int B, int H, int W, int C,
                                   int h, int wd, srl_stream_t stream) {

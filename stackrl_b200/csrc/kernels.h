@@ -118,6 +118,8 @@ int pack_rewards_f32(const srl_env_state* st, const float* walls, const float* g
                      int W, int h, int dtype_code, float obs_scale, int repeat_wall, int metric,
                      double scale, double pixel_h, double pixel_w, double pmax, double pexp,
                      double oexp, cudaStream_t stream);
+int gather_rows_f32(const float* table, const int32_t* index, float* out, int rows_out,
+                    int row_floats, int table_rows, cudaStream_t stream);
 int quantise_planes_u8(const float* walls, const float* goals, const float* rocks,
                        uint8_t* walls8, uint8_t* goals8, uint8_t* rocks8, int E, int R, int H,
                        int W, int h, float scale, cudaStream_t stream);

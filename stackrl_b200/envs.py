@@ -43,14 +43,16 @@ class BatchedStackEnv(object):
                observable_size_ratio=4, resolution_factor=5, max_z=0.375,
                rewarder=None, goal_size_ratio=.25, reward_scale=1., reward_params=None,
                orientation_freedom=0, dtype='float32', settle=None, seed=None,
-               device=None, vector_rng=False):
+               device=None, vector_rng=False, rock_cache_bytes=1 << 30):
     """Arguments follow StackEnv (env.py:28-50); ``bank`` is the MeshBank of
     candidate rocks (the reference's ``urdfs`` list), ``orientation_freedom``
     the TestStackEnv option (env.py:443-463), ``settle`` the physics hook:
     ``settle(mesh_ids [E], positions [E,3], quaternions [E,4]) -> (positions,
     quaternions)`` of the new rocks at rest, optionally followed by a third item,
     the rest poses [E, n_placed, 7] of ALL placed rocks including the new one
-    (Simulator.positions re-reads every body, simulator.py:86-92)."""
+    (Simulator.positions re-reads every body, simulator.py:86-92).  ``rock_cache_bytes``:
+    see BatchedObserver (the spawned rocks' images are fetched from a per-bank table
+    rasterised once, when it fits)."""
     if dtype not in self.metadata['dtypes']:
       raise ValueError('Invalid value {} for argument dtype.'.format(dtype))
     if len(bank) == 0:
@@ -70,7 +72,7 @@ class BatchedStackEnv(object):
       bank, self.E, self._length, overhead_resolution, object_resolution,
       object_max_dimension / object_resolution, max_z, orientation_freedom,
       spawn_pose=((0., 0., max_z + object_max_dimension), (0., 0., 0., 1.)), device=device,
-      episode_length=self._length)
+      episode_length=self._length, rock_cache_bytes=rock_cache_bytes)
     self.dev = self.obs.dev
     g = self.obs.geo
     self.R = g.n_orientations

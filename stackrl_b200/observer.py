@@ -360,7 +360,12 @@ class BatchedObserver(object):
 
   def __init__(self, bank, envs, capacity, overhead_resolution=128, object_resolution=32,
                pixel_size=0.125 / 32, max_z=0.375, orientation_freedom=0,
-               spawn_pose=None, device=None, episode_length=None):
+               spawn_pose=None, device=None, episode_length=None,
+               rock_cache_bytes=1 << 30):
+    """``rock_cache_bytes``: the image of a spawned rock depends only on its mesh (fixed
+    spawn pose and orientation list), so when the images of the whole bank fit this many
+    bytes they are rasterised once and a step fetches them by mesh id (0: rasterise the
+    spawned rocks every step)."""
     self.geo = g = camera.ObserverGeometry(
       overhead_resolution, object_resolution, pixel_size, max_z, orientation_freedom)
     self.bank = bank
@@ -417,6 +422,8 @@ class BatchedObserver(object):
     self._wall_depth = torch.ones((E, g.overhead_h, g.overhead_w), dtype=torch.float32,
                                   device=self.dev)
     self._wall_depth_valid = False
+    self._rock_cache = None
+    self._cache_rocks = 0 < n * R * g.object_h * g.object_w * 4 <= int(rock_cache_bytes)
 
   # -- instance rows -------------------------------------------------------------- #
   def _rows(self, mesh_ids, positions, quaternions):
@@ -525,6 +532,11 @@ class BatchedObserver(object):
     ``rocks`` (observer.py:262-293).  ``mesh_ids`` (host array) replaces the
     device-side episode state with explicit meshes (set-up paths)."""
     g = self.geo
+    if mesh_ids is None and self._cache_rocks:
+      if self._rock_cache is None:
+        self._rock_cache = self._render_bank()
+      capi.gather_rows(self._rock_cache, self.state.current, self.rocks.view(self.E, -1))
+      return self.rocks
     if mesh_ids is not None:
       ids = torch.as_tensor(np.asarray(mesh_ids, dtype='int64')).to(self.dev, non_blocking=True)
       torch.index_select(self._spawn_rows, 0, ids,
@@ -534,6 +546,26 @@ class BatchedObserver(object):
                 out=self.rocks.view(self.E * self.R, g.object_h, g.object_w),
                 max_cached_verts=max(256, self._max_verts))
     return self.rocks
+
+  def _render_bank(self):
+    """[n_meshes, R*h*w] float32: every mesh of the bank at the spawn pose, seen by the
+    R orientation cameras -- the same instance rows, jobs and kernel as the per-step
+    rasterisation, so the fetched images have its bits."""
+    g, n, R = self.geo, len(self.bank), self.R
+    jobs = np.zeros((n, R), dtype=capi.JOB_DTYPE)
+    for k in range(R):
+      jobs[:, k]['view'] = g.object_view(self.spawn_pose, k)
+    jobs['proj'] = g.object_projection
+    jobs['inst_begin'] = np.arange(n)[:, None]
+    jobs['inst_count'] = 1
+    jobs['zrange'] = g.object_z
+    jobs_d = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(self.dev)
+    cache = torch.empty((n, R * g.object_h * g.object_w), dtype=torch.float32, device=self.dev)
+    insts = self._spawn_rows.view(torch.uint8).view(-1)
+    capi.raster(self._verts, self._tris, insts, jobs_d, g.object_h, g.object_w,
+                capi.RASTER_ROCK, far_plane=FAR, out=cache.view(n * R, g.object_h, g.object_w),
+                max_cached_verts=max(256, self._max_verts))
+    return cache
 
   def poses(self, views, flat_actions):
     """Observer.pose for every environment, on the host (observer.py:392-421):

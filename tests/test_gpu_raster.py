@@ -673,6 +673,40 @@ def test_pack_rewards_goal_rectangle_equals_goal_plane(mods, dtype, freedom):
   assert outs[0][0][..., 1].any()
 
 
+@pytest.mark.parametrize('dtype,freedom', [('float32', 0), ('uint8', 2)])
+def test_cached_rock_images_equal_the_per_step_rasterisation(mods, dtype, freedom):
+  """The images of the spawned rocks fetched from the per-bank table (rasterised once,
+  srl_gather_rows_f32) are the images rasterised every step: same observations, rewards
+  and rock planes over an episode, bit for bit."""
+  a = _synthetic_env(mods, 20, dtype=dtype, freedom=freedom, steps=5)
+  b = _synthetic_env(mods, 20, dtype=dtype, freedom=freedom, steps=5, rock_cache_bytes=0)
+  assert a.obs._cache_rocks and not b.obs._cache_rocks
+  oa, ob = a.reset()[0], b.reset()[0]
+  for _ in range(5):
+    for x, y in zip(oa, ob):
+      assert torch.equal(x, y)
+    assert torch.equal(a.obs.rocks, b.obs.rocks) and bool((a.obs.rocks > 0).any())
+    action = a.sample()
+    (oa, ra, ta), (ob, rb, tb) = a.step(action), b.step(action)
+    assert torch.equal(ra, rb) and torch.equal(ta, tb)
+  assert a.obs._rock_cache is not None and b.obs._rock_cache is None
+
+
+def test_gather_rows_out_of_range_index_is_nan(mods):
+  from stackrl_b200 import capi
+  dev = torch.device('cuda')
+  for row in (7, 64, 1024, 3000):
+    table = torch.arange(5 * row, dtype=torch.float32, device=dev).view(5, row)
+    index = torch.tensor([4, 0, -1, 2, 5, 3], dtype=torch.int32, device=dev)
+    out = torch.zeros((6, row), dtype=torch.float32, device=dev)
+    capi.gather_rows(table, index, out)
+    for k, src in enumerate(index.tolist()):
+      if 0 <= src < 5:
+        assert torch.equal(out[k], table[src])
+      else:
+        assert bool(torch.isnan(out[k]).all())
+
+
 def test_contact_precheck_matches_oracle(mods):
   """contact cells / octants / support verdict of the chosen
   placements against the numpy restatement (exact: counts and integer octants)."""
