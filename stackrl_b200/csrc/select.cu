@@ -641,14 +641,19 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
   }
   __syncthreads();
   }
-  for (int k = tid; k < H * Pw; k += kSelThreads) {
-    const int row = kFixed ? k / Pw : (int)__umulhi((uint32_t)k, q.mulPw), j = k - row * Pw;
-    uint32_t packed = 0;
-    for (int s = 0; s < g_pf && row + s < H; ++s) {
-      const uint32_t* b = below + (row + s) * g_nW + (j >> 5);
-      packed |= (__funnelshift_r(b[0], b[1], j & 31) & hmask) << (s * g_hb);
+  // one warp per wall row, lanes along the output columns: no index division, and the
+  // two words of a window are the same (or neighbouring) words for the whole warp
+  for (int row = warp; row < H; row += NW) {
+    for (int j = lane; j < Pw; j += 32) {
+      const uint32_t* b = below + row * g_nW + (j >> 5);
+      uint32_t packed = 0;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (s < g_pf && row + s < H)
+          packed |= (__funnelshift_r(b[s * g_nW], b[s * g_nW + 1], j & 31) & hmask) << (s * g_hb);
+      }
+      win[row * Pw + j] = packed;
     }
-    win[k] = packed;
   }
   __syncthreads();
 
