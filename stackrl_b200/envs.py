@@ -43,7 +43,7 @@ class BatchedStackEnv(object):
                observable_size_ratio=4, resolution_factor=5, max_z=0.375,
                rewarder=None, goal_size_ratio=.25, reward_scale=1., reward_params=None,
                orientation_freedom=0, dtype='float32', settle=None, seed=None,
-               device=None, vector_rng=False, rock_cache_bytes=1 << 30):
+               device=None, vector_rng=False, rock_cache_bytes=1 << 30, block=True):
     """Arguments follow StackEnv (env.py:28-50); ``bank`` is the MeshBank of
     candidate rocks (the reference's ``urdfs`` list), ``orientation_freedom``
     the TestStackEnv option (env.py:443-463), ``settle`` the physics hook:
@@ -52,7 +52,9 @@ class BatchedStackEnv(object):
     the rest poses [E, n_placed, 7] of ALL placed rocks including the new one
     (Simulator.positions re-reads every body, simulator.py:86-92).  ``rock_cache_bytes``:
     see BatchedObserver (the spawned rocks' images are fetched from a per-bank table
-    rasterised once, when it fits)."""
+    rasterised once, when it fits).  ``block``: ParallelEnv's default for ``step`` /
+    ``reset`` (utils.py:393-428): False makes them return a callable that waits for the
+    kernels of the call and returns the time step."""
     if dtype not in self.metadata['dtypes']:
       raise ValueError('Invalid value {} for argument dtype.'.format(dtype))
     if len(bank) == 0:
@@ -118,6 +120,7 @@ class BatchedStackEnv(object):
     self._sampler = EpisodeSampler(E, len(bank), self._length, (H, W), (g.object_h, g.object_w),
                                    goal_size_ratio, vector=vector_rng)
     self._graph = None
+    self._block = bool(block)
     self.seed(seed)
 
   # -- ParallelEnv-style metadata (utils.py:185-300) --------------------------------- #
@@ -144,11 +147,15 @@ class BatchedStackEnv(object):
   def seed(self, seed=None):
     """Per-environment streams seeded seed + i (utils.py:433, 530-532); the goal
     stream of each environment is seeded from its rock stream like
-    StackEnv.seed -> Rewarder.seed (env.py:340-346, rewarder.py:196-200)."""
+    StackEnv.seed -> Rewarder.seed (env.py:340-346, rewarder.py:196-200).  Returns what
+    ParallelEnv.seed returns: one ``[seed_i, goal_seed_i]`` per environment
+    (``vector_rng``: the single ``[[seed]]`` of the batch-wide stream)."""
     seed = self._sampler.seed(seed)
     self._seed = seed
     self._action_rng = np.random.RandomState(seed % 2 ** 32)
-    return [seed]
+    if self._sampler.vector:
+      return [[seed]]
+    return [[(seed + i) % 2 ** 32, g] for i, g in enumerate(self._sampler.goal_seeds)]
 
   def sample(self):
     n = self._Ph * self._Pw
@@ -192,7 +199,27 @@ class BatchedStackEnv(object):
       capi.fill_goals(rects, self._goal_z_d, self.goals, env_ids=ids_d)
 
   # -- episode control ----------------------------------------------------------------- #
-  def reset(self, env_ids=None, rock_orders=None, goal_lims=None):
+  def _deliver(self, out, block):
+    """ParallelEnv's ``block`` convention (utils.py:393-428): the time step itself, or a
+    callable that waits for the kernels queued so far and returns it.  (A blocking
+    call does not synchronise either: the tensors are ordered on the current stream.)"""
+    if self._block if block is None else block:
+      return out
+    done = torch.cuda.Event()
+    done.record(torch.cuda.current_stream(self.dev))
+    def ready():
+      done.synchronize()
+      return out
+    return ready
+
+  def __call__(self, *args, **kwargs):
+    """Calls step (utils.py:263-265)."""
+    return self.step(*args, **kwargs)
+
+  def close(self):
+    """Nothing to release: no worker processes, no physics client (env.py:333-338)."""
+
+  def reset(self, env_ids=None, rock_orders=None, goal_lims=None, block=None):
     """Start new episodes (env.py:266-293).  ``rock_orders`` / ``goal_lims``
     override the random draws (used to replay recorded episodes)."""
     ids = np.arange(self.E) if env_ids is None else np.asarray(list(env_ids), dtype='int64')
@@ -227,7 +254,8 @@ class BatchedStackEnv(object):
       self.set_goals(lims, None if env_ids is None else ids)
       self.obs.begin(self._order_h, None if env_ids is None else ids)
     self._observe()
-    return self.observation, self._zero_reward, self.obs.state.done.view(torch.bool)
+    return self._deliver(
+      (self.observation, self._zero_reward, self.obs.state.done.view(torch.bool)), block)
 
   @property
   def _current(self):
@@ -325,10 +353,10 @@ class BatchedStackEnv(object):
       r = {name: r[:, k] for k, name in enumerate(METRIC_NAMES)}
     return (wall_goal, rock if self.R > 1 else rock[:, 0]), r
 
-  def step(self, action):
+  def step(self, action, block=None):
     """action: [E] flat indices, or (views [E], flat indices [E]) when
     orientation_freedom > 0 (env.py:233-264, 482-520).  Device int64 tensors are
-    used in place; anything else is uploaded."""
+    used in place; anything else is uploaded.  ``block``: see ``_deliver``."""
     if self._done.any():
       raise RuntimeError('reset() the finished environments before stepping them')
     views, flat = self._as_action(action)
@@ -341,7 +369,7 @@ class BatchedStackEnv(object):
     else:
       observation, reward = self._step_device(views, flat)
     self._advance_host()
-    return observation, reward, self.obs.state.done.view(torch.bool)
+    return self._deliver((observation, reward, self.obs.state.done.view(torch.bool)), block)
 
   def _advance_host(self):
     more = self._cursor < self._length

@@ -61,7 +61,9 @@ class EpisodeSampler(object):
       self.rngs = self.goal_rngs = None
     else:
       self.rngs = [np.random.RandomState((seed + i) % 2 ** 32) for i in range(self.E)]
-      self.goal_rngs = [np.random.RandomState(r.randint(2 ** 32)) for r in self.rngs]
+      # StackEnv.seed -> Rewarder.seed(self._random.randint(2**32)) (env.py:340-346)
+      self.goal_seeds = [int(r.randint(2 ** 32)) for r in self.rngs]
+      self.goal_rngs = [np.random.RandomState(g) for g in self.goal_seeds]
     return seed
 
   # -- rock orders (env.py:268-272): [n, L] in the order ``choice`` returned them ------- #

@@ -707,6 +707,30 @@ def test_gather_rows_out_of_range_index_is_nan(mods):
         assert bool(torch.isnan(out[k]).all())
 
 
+def test_parallel_env_contract_block_call_seed(mods):
+  """ParallelEnv's surface (utils.py:393-428, 520-536): ``block=False`` returns a callable
+  that delivers the same time step, ``env(action)`` is ``step``, ``seed`` returns one
+  ``[seed_i, goal_seed_i]`` per environment with the reference's derivation."""
+  a = _synthetic_env(mods, 6, steps=4, seed=11)
+  b = _synthetic_env(mods, 6, steps=4, seed=11, block=False)
+  ra, rb = a.reset(), b.reset()
+  assert callable(rb) and not callable(ra)
+  rb = rb()
+  for _ in range(3):
+    for x, y in zip(ra[0], rb[0]):
+      assert torch.equal(x, y)
+    assert torch.equal(ra[1], rb[1]) and torch.equal(ra[2], rb[2])
+    action = a.sample()
+    ra, rb = a(action), b.step(action)()
+  assert not callable(b.step(b.sample(), block=True))
+  seeds = a.seed(40)
+  assert len(seeds) == 6
+  for i, (s0, s1) in enumerate(seeds):
+    assert s0 == 40 + i
+    assert s1 == int(np.random.RandomState(40 + i).randint(2 ** 32))
+  a.close()
+
+
 def test_contact_precheck_matches_oracle(mods):
   """contact cells / octants / support verdict of the chosen
   placements against the numpy restatement (exact: counts and integer octants)."""
