@@ -24,6 +24,8 @@ seeded with ``randint(2**32)`` of the first (env.py:166, 346; rewarder.py:
 ``vector_rng=True`` replaces the 2E streams by one vectorised stream (same
 distributions, not the reference's draw sequence) for very large batches.
 """
+import collections
+
 import numpy as np
 import torch
 
@@ -34,6 +36,10 @@ from stackrl_b200.episodes import EpisodeSampler
 from stackrl_b200.observer import BatchedObserver
 
 METRIC_NAMES = ('IoU', 'OR', 'DIoU', 'DOR')      # Rewarder.metrics (rewarder.py:7)
+
+# What get_space_spec (utils.py:19-48) returns is a tf.TensorSpec; TensorFlow is not part of
+# this package, so a spec is its two fields the callers read: ``.shape`` and ``.dtype``.
+Spec = collections.namedtuple('Spec', 'shape dtype')
 
 
 class BatchedStackEnv(object):
@@ -134,15 +140,18 @@ class BatchedStackEnv(object):
 
   @property
   def observation_spec(self):
+    """get_space_spec of the observation space (utils.py:24-39): at most the last three
+    dimensions are kept, so the view axis of TestStackEnv is not part of the spec."""
     g = self.obs.geo
-    lead = (self.R,) if self.R > 1 else ()
-    return ((lead + (g.overhead_h, g.overhead_w, 2), self._dtype),
-            (lead + (g.object_h, g.object_w, 1), self._dtype))
+    return (Spec((g.overhead_h, g.overhead_w, 2), self._dtype),
+            Spec((g.object_h, g.object_w, 1), self._dtype))
 
   @property
   def action_spec(self):
     n = self._Ph * self._Pw
-    return ((self.R, n), 'int64') if self.R > 1 else (n, 'int64')
+    # Discrete(n) -> a scalar int64 per environment (TestStackEnv: Tuple(Discrete(R),
+    # Discrete(n)), env.py:463); the bounds are not part of a TensorSpec
+    return (Spec((), 'int64'), Spec((), 'int64')) if self.R > 1 else Spec((), 'int64')
 
   def seed(self, seed=None):
     """Per-environment streams seeded seed + i (utils.py:433, 530-532); the goal
