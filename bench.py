@@ -252,7 +252,9 @@ def cpu_arm(name, steps, warmup, cores):
   P = positions(w)
   with ctx.Pool(cores) as pool:
     if name in ('c2', 'c5'):
-      per_core = 16 if name == 'c2' else 1           # environments (all their views) per core
+      # environments (all their views) per core and step: ~0.6 s of reference code per
+      # step and core, so the default two steps are ~20 core-seconds of CPU work
+      per_core = 48 if name == 'c2' else 2
       views = _CPU_SAMPLE[name]['rotations']
       fn = _cpu_c2
       job = lambda s, k: (name, 1000 * s + k, per_core)
@@ -269,7 +271,7 @@ def cpu_arm(name, steps, warmup, cores):
                 'unmodified reference'.format(cores * per_core, views, w['H'], w['W'], w['h'],
                                               w['h'], cores))
     else:
-      per = 12
+      per = 36                     # env steps per core and step (~0.6 s)
       for _ in range(max(1, warmup)):
         pool.map(_cpu_c4, [(name, k, 2) for k in range(cores)])
       t0 = time.perf_counter()
@@ -902,7 +904,8 @@ def extra_metrics(torch, dev, cpu_baseline=True):
   for k in range(n):
     bank.add(verts[k], tris)
   obs = BatchedObserver(bank, n, 1, overhead_resolution=128, object_resolution=32,
-                        pixel_size=0.005, max_z=0.375, device=dev)
+                        pixel_size=0.005, max_z=0.375, device=dev,
+                        rock_cache_bytes=0)       # time the rasterisation, not the image table
   obs.observe_rocks(np.arange(n))
   torch.cuda.synchronize()
   ms = _time_loop(torch, lambda _: obs.observe_rocks(), 20)
@@ -970,7 +973,9 @@ def extra_metrics(torch, dev, cpu_baseline=True):
   # -- the DQN's Siamese correlation layer (nets/layers.py:21-38) -- #
   try:
     from stackrl_b200 import nets
-    out['siam_correlation'] = nets.benchmark(torch, dev)
+    out['siam_correlation'] = nets.benchmark(
+      torch, dev, tensor_peak_tflops=peaks.get('bf16_tflops'),
+      tensor_peak_source=peak_src + ': dense bf16 (= fp16) cuBLAS burst figure')
   except Exception as exc:
     out['siam_correlation'] = {'error': repr(exc)}
   return out

@@ -54,7 +54,8 @@ def correlation(in0, in1, parallel_iterations=None):
   return capi.siam_correlation_f32(in0.contiguous(), in1.contiguous())
 
 
-def benchmark(torch_module, device, samples=148, channels=16, side=128, rock=32, reps=10):
+def benchmark(torch_module, device, samples=148, channels=16, side=128, rock=32, reps=10,
+              tensor_peak_tflops=None, tensor_peak_source=''):
   """Throughput of the correlation layer at the config.gin geometry (config.gin:55):
   ``samples`` x (side^2 x channels (*) rock^2 x channels).  Returned as the dict
   bench.py puts under ``extra.siam_correlation``."""
@@ -73,15 +74,32 @@ def benchmark(torch_module, device, samples=148, channels=16, side=128, rock=32,
   b.record()
   torch_module.cuda.synchronize()
   ms = a.elapsed_time(b) / reps
-  flops = 2.0 * samples * (side - rock + 1) ** 2 * rock * rock * channels
+  P = side - rock + 1
+  flops = 2.0 * samples * P * P * rock * rock * channels
   fma_peak = 2 * max(capi.microbench_fma(v, 400) for v in (0, 1, 2)) / 1e12
-  return {
+  # Tensor-core work the kernel issues (csrc/siam_tc.cu): three products (hi*hi, hi*lo,
+  # lo*hi) of every (image row, 128-pixel tile, filter row) -- all `side` image rows meet all
+  # `rock` filter rows, and the pixel tiles are padded to 128.
+  tiles = (P + 127) // 128
+  tensor_flops = 3 * 2.0 * samples * side * (128 * tiles) * rock * rock * channels
+  out = {
     'workload': '{} samples, {}x{}x{} wall features * {}x{}x{} rock features, float32 '
                 '(stackrl.nets.correlation, config.gin geometry)'.format(
                   samples, side, side, channels, rock, rock, channels),
     'ms': ms, 'samples_per_s': samples / (ms * 1e-3),
-    'roofline': {'bound': 'fp32-fma', 'achieved': flops / (ms * 1e-3) / 1e12,
-                 'peak': fma_peak, 'unit': 'TFLOP/s',
-                 'frac': flops / (ms * 1e-3) / 1e12 / fma_peak,
-                 'peak_source': 'srl_microbench_fma, best of FFMA / FFMA2 measured in this run '
-                                '(nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4)'}}
+    'fp32_equivalent_tflops': flops / (ms * 1e-3) / 1e12,
+    'fp32_fma_peak_tflops': fma_peak,
+    'fp32_fma_peak_source': 'srl_microbench_fma, best of FFMA / FFMA2 measured in this run '
+                            '(nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4): what a '
+                            'float32 kernel of this layer is bound by'}
+  if tensor_peak_tflops:
+    out['roofline'] = {
+      'bound': 'tensor', 'kernel': 'siam_tc_kernel (tcgen05, FP16 hi/lo operand pairs)',
+      'achieved': tensor_flops / (ms * 1e-3) / 1e12, 'peak': tensor_peak_tflops,
+      'unit': 'TFLOP/s', 'frac': tensor_flops / (ms * 1e-3) / 1e12 / tensor_peak_tflops,
+      'peak_source': tensor_peak_source,
+      'note': 'achieved counts the three error-compensation products and the padded rows / '
+              'pixels the kernel really multiplies; the layer itself is fp32_equivalent_tflops. '
+              'The limiter is the operand read of an N = 64 MMA from shared memory, not the '
+              'tensor pipe (DESIGN 3.8)'}
+  return out

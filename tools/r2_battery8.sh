@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round-2 final measurement battery (one GPU).  Every ncu pass runs after the same command has
-# exited 0 without ncu.
+# Round-2 final measurement battery, part 1 (one GPU): tests, smoke, bench lines, logs.
+# (The ncu passes are tools/r2_battery8_ncu.sh: a call may bring back 64 MiB at most.)
 set -x
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -q -m gpu --maxfail=10 -p no:cacheprovider > gpurun_out/b8_pytest.log 2>&1; tail -3 gpurun_out/b8_pytest.log
@@ -29,26 +29,3 @@ timeout 1200 python bench.py --workload c5 > gpurun_out/b8_bench_c5.json 2> gpur
 timeout 600 python bench.py --workload c5 --impl reference --steps 2 --warmup 1 > gpurun_out/b8_bench_c5_ref.json 2> gpurun_out/b8_bench_c5_ref.err
 head -c 700 gpurun_out/b8_bench_c2.json; echo; head -c 400 gpurun_out/b8_bench_c4.json; echo; head -c 400 gpurun_out/b8_bench_c5.json; echo
 python tools/microbench.py 2000 0,2,7,3,6,8,14,17,18 fma > gpurun_out/b8_micro.log 2>&1; cat gpurun_out/b8_micro.log
-# ---- ncu: launch list of the benched command, then full captures of the top kernels ---- #
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extra > /dev/null 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
-  --log-file gpurun_out/b8_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extra \
-  > gpurun_out/b8_ncu_launches.log 2>&1
-python tools/run_step.py 16 8 > gpurun_out/b8_step.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'maxplus_stream|mask_select' -c 2 -s 40 \
-  -f -o gpurun_out/prof_r2c_step python tools/run_step.py 16 8 > gpurun_out/b8_ncu_step.log 2>&1
-SRL_RASTER_MODE=0 python tools/bench_raster.py 4096 10 5 > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:raster_kernel -c 1 -s 4 \
-  -f -o gpurun_out/prof_r2c_raster python tools/bench_raster.py 4096 10 2 > gpurun_out/b8_ncu_raster.log 2>&1
-SRL_SIAM_MODE=2 python tools/bench_siam.py 148 16 > /dev/null 2>&1 && \
-SRL_SIAM_MODE=2 ncu --set full --clock-control none --import-source on -k regex:siam_tc_kernel -c 1 -s 2 \
-  -f -o gpurun_out/prof_r2c_siam_tc python tools/bench_siam.py 148 16 > gpurun_out/b8_ncu_siam.log 2>&1
-python tools/run_env_steps.py 16384 6 > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'raster_kernel|mask_select|pack_rewards|maxplus_stream|gather_rows|place_poses' -s 18 -c 6 -f -o gpurun_out/prof_r2c_env python tools/run_env_steps.py 16384 6 > gpurun_out/b8_ncu_env.log 2>&1
-python tools/bench_misc.py > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'maxplus_u8' -c 1 -s 3 -f -o gpurun_out/prof_r2c_u8 python tools/bench_misc.py > gpurun_out/b8_ncu_u8.log 2>&1
-python tools/microbench.py 400 2,7,14,6,8 > /dev/null 2>&1 && \
-ncu --metrics smsp__inst_executed.sum,smsp__issue_active.sum,smsp__cycles_active.sum,smsp__inst_executed_pipe_fma.sum,smsp__inst_executed_pipe_alu.sum,smsp__inst_executed_pipe_fmaheavy.sum,smsp__inst_executed_pipe_fmalite.sum,gpu__time_duration.sum \
-  --clock-control none -k regex:addmax_kernel --csv --log-file gpurun_out/b8_micro_pipes.csv \
-  python tools/microbench.py 400 2,7,14,6,8 > gpurun_out/b8_ncu_micro.log 2>&1
-tail -2 gpurun_out/b8_ncu_micro.log
