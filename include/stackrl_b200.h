@@ -291,6 +291,20 @@ SRL_API int srl_raster_incremental(const float* verts, const int32_t* tris,
                                    int rows, int cols, int mode, double far_plane,
                                    int max_cached_verts, srl_stream_t stream);
 
+/* srl_raster_incremental that also reports, per job, the image rows it may have changed:
+ * rows_out [njobs,2] int32 = (first row, past-last row); (0, rows) for a whole-scene draw,
+ * the span of the appended instance's projected vertices (one row of margin) for
+ * only_last == 2.  srl_pack_rewards_rows_f32 uses it to rewrite only those rows of a
+ * persistent packed observation. */
+SRL_API int srl_raster_incremental_rows(const float* verts, const int32_t* tris,
+                                        const srl_raster_instance* insts,
+                                        const srl_raster_job* jobs,
+                                        const int32_t* inst_counts, float* depth_state,
+                                        int only_last, float* out, int32_t* rows_out,
+                                        int njobs, int rows, int cols, int mode,
+                                        double far_plane, int max_cached_verts,
+                                        srl_stream_t stream);
+
 /* ---- a11: Rewarder._intersection/_union (rewarder.py:297-307) ---------------
  * inter[e] = sum(min(walls[e][goal != 0], goal_z[e])), uni[e] = sum(max(walls[e],
  * goals[e])), vol[e] = sum(goals[e]).  Accumulated in float64 and rounded once;
@@ -451,6 +465,24 @@ SRL_API int srl_pack_rewards_f32(const srl_env_state* host_state, const float* w
                                  int dtype_code, float obs_scale, int repeat_wall, int metric,
                                  double scale, double pixel_h, double pixel_w, double pmax,
                                  double pexp, double oexp, srl_stream_t stream);
+
+/* srl_pack_rewards_f32 into PERSISTENT observation buffers: wall_goal still holds what
+ * the previous call wrote for the same environments, and only the wall-image rows
+ * rows[e] = (first, past-last) that changed since (srl_raster_incremental_rows) are
+ * rewritten -- a placed rock touches ~18 of 64 rows, so a step writes a quarter of the
+ * packed observation.  full [E] (uint8, may be NULL = always everything): non-zero
+ * entries rewrite every row of that environment (new episode / goal, whole-scene redraw,
+ * first use of the buffer) and are cleared by the call.  The rock images and the rewards
+ * are always written in full; the result is the same bytes as srl_pack_rewards_f32. */
+SRL_API int srl_pack_rewards_rows_f32(const srl_env_state* host_state, const float* walls,
+                                      const float* goals, const float* rocks,
+                                      const float* goal_z, const int32_t* rects,
+                                      const int32_t* rows, uint8_t* full, void* wall_goal,
+                                      void* rock, float* reward, double* value, int R, int H,
+                                      int W, int h, int dtype_code, float obs_scale,
+                                      int repeat_wall, int metric, double scale,
+                                      double pixel_h, double pixel_w, double pmax, double pexp,
+                                      double oexp, srl_stream_t stream);
 
 /* StackEnv._return's uint8 cast (env.py:171-178) on the planar maps (the form the
  * scoring kernels take): q = trunc(x*255/scale) in float32. */

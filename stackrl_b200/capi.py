@@ -62,6 +62,8 @@ _SIGNATURES = {
   'srl_raster_ex': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _c.c_double, _I, _P]),
   'srl_raster_incremental': (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _c.c_double,
                                    _I, _P]),
+  'srl_raster_incremental_rows': (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I,
+                                        _c.c_double, _I, _P]),
   'srl_reward_sums_f32': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
   'srl_pack_obs': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_float, _I, _P]),
   'srl_place_poses_f32': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_double,
@@ -79,6 +81,8 @@ _SIGNATURES = {
                             _c.c_double, _c.c_double, _c.c_double, _c.c_double, _P]),
   'srl_pack_rewards_f32': (_I, [_P] * 10 + [_I, _I, _I, _I, _I, _c.c_float, _I, _I] +
                            [_c.c_double] * 6 + [_P]),
+  'srl_pack_rewards_rows_f32': (_I, [_P] * 12 + [_I, _I, _I, _I, _I, _c.c_float, _I, _I] +
+                                [_c.c_double] * 6 + [_P]),
   'srl_quantise_planes_u8': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _c.c_float, _P]),
   'srl_gather_rows_f32': (_I, [_P, _P, _P, _I, _I, _I, _P]),
   'srl_microbench_addmax': (_I, [_I, _I, _c.POINTER(_c.c_double)]),
@@ -342,7 +346,8 @@ RASTER_DEPTH, RASTER_WALL, RASTER_ROCK = 0, 1, 2
 
 
 def raster(verts, tris, instances, jobs, rows, cols, mode, far_plane=1000., out=None,
-           inst_counts=None, max_cached_verts=0, depth_state=None, only_last=False):
+           inst_counts=None, max_cached_verts=0, depth_state=None, only_last=False,
+           rows_out=None):
   """verts [NV,3] f32 / tris [NT,3] i32 CUDA tensors (the mesh bank),
   instances / jobs numpy structured arrays (INSTANCE_DTYPE / JOB_DTYPE) or
   CUDA uint8 tensors holding them -> [njobs, rows, cols] float32.
@@ -351,7 +356,9 @@ def raster(verts, tris, instances, jobs, rows, cols, mode, far_plane=1000., out=
   ``depth_state`` [njobs, rows, cols] float32: the GL depth image kept between calls
   (srl_raster_incremental); with ``only_last`` only the last instance of every job
   is drawn onto it -- same bits as re-drawing the whole scene; ``only_last=2``: ``out``
-  still holds the image of ``depth_state`` and is updated in place."""
+  still holds the image of ``depth_state`` and is updated in place.  ``rows_out``
+  [njobs, 2] int32 (with ``depth_state``): receives the image rows each job may have
+  changed (srl_raster_incremental_rows)."""
   dev = verts.device
   def as_bytes(a, dtype):
     if isinstance(a, torch.Tensor):
@@ -375,7 +382,14 @@ def raster(verts, tris, instances, jobs, rows, cols, mode, far_plane=1000., out=
           _dev(inst_t, torch.uint8, 'instances'), _dev(jobs_t, torch.uint8, 'jobs'),
           _dev(out, torch.float32, 'out'))
   with torch.cuda.device(dev):
-    if depth_state is not None:
+    if depth_state is not None and rows_out is not None:
+      _check(lib.srl_raster_incremental_rows(
+        *args[:4], _opt(inst_counts, torch.int32, 'inst_counts'),
+        _out(depth_state, torch.float32, (njobs, rows, cols), verts, 'depth_state'),
+        int(only_last), args[4], _out(rows_out, torch.int32, (njobs, 2), verts, 'rows_out'),
+        int(njobs), int(rows), int(cols), int(mode), float(far_plane), int(max_cached_verts),
+        _stream()))
+    elif depth_state is not None:
       _check(lib.srl_raster_incremental(
         *args[:4], _opt(inst_counts, torch.int32, 'inst_counts'),
         _out(depth_state, torch.float32, (njobs, rows, cols), verts, 'depth_state'),
@@ -735,16 +749,21 @@ def rewards(state, walls, goals, goal_z, rects, metric, scale, pixel, pmax, pexp
 
 
 def pack_rewards(state, walls, goals, rocks, goal_z, rects, metric, scale, pixel, pmax, pexp,
-                 oexp, dtype='float32', obs_scale=1., repeat_wall=False, out=None):
+                 oexp, dtype='float32', obs_scale=1., repeat_wall=False, out=None, rows=None,
+                 full=None):
   """pack_obs + rewards of one step in one launch -> (wall_goal, rock, reward).
   ``goals=None``: the goal maps are the rectangles ``rects`` at ``goal_z`` (what
-  ``fill_goals`` writes) and are not read from memory."""
+  ``fill_goals`` writes) and are not read from memory.  ``rows`` [E,2] int32 (+ ``full``
+  [E] uint8, + ``out``): ``out`` is persistent and only the wall rows that changed are
+  rewritten (srl_pack_rewards_rows_f32)."""
   E, R, H, W, h = _batch_dims(walls, rocks)
   dev = walls.device
   m = METRICS[metric]
   tdt = {'float32': torch.float32, 'uint8': torch.uint8}[str(dtype)]
   wg_shape = (E, R, H, W, 2) if repeat_wall else (E, H, W, 2)
   if out is None:
+    if rows is not None:
+      raise ValueError('row-incremental packing needs the persistent buffers as `out`')
     wall_goal = torch.empty(wg_shape, dtype=tdt, device=dev)
     rock = torch.empty((E, R, h, h, 1), dtype=tdt, device=dev)
   else:
@@ -752,16 +771,21 @@ def pack_rewards(state, walls, goals, rocks, goal_z, rects, metric, scale, pixel
     _out(wall_goal, tdt, wg_shape, walls, 'wall_goal')
     _out(rock, tdt, (E, R, h, h, 1), walls, 'rock')
   reward = torch.empty((E, 4) if m == 4 else (E,), dtype=torch.float32, device=dev)
+  head = (state.ref(), _dev(walls, torch.float32, 'walls'),
+          _P(None) if goals is None else _dev(goals, torch.float32, 'goals'),
+          _dev(rocks, torch.float32, 'rocks'), _dev(goal_z, torch.float32, 'goal_z'),
+          _dev(rects, torch.int32, 'rects'))
+  tail = (_P(wall_goal.data_ptr()), _P(rock.data_ptr()), _P(reward.data_ptr()), _P(None), R, H,
+          W, h, 0 if tdt == torch.float32 else 1, float(obs_scale), int(bool(repeat_wall)), m,
+          float(scale), float(pixel[0]), float(pixel[1]), float(pmax),
+          -1.0 if pexp is None else float(pexp), -1.0 if oexp is None else float(oexp), _stream())
   with torch.cuda.device(dev):
-    _check(lib.srl_pack_rewards_f32(
-      state.ref(), _dev(walls, torch.float32, 'walls'),
-      _P(None) if goals is None else _dev(goals, torch.float32, 'goals'),
-      _dev(rocks, torch.float32, 'rocks'), _dev(goal_z, torch.float32, 'goal_z'),
-      _dev(rects, torch.int32, 'rects'), _P(wall_goal.data_ptr()), _P(rock.data_ptr()),
-      _P(reward.data_ptr()), _P(None), R, H, W, h, 0 if tdt == torch.float32 else 1,
-      float(obs_scale), int(bool(repeat_wall)), m, float(scale), float(pixel[0]),
-      float(pixel[1]), float(pmax), -1.0 if pexp is None else float(pexp),
-      -1.0 if oexp is None else float(oexp), _stream()))
+    if rows is not None:
+      _check(lib.srl_pack_rewards_rows_f32(
+        *head, _out(rows, torch.int32, (E, 2), walls, 'rows'),
+        _P(None) if full is None else _out(full, torch.uint8, (E,), walls, 'full'), *tail))
+    else:
+      _check(lib.srl_pack_rewards_f32(*head, *tail))
   return wall_goal, rock, reward
 
 

@@ -325,6 +325,37 @@ int srl_quantise_planes_u8(const float* walls, const float* goals, const float* 
                                  scale, (cudaStream_t)stream);
 }
 
+int srl_raster_incremental_rows(const float* verts, const int32_t* tris,
+                                const srl_raster_instance* insts, const srl_raster_job* jobs,
+                                const int32_t* inst_counts, float* depth_state, int only_last,
+                                float* out, int32_t* rows_out, int njobs, int rows, int cols,
+                                int mode, double far_plane, int max_cached_verts,
+                                srl_stream_t stream) {
+  SRL_REQUIRE(depth_state != nullptr || njobs == 0, SRL_E_INVALID,
+              "raster_incremental_rows: depth_state is null");
+  SRL_REQUIRE(rows_out != nullptr || njobs == 0, SRL_E_INVALID,
+              "raster_incremental_rows: rows_out is null");
+  return srl::raster(verts, tris, insts, jobs, inst_counts, depth_state, only_last, out, njobs,
+                     rows, cols, mode, far_plane, max_cached_verts, (cudaStream_t)stream,
+                     rows_out);
+}
+
+int srl_pack_rewards_rows_f32(const srl_env_state* host_state, const float* walls,
+                              const float* goals, const float* rocks, const float* goal_z,
+                              const int32_t* rects, const int32_t* rows, uint8_t* full,
+                              void* wall_goal, void* rock, float* reward, double* value, int R,
+                              int H, int W, int h, int dtype_code, float obs_scale,
+                              int repeat_wall, int metric, double scale, double pixel_h,
+                              double pixel_w, double pmax, double pexp, double oexp,
+                              srl_stream_t stream) {
+  SRL_REQUIRE(rows != nullptr || host_state == nullptr || host_state->E == 0, SRL_E_INVALID,
+              "pack_rewards_rows: rows is null");
+  return srl::pack_rewards_f32(host_state, walls, goals, rocks, goal_z, rects, wall_goal, rock,
+                               reward, value, R, H, W, h, dtype_code, obs_scale, repeat_wall,
+                               metric, scale, pixel_h, pixel_w, pmax, pexp, oexp,
+                               (cudaStream_t)stream, rows, full);
+}
+
 int srl_gather_rows_f32(const float* table, const int32_t* index, float* out, int rows_out,
                         int row_floats, int table_rows, srl_stream_t stream) {
   return srl::gather_rows_f32(table, index, out, rows_out, row_floats, table_rows,

@@ -67,7 +67,8 @@ int corrcoef_localized_u8(const uint8_t* walls, const uint8_t* rocks, const uint
 int raster(const float* verts, const int32_t* tris, const srl_raster_instance* insts,
            const srl_raster_job* jobs, const int32_t* inst_counts, float* depth_state,
            int only_last, float* out, int njobs, int rows, int cols, int mode,
-           double far_plane, int vert_cap_hint, cudaStream_t stream);
+           double far_plane, int vert_cap_hint, cudaStream_t stream,
+           int32_t* rows_out = nullptr);
 
 int pack_obs(const float* walls, const float* goals, const float* rocks, void* wall_goal,
              void* rock, int E, int R, int H, int W, int h, int dtype_code, float scale,
@@ -117,7 +118,8 @@ int pack_rewards_f32(const srl_env_state* st, const float* walls, const float* g
                      void* wall_goal, void* rock, float* reward, double* value, int R, int H,
                      int W, int h, int dtype_code, float obs_scale, int repeat_wall, int metric,
                      double scale, double pixel_h, double pixel_w, double pmax, double pexp,
-                     double oexp, cudaStream_t stream);
+                     double oexp, cudaStream_t stream, const int32_t* rows = nullptr,
+                     uint8_t* full = nullptr);
 int gather_rows_f32(const float* table, const int32_t* index, float* out, int rows_out,
                     int row_floats, int table_rows, cudaStream_t stream);
 int quantise_planes_u8(const float* walls, const float* goals, const float* rocks,

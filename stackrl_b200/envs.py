@@ -49,7 +49,8 @@ class BatchedStackEnv(object):
                observable_size_ratio=4, resolution_factor=5, max_z=0.375,
                rewarder=None, goal_size_ratio=.25, reward_scale=1., reward_params=None,
                orientation_freedom=0, dtype='float32', settle=None, seed=None,
-               device=None, vector_rng=False, rock_cache_bytes=1 << 30, block=True):
+               device=None, vector_rng=False, rock_cache_bytes=1 << 30, block=True,
+               persistent_observation=False):
     """Arguments follow StackEnv (env.py:28-50); ``bank`` is the MeshBank of
     candidate rocks (the reference's ``urdfs`` list), ``orientation_freedom``
     the TestStackEnv option (env.py:443-463), ``settle`` the physics hook:
@@ -60,7 +61,11 @@ class BatchedStackEnv(object):
     see BatchedObserver (the spawned rocks' images are fetched from a per-bank table
     rasterised once, when it fits).  ``block``: ParallelEnv's default for ``step`` /
     ``reset`` (utils.py:393-428): False makes them return a callable that waits for the
-    kernels of the call and returns the time step."""
+    kernels of the call and returns the time step.  ``persistent_observation``: ``step``
+    returns the SAME observation tensors every time and rewrites only the wall rows the
+    placed rock changed (a quarter of the bytes of a step's packed observation); a caller
+    that keeps an observation across steps must copy it.  ``capture()`` always works that
+    way (a CUDA graph replays into fixed buffers)."""
     if dtype not in self.metadata['dtypes']:
       raise ValueError('Invalid value {} for argument dtype.'.format(dtype))
     if len(bank) == 0:
@@ -127,6 +132,9 @@ class BatchedStackEnv(object):
                                    goal_size_ratio, vector=vector_rng)
     self._graph = None
     self._block = bool(block)
+    self._obs_buf = self._obs_full = None
+    if persistent_observation:
+      self._make_persistent()
     self.seed(seed)
 
   # -- ParallelEnv-style metadata (utils.py:185-300) --------------------------------- #
@@ -195,6 +203,7 @@ class BatchedStackEnv(object):
     """Install goal rectangles ((u, v), (u+h, v+w)) (rewarder.py:252-258): the
     limits go to the device, the maps are filled there."""
     ids = np.arange(self.E) if env_ids is None else np.asarray(list(env_ids), dtype='int64')
+    self._mark_full(None if env_ids is None else ids)
     self._sync_host()
     self._goal_lims[ids] = np.asarray(lims, dtype='int64').reshape(len(ids), 2, 2)
     self._rects_d.copy_(torch.from_numpy(
@@ -233,6 +242,7 @@ class BatchedStackEnv(object):
     override the random draws (used to replay recorded episodes)."""
     ids = np.arange(self.E) if env_ids is None else np.asarray(list(env_ids), dtype='int64')
     n = len(ids)
+    self._mark_full(None if env_ids is None else ids)
     self._cursor[ids] = 1
     self._done[ids] = False
     if self._sampler.vector and rock_orders is None and goal_lims is None:
@@ -348,15 +358,36 @@ class BatchedStackEnv(object):
     self._observe(appended)
     return self._reward_and_pack()
 
+  def _make_persistent(self):
+    """Fixed observation buffers + the per-environment "rewrite everything" flags."""
+    g = self.obs.geo
+    tdt = {'float32': torch.float32, 'uint8': torch.uint8}[self._dtype]
+    lead = (self.E, self.R) if self.R > 1 else (self.E,)
+    self._obs_buf = (
+      torch.empty(lead + (g.overhead_h, g.overhead_w, 2), dtype=tdt, device=self.dev),
+      torch.empty((self.E, self.R, g.object_h, g.object_w, 1), dtype=tdt, device=self.dev))
+    self._obs_full = torch.ones((self.E,), dtype=torch.uint8, device=self.dev)
+
+  def _mark_full(self, ids=None):
+    """New goal / new episode: every row of the persistent observation is stale."""
+    if self._obs_full is None:
+      return
+    if ids is None:
+      self._obs_full.fill_(1)
+    else:
+      self._obs_full[torch.as_tensor(np.asarray(ids), device=self.dev, dtype=torch.long)] = 1
+
   def _reward_and_pack(self):
     """Packed observation + reward of the step in one launch (a14 + a11/a12)."""
     g = self.obs.geo
+    persistent = {} if self._obs_buf is None else dict(
+      out=self._obs_buf, rows=self.obs.wall_rows, full=self._obs_full)
     # self.goals is always fill_goals(self._rects_d, self._goal_z_d): the kernel takes the
     # rectangle instead of reading the map
     wall_goal, rock, r = capi.pack_rewards(
       self.obs.state, self.obs.walls, None, self.obs.rocks, self._goal_z_d, self._rects_d,
       self.metric, self.scale, (g.pixel_h, g.pixel_w), self._pmax, self._pexp, self._oexp,
-      dtype=self._dtype, obs_scale=self._scale, repeat_wall=self.R > 1)
+      dtype=self._dtype, obs_scale=self._scale, repeat_wall=self.R > 1, **persistent)
     if self.metric == 'all':
       # the reference returns the four metrics as the info dict (env.py:258-262)
       r = {name: r[:, k] for k, name in enumerate(METRIC_NAMES)}
@@ -406,6 +437,9 @@ class BatchedStackEnv(object):
     at least one eager step before (lazy kernel attributes).  Returns self."""
     if self._settle is not None:
       raise RuntimeError('a settle hook runs on the host and cannot be captured')
+    if self._obs_buf is None:
+      self._make_persistent()
+    self._mark_full()
     dev = self.dev
     self._g_views = torch.zeros(self.E, dtype=torch.int64, device=dev) if self.R > 1 else None
     self._g_flat = torch.zeros(self.E, dtype=torch.int64, device=dev)

@@ -422,6 +422,9 @@ class BatchedObserver(object):
     self._wall_depth = torch.ones((E, g.overhead_h, g.overhead_w), dtype=torch.float32,
                                   device=self.dev)
     self._wall_depth_valid = False
+    # image rows the last observe_walls may have changed, per environment (for consumers
+    # that keep a derived image, e.g. the packed observation, up to date row by row)
+    self.wall_rows = torch.zeros((E, 2), dtype=torch.int32, device=self.dev)
     self._rock_cache = None
     self._cache_rocks = 0 < n * R * g.object_h * g.object_w * 4 <= int(rock_cache_bytes)
 
@@ -522,6 +525,7 @@ class BatchedObserver(object):
                 g.overhead_w, capi.RASTER_WALL, far_plane=FAR, out=self.walls,
                 inst_counts=self.counts, depth_state=self._wall_depth,
                 only_last=2 if last else 0,       # walls still holds the kept image
+                rows_out=self.wall_rows,
                 max_cached_verts=max(256, self._max_verts) if last else
                 min(2048, max(256, self._max_verts * self.cap)))
     self._wall_depth_valid = True

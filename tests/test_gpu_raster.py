@@ -514,6 +514,41 @@ def test_step_graph_replays_the_eager_chain(mods, dtype, freedom):
   assert torch.equal(oc[0], od[0]) and torch.equal(oc[1], od[1]) and torch.equal(rc, rd)
 
 
+@pytest.mark.parametrize('dtype,freedom', [('float32', 0), ('uint8', 0), ('float32', 2)])
+def test_persistent_observation_equals_fresh_packing(mods, dtype, freedom):
+  """persistent_observation=True: step() rewrites only the wall rows the appended rock
+  changed (srl_raster_incremental_rows -> srl_pack_rewards_rows_f32) in fixed buffers;
+  the observation equals the freshly packed one at every step, across partial resets
+  (new goals: every row stale) and new episodes."""
+  E, steps = 24, 6
+  a = _synthetic_env(mods, E, dtype, freedom, steps, rewarder='all')
+  b = _synthetic_env(mods, E, dtype, freedom, steps, rewarder='all',
+                     persistent_observation=True)
+  a.reset()
+  b.reset()
+  first = None
+  for k in range(steps - 1):
+    action = a.sample()
+    (oa, ra, ta), (ob, rb, tb) = a.step(action), b.step(action)
+    assert torch.equal(oa[0], ob[0]) and torch.equal(oa[1], ob[1])
+    for name in ra:
+      assert torch.equal(ra[name], rb[name])
+    if first is None:
+      first = ob[0]
+    assert ob[0].data_ptr() == first.data_ptr()          # the same buffer every step
+    rows = b.obs.wall_rows.cpu().numpy()
+    assert (rows[:, 0] >= 0).all() and (rows[:, 1] <= a.obs.geo.overhead_h).all()
+    assert (rows[:, 1] - rows[:, 0] < a.obs.geo.overhead_h).all()     # a rock, not the scene
+    if k == 1:
+      for env in (a, b):
+        env.reset(env_ids=[1, 5, E - 1])
+  a.reset()
+  b.reset()
+  action = a.sample()
+  (oa, _, _), (ob, _, _) = a.step(action), b.step(action)
+  assert torch.equal(oa[0], ob[0]) and torch.equal(oa[1], ob[1])
+
+
 def test_uint8_policy_scores_the_packed_observation(mods):
   """The planar uint8 cast HeightPolicy scores equals the channels of the packed
   uint8 observation (env.py:171-178), and its level is the quantised goal height."""
