@@ -11,6 +11,9 @@ if len(sys.argv) > 2:
   cmd += ['--kernel-name', 'regex:' + sys.argv[2]]
 txt = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
+# one section per captured launch (a "Kernel Name" row, the header, the SASS rows): the first
+starts = [k for k, r in enumerate(rows) if r and r[0] == 'Kernel Name'] or [0]
+rows = rows[starts[0]:(starts[1] if len(starts) > 1 else len(rows))]
 h = rows[1]
 ix = {n: i for i, n in enumerate(h)}
 L, tot, ops, sm = [], collections.Counter(), collections.Counter(), collections.Counter()
