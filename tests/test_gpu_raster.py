@@ -130,6 +130,46 @@ def test_sphere_underside_analytic(mods):
   assert np.all(m[rho2 > (radius + 0.125 / 32) ** 2] == 0)
 
 
+@pytest.mark.parametrize('n,seed', [(2, 0), (9, 1), (33, 2)])
+def test_tessellated_plane_analytic(mods, n, seed):
+  """Known answer that does not involve the oracle: a tilted plane z = c + a x + b y,
+  tessellated into 2 (n-1)^2 triangles with random diagonals, seen by the overhead
+  camera.  Every covered pixel (i, j) must hold the plane's height at its CENTRE
+  x = (i + 0.5) px, y = (j + 0.5) px to within the float32 rounding of the reference's
+  depth -> elevation formula (observer.py:259-260: three roundings at magnitude 1000,
+  1.5 x 2^-14 m) -- interpolation across triangle edges, pixel-centre sampling (half a
+  pixel off would be 6e-4 m here) and the elevation formula in one check.  The grid is
+  asymmetric on purpose: a pixel centre EXACTLY on a shared edge can be dropped by both
+  triangles (separately rounded float32 edge functions)."""
+  geo = mods['camera'].ObserverGeometry(128, 32, 0.125 / 32, 0.375)
+  rng = np.random.default_rng(seed)
+  a, b, c = 0.3, -0.17, 0.16
+  x0, x1, y0, y1 = 0.0813, 0.4191, 0.0779, 0.4233
+  X, Y = np.meshgrid(np.linspace(x0, x1, n), np.linspace(y0, y1, n), indexing='ij')
+  verts = np.stack([X, Y, c + a * X + b * Y], -1).reshape(-1, 3).astype('float32')
+  tris = []
+  for i in range(n - 1):
+    for j in range(n - 1):
+      p00, p01, p10, p11 = i * n + j, i * n + j + 1, (i + 1) * n + j, (i + 1) * n + j + 1
+      if rng.random() < 0.5:
+        tris += [(p00, p10, p11), (p00, p11, p01)]
+      else:
+        tris += [(p00, p10, p01), (p10, p11, p01)]
+  tris = np.asarray(tris, dtype='int32')
+  bodies = [(verts, tris, np.identity(3), np.zeros(3))]
+  m = _gpu_render(mods, bodies, geo.overhead_view, geo.overhead_projection, 128, 128,
+                  mods['capi'].RASTER_WALL, 0.375)
+  px = 0.125 / 32
+  ctr = (np.arange(128) + 0.5) * px
+  inx, iny = (ctr > x0 + px) & (ctr < x1 - px), (ctr > y0 + px) & (ctr < y1 - px)
+  want = c + a * ctr[:, None] + b * ctr[None, :]
+  err = np.abs(m - want)[np.ix_(inx, iny)].max()
+  assert err <= 1.5 * 2.0 ** -14 + 2e-6, err
+  # outside the plane: ground, exactly 0
+  assert np.all(m[ctr < x0 - px, :] == 0) and np.all(m[ctr > x1 + px, :] == 0)
+  assert np.all(m[:, ctr < y0 - px] == 0) and np.all(m[:, ctr > y1 + px] == 0)
+
+
 def test_drop_lands_lowest_point_on_floor(mods):
   """A rock rendered from below and max-plus-dropped on an empty floor rests
   with its lowest vertex at z = 0 (known-answer 2)."""

@@ -94,3 +94,35 @@ def test_contact_precheck_known_cases():
   rock3 = np.zeros((h, h), 'float32')
   rock3[2:6, 2:6] = np.float32(0.03)
   assert O.contact_precheck(wall, rock3, (5, 5))[0] == 16
+
+
+@pytest.mark.parametrize('n,seed', [(2, 0), (9, 1)])
+def test_oracle_zbuffer_renders_a_tessellated_plane_analytically(n, seed):
+  """The oracle z-buffer against an analytic known answer (the same scene as the GPU test
+  test_tessellated_plane_analytic): every covered pixel holds the plane's height at the
+  pixel centre to within the elevation formula's float32 rounding (1.5 x 2^-14 m)."""
+  from oracle import raster_np as R
+  from stackrl_b200 import camera
+  geo = camera.ObserverGeometry(128, 32, 0.125 / 32, 0.375)
+  rng = np.random.default_rng(seed)
+  a, b, c = 0.3, -0.17, 0.16
+  x0, x1, y0, y1 = 0.0813, 0.4191, 0.0779, 0.4233
+  X, Y = np.meshgrid(np.linspace(x0, x1, n), np.linspace(y0, y1, n), indexing='ij')
+  verts = np.stack([X, Y, c + a * X + b * Y], -1).reshape(-1, 3).astype('float32')
+  tris = []
+  for i in range(n - 1):
+    for j in range(n - 1):
+      p00, p01, p10, p11 = i * n + j, i * n + j + 1, (i + 1) * n + j, (i + 1) * n + j + 1
+      if rng.random() < 0.5:
+        tris += [(p00, p10, p11), (p00, p11, p01)]
+      else:
+        tris += [(p00, p10, p01), (p10, p11, p01)]
+  depth = R.render_depth(geo.overhead_view, geo.overhead_projection, 128, 128,
+                         [(verts, np.asarray(tris, dtype='int32'), np.identity(3), np.zeros(3))])
+  m = O.wall_elevation(depth, 0.375)
+  px = 0.125 / 32
+  ctr = (np.arange(128) + 0.5) * px
+  inx, iny = (ctr > x0 + px) & (ctr < x1 - px), (ctr > y0 + px) & (ctr < y1 - px)
+  want = c + a * ctr[:, None] + b * ctr[None, :]
+  assert np.abs(m - want)[np.ix_(inx, iny)].max() <= 1.5 * 2.0 ** -14 + 2e-6
+  assert np.all(m[ctr < x0 - px, :] == 0) and np.all(m[:, ctr > y1 + px] == 0)
