@@ -170,6 +170,32 @@ def test_tessellated_plane_analytic(mods, n, seed):
   assert np.all(m[:, ctr < y0 - px] == 0) and np.all(m[:, ctr > y1 + px] == 0)
 
 
+def test_rock_view_plane_analytic(mods):
+  """Rock view (the camera under the spawned rock, observer.py:262-293, with the column
+  mirror of :277): a tilted plane through the spawn point maps to object_z / 2 - (a x + b
+  y) at the pixel centres x = (i + 0.5 - 16) px, y = (j + 0.5 - 16) px, to within the
+  elevation formula's float32 rounding -- pins the axes and the mirror analytically."""
+  geo = mods['camera'].ObserverGeometry(128, 32, 0.125 / 32, 0.375)
+  spawn = ((0., 0., 0.5), (0., 0., 0., 1.))
+  a, b, n = 0.21, -0.13, 9
+  X, Y = np.meshgrid(np.linspace(-0.0571, 0.0593, n), np.linspace(-0.0589, 0.0577, n),
+                     indexing='ij')
+  verts = np.stack([X, Y, a * X + b * Y], -1).reshape(-1, 3).astype('float32')
+  tris = []
+  for i in range(n - 1):
+    for j in range(n - 1):
+      p00, p01, p10, p11 = i * n + j, i * n + j + 1, (i + 1) * n + j, (i + 1) * n + j + 1
+      tris += [(p00, p10, p11), (p00, p11, p01)] if (i + j) % 2 else \
+        [(p00, p10, p01), (p10, p11, p01)]
+  bodies = [(verts, np.asarray(tris, dtype='int32'), np.identity(3), np.array(spawn[0]))]
+  m = _gpu_render(mods, bodies, geo.object_view(spawn, 0), geo.object_projection, 32, 32,
+                  mods['capi'].RASTER_ROCK, geo.object_z)
+  ctr = (np.arange(32) + 0.5 - 16) * (0.125 / 32)
+  inside = np.abs(ctr) < 0.05
+  want = geo.object_z / 2 - (a * ctr[:, None] + b * ctr[None, :])
+  assert np.abs(m - want)[np.ix_(inside, inside)].max() <= 1.5 * 2.0 ** -14 + 2e-6
+
+
 def test_drop_lands_lowest_point_on_floor(mods):
   """A rock rendered from below and max-plus-dropped on an empty floor rests
   with its lowest vertex at z = 0 (known-answer 2)."""
