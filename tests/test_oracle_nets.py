@@ -68,3 +68,30 @@ def test_gradients_match_finite_differences():
     d = np.zeros_like(f)
     d[idx] = 1e-3
     assert abs((loss(x, f + d) - loss(x, f - d)) / 2e-3 - g1[idx]) < 1e-9
+
+
+@pytest.mark.parametrize('shape', [(2, 9, 11, 3, 4, 5), (3, 12, 7, 5, 2, 3)])
+def test_oracle_equals_an_independent_framework_conv2d_and_its_autograd(shape):
+  """TensorFlow is absent, PyTorch is not: torch.nn.functional.conv2d is, like
+  tf.nn.conv2d, a cross-correlation (no kernel flip), so `correlation(x, w)[b] =
+  conv2d(x[b] as NCHW, w[b] as one output channel)` is the layer of nets/layers.py:21-38
+  computed by an independent implementation -- and its autograd gives independent
+  gradients for the two inputs (what DQN.train back-propagates, nets/models.py:89, 182).
+  float64 on the CPU."""
+  import torch
+  B, H, W, C, h, w = shape
+  rng = np.random.default_rng(5)
+  x = rng.standard_normal((B, H, W, C)).astype('float32')
+  f = rng.standard_normal((B, h, w, C)).astype('float32')
+  g = rng.standard_normal((B, H - h + 1, W - w + 1, 1)).astype('float32')
+  xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+  ft = torch.tensor(f, dtype=torch.float64, requires_grad=True)
+  outs = [torch.nn.functional.conv2d(xt[b].permute(2, 0, 1)[None], ft[b].permute(2, 0, 1)[None])
+          for b in range(B)]
+  out = torch.cat(outs, 0).permute(0, 2, 3, 1)              # [B, Ph, Pw, 1]
+  np.testing.assert_allclose(nets_np.correlation(x, f), out.detach().numpy(), rtol=0,
+                             atol=1e-12)
+  (out * torch.tensor(g, dtype=torch.float64)).sum().backward()
+  gx, gf = nets_np.correlation_grads(x, f, g)
+  np.testing.assert_allclose(gx, xt.grad.numpy(), rtol=0, atol=1e-12)
+  np.testing.assert_allclose(gf, ft.grad.numpy(), rtol=0, atol=1e-12)
