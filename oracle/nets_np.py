@@ -11,7 +11,9 @@ filter, so  out[b,i,j,0] = sum_{u,v,c} in0[b,i+u,j+v,c] * in1[b,u,v,c].
 PARITY UNPINNED against TensorFlow itself: tensorflow is not installable in the
 build container and the reference holds no golden values for this layer; the
 restatement follows the published definition of conv2d above and is checked
-against scipy.signal.correlate2d (tests/test_oracle_nets.py).  Sums in float64.
+against scipy.signal.correlate2d and -- forward and both gradients -- against
+torch.nn.functional.conv2d + autograd, an independent framework's implementation of the
+same cross-correlation (tests/test_oracle_nets.py).  Sums in float64.
 """
 import numpy as np
 
