@@ -5,8 +5,10 @@
 // Both reference results come out of third-party library code (scipy's direct
 // sum, OpenCV's DFT / integral-image path) whose internal summation order is not
 // part of the reference tree, so these two maps are matched to a TOLERANCE
-// (1e-5 relative / 2e-5 absolute in the tests), not bit for bit: every window sum
-// is accumulated in float64 here and rounded once.
+// (1e-5 relative / 2e-5 absolute in the tests), not bit for bit.  corrcoef: every window
+// sum is accumulated in float64 and rounded once (variance and covariance cancel).
+// correlate alone: float32 FMAs over a rock row (scipy itself sums in float32), rows added
+// in float64.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -18,6 +20,7 @@ __device__ __forceinline__ float div_level(float x, float level) {
   return x == 0.f ? __fmul_rn(x, level) : __fdiv_rn(x, level);
 }
 
+template <bool COEF>
 __global__ void __launch_bounds__(128)
 correlate_kernel(const float* __restrict__ walls, const float* __restrict__ rocks,
                  const float* __restrict__ level, float* __restrict__ corr,
@@ -33,13 +36,16 @@ correlate_kernel(const float* __restrict__ walls, const float* __restrict__ rock
   const int rows_out = min(band, Ph - i0);
   const int rows_in = rows_out + h - 1;
   float* rock_s = reinterpret_cast<float*>(smem_raw);     // [h*h]
-  float* wall_s = rock_s + h * h;                         // [rows_in][W]
+  float* wall_s = rock_s + h * h;                         // [rows_in][Ws]
+  const int Ws = W | 1;      // odd row stride: consecutive rows fall into consecutive banks
   const int tid = threadIdx.x;
   const bool scaled = level != nullptr;
   const float g = scaled ? level[e] : 1.f;
   const float* wall = walls + ((size_t)e * H + i0) * W;
-  for (int k = tid; k < rows_in * W; k += blockDim.x)
-    wall_s[k] = scaled ? div_level(wall[k], g) : wall[k];
+  for (int k = tid; k < rows_in * W; k += blockDim.x) {
+    const int row = k / W, col = k - row * W;
+    wall_s[row * Ws + col] = scaled ? div_level(wall[k], g) : wall[k];
+  }
   const float* rock = rocks + ((size_t)e * R + r) * h * h;
   double sn = 0., snn = 0.;
   for (int k = tid; k < h * h; k += blockDim.x) {
@@ -63,13 +69,55 @@ correlate_kernel(const float* __restrict__ walls, const float* __restrict__ rock
   const double N = (double)h * h;
   const double n_var = snn - sn * sn / N;
 
+  if constexpr (!COEF) {
+    // `correlate` alone: the window sums of o and o^2 are not needed, and scipy's own
+    // correlate2d accumulates in float32.  Four adjacent outputs per thread share every rock
+    // value; a rock row is accumulated with float32 FMAs (h terms), rows are added in float64.
+    // (The last group of a row reads up to 3 floats past its window: inside wall_s, which is
+    // allocated 4 floats longer; those outputs are not stored.)
+    const int groups = (Pw + 3) / 4;
+    for (int item = tid; item < rows_out * groups; item += blockDim.x) {
+      // consecutive lanes = consecutive rows of one column group (conflict-free wall loads)
+      const int grp = item / rows_out, i = item - grp * rows_out, j0 = grp * 4;
+      double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+      for (int u = 0; u < h; ++u) {
+        const float* wr = wall_s + (i + u) * Ws + j0;
+        const float* rr = rock_s + u * h;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float w0 = wr[0], w1 = wr[1], w2 = wr[2];
+        int v = 0;
+        for (; v + 4 <= h; v += 4) {          // register window slides without moves
+          const float w3 = wr[v + 3], w4 = wr[v + 4], w5 = wr[v + 5], w6 = wr[v + 6];
+          const float n0 = rr[v], n1 = rr[v + 1], n2 = rr[v + 2], n3 = rr[v + 3];
+          a0 = fmaf(w0, n0, a0); a1 = fmaf(w1, n0, a1); a2 = fmaf(w2, n0, a2); a3 = fmaf(w3, n0, a3);
+          a0 = fmaf(w1, n1, a0); a1 = fmaf(w2, n1, a1); a2 = fmaf(w3, n1, a2); a3 = fmaf(w4, n1, a3);
+          a0 = fmaf(w2, n2, a0); a1 = fmaf(w3, n2, a1); a2 = fmaf(w4, n2, a2); a3 = fmaf(w5, n2, a3);
+          a0 = fmaf(w3, n3, a0); a1 = fmaf(w4, n3, a1); a2 = fmaf(w5, n3, a2); a3 = fmaf(w6, n3, a3);
+          w0 = w4; w1 = w5; w2 = w6;
+        }
+        for (; v < h; ++v) {
+          const float w3 = wr[v + 3], n = rr[v];
+          a0 = fmaf(w0, n, a0); a1 = fmaf(w1, n, a1); a2 = fmaf(w2, n, a2); a3 = fmaf(w3, n, a3);
+          w0 = w1; w1 = w2; w2 = w3;
+        }
+        s0 += (double)a0; s1 += (double)a1; s2 += (double)a2; s3 += (double)a3;
+      }
+      const size_t at = (((size_t)e * R + r) * Ph + i0 + i) * Pw + j0;
+      const float d = (float)sn;
+      const double sv[4] = {s0, s1, s2, s3};
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (j0 + t < Pw) corr[at + t] = (float)sv[t] / d;
+    }
+    return;
+  }
   for (int item = tid; item < rows_out * Pw; item += blockDim.x) {
     const int i = item / Pw, j = item % Pw;
-    const float* win = wall_s + i * W + j;
+    const float* win = wall_s + i * Ws + j;
     double son = 0., so = 0., soo = 0.;
     for (int u = 0; u < h; ++u)
       for (int v = 0; v < h; ++v) {
-        const double o = (double)win[u * W + v];
+        const double o = (double)win[u * Ws + v];
         son += o * (double)rock_s[u * h + v];
         so += o;
         soo += o * o;
@@ -102,7 +150,9 @@ int correlate_f32(const float* walls, const float* rocks, const float* level, fl
   const int Ph = H - h + 1;
   const int sms = sm_count();
   SRL_REQUIRE(sms > 0, SRL_E_CUDA, "correlate: no CUDA device");
-  auto smem_for = [&](int band) { return (size_t)4 * h * h + (size_t)4 * (band + h - 1) * W; };
+  auto smem_for = [&](int band) {
+    return (size_t)4 * h * h + (size_t)4 * (band + h - 1) * (W | 1) + 16;      // + the 4-float overrun
+  };
   int band = Ph;
   while (band > 1 && ((size_t)E * R * ((Ph + band - 1) / band) < (size_t)2 * sms ||
                       smem_for(band) > 100 * 1024))
@@ -111,10 +161,17 @@ int correlate_f32(const float* walls, const float* rocks, const float* level, fl
               "correlate: %d-column wall rows with a %d-row rock exceed shared memory", W, h);
   const int nbands = (Ph + band - 1) / band;
   const size_t smem = smem_for(band);
-  SRL_CUDA(cudaFuncSetAttribute(correlate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-  correlate_kernel<<<E * R * nbands, 128, smem, stream>>>(walls, rocks, level, corr, coef, R, H,
-                                                         W, h, band, nbands);
+  if (coef) {
+    SRL_CUDA(cudaFuncSetAttribute(correlate_kernel<true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    correlate_kernel<true><<<E * R * nbands, 128, smem, stream>>>(walls, rocks, level, corr, coef,
+                                                                 R, H, W, h, band, nbands);
+  } else {
+    SRL_CUDA(cudaFuncSetAttribute(correlate_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    correlate_kernel<false><<<E * R * nbands, 128, smem, stream>>>(walls, rocks, level, corr,
+                                                                  coef, R, H, W, h, band, nbands);
+  }
   return check_launch("correlate_kernel");
 }
 

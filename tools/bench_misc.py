@@ -38,8 +38,10 @@ def main():
     wts = capi.difference_weights(rd, ld)
     ms = timeit(lambda: capi.difference_f32(wd, rd, ld, wts), 5)
     print('%-10s difference   %8.3f ms  %.3e evals/s' % (name, ms, evals / ms * 1e3))
-    ms = timeit(lambda: capi.correlate_f32(wd, rd, ld), 5)
+    ms = timeit(lambda: capi.correlate_f32(wd, rd, ld, want_coef=False), 5)
     print('%-10s correlate    %8.3f ms  %.3e evals/s' % (name, ms, evals / ms * 1e3))
+    ms = timeit(lambda: capi.correlate_f32(wd, rd, ld, want_corr=False), 5)
+    print('%-10s corrcoef     %8.3f ms  %.3e evals/s' % (name, ms, evals / ms * 1e3))
     ms = timeit(lambda: capi.maxplus_f32(wd, rd, ld))
     print('%-10s maxplus_f32  %8.3f ms  %.3e evals/s' % (name, ms, evals / ms * 1e3))
 
