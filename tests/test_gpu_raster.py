@@ -685,6 +685,40 @@ def test_discounted_rewards_and_settle_hook_moving_every_rock(mods):
     assert torch.equal(walls, env.obs.walls)
 
 
+def test_persistent_observation_with_a_settle_hook(mods):
+  """A settle hook that moves the new rock only (appended image, a few rows rewritten) or
+  every rock (whole-scene redraw: srl_raster_incremental_rows reports all rows): the
+  persistent observation still equals the freshly packed one."""
+  E, steps = 6, 4
+  for move_all in (False, True):
+    envs_ = []
+    for persistent in (False, True):
+      rng = np.random.default_rng(3)
+      rest = [[] for _ in range(E)]
+
+      def settle(mesh_ids, positions, quats, rng=rng, rest=rest):
+        new = np.concatenate([positions + rng.normal(scale=0.003, size=positions.shape), quats], 1)
+        for e in range(E):
+          rest[e] = [p + (np.r_[rng.normal(scale=0.001, size=3), np.zeros(4)] if move_all
+                          else 0.) for p in rest[e]] + [new[e]]
+        if move_all:
+          return new[:, :3], new[:, 3:], np.stack([np.stack(rest[e]) for e in range(E)])
+        return new[:, :3], new[:, 3:]
+
+      env = _synthetic_env(mods, E, steps=steps, settle=settle,
+                           persistent_observation=persistent)
+      env.reset()
+      envs_.append(env)
+    a, b = envs_
+    for _ in range(steps):
+      action = a.sample()
+      (oa, ra, _), (ob, rb, _) = a.step(action), b.step(action)
+      assert torch.equal(oa[0], ob[0]) and torch.equal(oa[1], ob[1]) and torch.equal(ra, rb)
+      rows = b.obs.wall_rows.cpu().numpy()
+      H = a.obs.geo.overhead_h
+      assert ((rows[:, 1] - rows[:, 0] == H).all()) == (move_all and len(rows) > 0)
+
+
 def test_incremental_wall_image_equals_the_full_redraw(mods):
   """A step draws only the appended rock onto the kept depth image
   (srl_raster_incremental); re-drawing every placed rock gives the same bits."""
