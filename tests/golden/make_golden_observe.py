@@ -17,7 +17,10 @@ from oracle import fake_pybullet, refload
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _episode(ns, fb, env_cls, urdfs, dtype, steps, policy_kwargs, out, prefix, **env_kwargs):
+def _episode(ns, fb, env_cls, urdfs, dtype, steps, policy_kwargs, out, prefix, light=False,
+             **env_kwargs):
+  """``light``: a long episode (C1: 30 steps) keeps the packed observations, actions, poses
+  and rewards of every step but not the float maps and depth images."""
   depth_log = []
   real = fb.getCameraImage
 
@@ -39,13 +42,14 @@ def _episode(ns, fb, env_cls, urdfs, dtype, steps, policy_kwargs, out, prefix, *
   done = False
   while not done:
     m, n = env._obs.state
-    out['{}/s{}/overhead_map'.format(prefix, k)] = np.array(m)
-    out['{}/s{}/object_map'.format(prefix, k)] = np.array(n)
     out['{}/s{}/obs0'.format(prefix, k)] = obs[0]
     out['{}/s{}/obs1'.format(prefix, k)] = obs[1]
-    out['{}/s{}/depths'.format(prefix, k)] = np.concatenate(
-      [d.ravel() for d in depth_log]) if depth_log else np.zeros(0, 'float32')
-    out['{}/s{}/depth_shapes'.format(prefix, k)] = np.array([d.shape for d in depth_log])
+    if not light:
+      out['{}/s{}/overhead_map'.format(prefix, k)] = np.array(m)
+      out['{}/s{}/object_map'.format(prefix, k)] = np.array(n)
+      out['{}/s{}/depths'.format(prefix, k)] = np.concatenate(
+        [d.ravel() for d in depth_log]) if depth_log else np.zeros(0, 'float32')
+      out['{}/s{}/depth_shapes'.format(prefix, k)] = np.array([d.shape for d in depth_log])
     del depth_log[:]
     a, v = pol(obs)
     if isinstance(a, tuple):
@@ -67,8 +71,9 @@ def _episode(ns, fb, env_cls, urdfs, dtype, steps, policy_kwargs, out, prefix, *
   m, n = env._obs.state
   out['{}/s{}/overhead_map'.format(prefix, k)] = np.array(m)
   out['{}/s{}/obs0'.format(prefix, k)] = obs[0]
-  out['{}/s{}/depths'.format(prefix, k)] = np.concatenate([d.ravel() for d in depth_log])
-  out['{}/s{}/depth_shapes'.format(prefix, k)] = np.array([d.shape for d in depth_log])
+  if not light:
+    out['{}/s{}/depths'.format(prefix, k)] = np.concatenate([d.ravel() for d in depth_log])
+    out['{}/s{}/depth_shapes'.format(prefix, k)] = np.array([d.shape for d in depth_log])
   out[prefix + '/n_recorded'] = np.int64(k)
   fb.getCameraImage = real
   env.close()
@@ -151,6 +156,12 @@ def main(ns=None):
     del loaded[:]
     _episode(ns, fb, cls, urdfs, dtype, steps, pk, out, prefix, **ek)
     out[prefix + '/urdf_order'] = np.array([n[:-5] for n in loaded])
+  # C1 (BASELINE config 1): the registered Stack-v0 defaults -- uint8 observations, 128x128
+  # wall, 32x32 rock, 30 rocks per episode (env.py:20) -- with Baseline('height'); 30 > 8
+  # meshes, so the episode list is drawn with replacement (env.py:268-272).
+  del loaded[:]
+  _episode(ns, fb, ns.env.StackEnv, urdfs, 'uint8', 30, {}, out, 'c1_stack_v0_30', light=True)
+  out['c1_stack_v0_30/urdf_order'] = np.array([n[:-5] for n in loaded])
   path = os.path.join(HERE, 'observe.npz')
   np.savez_compressed(path, **out)
   print('observe.npz: {} arrays, {:.0f} KB'.format(len(out), os.path.getsize(path) / 1024))

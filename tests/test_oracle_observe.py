@@ -76,6 +76,29 @@ def test_iou_and_or_rewards(observe_golden, name):
       assert r == want[col], (k, metric)
 
 
+def test_c1_stack_v0_episode_actions_and_final_packing(observe_golden):
+  """BASELINE config 1: the 30-rock Stack-v0 episode (uint8 observations) of the unmodified
+  reference.  The oracle's height policy picks the recorded action from every recorded
+  observation, the final wall packs to the recorded observation, and the 30 step rewards
+  telescope to the final wall's IoU / occupation ratio."""
+  g = observe_golden
+  name = 'c1_stack_v0_30'
+  assert int(g[name + '/n_recorded']) == 30
+  for k in range(30):
+    key = '{}/s{}'.format(name, k)
+    a, _ = S.baseline_call((g[key + '/obs0'], g[key + '/obs1']), method='height')
+    assert a == int(g[key + '/action']), k
+  wall = g[name + '/s30/overhead_map']
+  obs = O.pack_obs(wall, g[name + '/goal'], np.zeros((32, 32), 'float32'), 'uint8',
+                   GEOM['max_z'], GEOM['object_max_dimension'])
+  assert np.array_equal(obs[0], g[name + '/s30/obs0'])
+  tot_iou = sum(float(g['{}/s{}/rewards'.format(name, k)][0]) for k in range(30))
+  tot_or = sum(float(g['{}/s{}/rewards'.format(name, k)][1]) for k in range(30))
+  _, iou = O.reward(wall, g[name + '/goal'], GEOM['goal_z'], 'iou', 0.)
+  _, occ = O.reward(wall, g[name + '/goal'], GEOM['goal_z'], 'or', 0.)
+  assert abs(tot_iou - iou) < 1e-12 and abs(tot_or - occ) < 1e-12
+
+
 def test_contact_precheck_known_cases():
   """The heightmap contact pre-check on configurations with a known answer."""
   h = 8
