@@ -526,7 +526,9 @@ class BatchedObserver(object):
                 inst_counts=self.counts, depth_state=self._wall_depth,
                 only_last=2 if last else 0,       # walls still holds the kept image
                 rows_out=self.wall_rows,
-                max_cached_verts=max(256, self._max_verts) if last else
+                # (the true mesh size: up to 128 vertices the appended rock is drawn by the
+                # warp-per-image kernel)
+                max_cached_verts=self._max_verts if last else
                 min(2048, max(256, self._max_verts * self.cap)))
     self._wall_depth_valid = True
     return self.walls

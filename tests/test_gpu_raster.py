@@ -944,3 +944,95 @@ def test_gpu_camera_returns_the_recorded_depth_images(mods, observe_golden):
         projectionMatrix=geo.object_projection)
       assert np.array_equal(depth, depths[1 + r])
     placed.append(body(order[k], g[key + '/pose_position'], g[key + '/pose_orientation']))
+
+
+@pytest.mark.parametrize('mode_name', ['RASTER_DEPTH', 'RASTER_WALL', 'RASTER_ROCK'])
+def test_warp_per_image_kernel_equals_cta_kernel_and_redraw(mods, monkeypatch, mode_name):
+  """The in-place incremental image of a small mesh is drawn by one warp per image into a
+  window of the image (raster_warp_kernel).  Same state, image and reported rows as the
+  CTA-per-image kernel (SRL_RASTER_WARP=0) and as re-drawing the whole scene, and the
+  depth state is the oracle's -- for small rocks, a slab wider than one window pass (several
+  passes by rows and columns), a rock half outside the image, a mesh too big for the warp's
+  vertex cache (uncached path), a vertex far outside the image (window = whole image),
+  jobs without instances, and a job count that does not fill the last CTA."""
+  capi, obs_mod, meshes = mods['capi'], mods['observer'], mods['meshes']
+  mode = getattr(capi, mode_name)
+  geo = mods['camera'].ObserverGeometry(96, 32, 0.125 / 32, 0.375)
+  rows = cols = 96
+  rng = np.random.default_rng(11)
+  small_v, small_t = meshes.synthetic_rocks(3, 40, 1, max_dimension=0.06)     # 42 vertices
+  big_v, big_t = meshes.synthetic_rocks(4, 2, 3, max_dimension=0.1)           # 642 vertices
+  box_t = np.array([[0, 1, 2], [0, 2, 3], [4, 6, 5], [4, 7, 6], [0, 4, 5], [0, 5, 1],
+                    [1, 5, 6], [1, 6, 2], [2, 6, 7], [2, 7, 3], [3, 7, 4], [3, 4, 0]], 'int32')
+  def box(hx, hy, hz):
+    return np.array([[sx * hx, sy * hy, sz * hz] for sz in (-1, 1)
+                     for sx, sy in ((-1, -1), (1, -1), (1, 1), (-1, 1))], 'float32')
+  def pose(lo=0.06, hi=0.31):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    return R.quat_matrix(q), np.array([rng.uniform(lo, hi), rng.uniform(lo, hi),
+                                       rng.uniform(0.03, 0.3)])
+  scenes = []
+  for k in range(37):
+    n = int(rng.integers(0, 5))
+    bodies = [(small_v[int(rng.integers(40))], small_t) + pose() for _ in range(n)]
+    scenes.append(bodies)
+  eye = np.identity(3)
+  scenes[3] = scenes[3][:1] + [(box(0.16, 0.15, 0.01), box_t, eye, np.array([.19, .19, .2]))]
+  scenes[5] = [(box(0.02, 0.17, 0.02), box_t) + (pose()[0], np.array([.19, .19, .1]))]
+  scenes[8] = scenes[8][:2] + [(small_v[0], small_t, eye, np.array([0.37, 0.005, 0.1]))]
+  scenes[13] = scenes[13][:1] + [(big_v[1], big_t) + pose()]
+  far_vertex = small_v[1].copy()
+  far_vertex[0] = [5.0e8, 0., 0.01]                       # projects beyond |1e9| px
+  scenes[21] = [(far_vertex, small_t, eye, np.array([.2, .2, .1]))]
+  scenes[30] = []
+  bodies_all, begin = [], []
+  for s in scenes:
+    begin.append(len(bodies_all))
+    bodies_all += s
+  verts, tris, inst = obs_mod._instances(bodies_all)
+  jobs = np.zeros(len(scenes), dtype=capi.JOB_DTYPE)
+  jobs['view'], jobs['proj'] = geo.overhead_view, geo.overhead_projection
+  jobs['inst_begin'] = begin
+  jobs['inst_count'] = [len(s) for s in scenes]
+  jobs['zrange'] = 0.375
+  dev = torch.device('cuda')
+  verts_d, tris_d = torch.from_numpy(verts).to(dev), torch.from_numpy(tris).to(dev)
+  counts = torch.tensor([len(s) for s in scenes], dtype=torch.int32, device=dev)
+  before = (counts - 1).clamp(min=0)
+
+  def run(inst_counts, only_last, state, out, rows_out, hint):
+    capi.raster(verts_d, tris_d, inst, jobs, rows, cols, mode, out=out, inst_counts=inst_counts,
+                depth_state=state, only_last=only_last, rows_out=rows_out, max_cached_verts=hint)
+    torch.cuda.synchronize()
+  shape = (len(scenes), rows, cols)
+  state0 = torch.empty(shape, dtype=torch.float32, device=dev)
+  out0 = torch.empty(shape, dtype=torch.float32, device=dev)
+  rows0 = torch.zeros((len(scenes), 2), dtype=torch.int32, device=dev)
+  run(before, 0, state0, out0, rows0, 2048)               # every instance but the last
+  results = []
+  for warp in ('1', '0'):
+    monkeypatch.setenv('SRL_RASTER_WARP', warp)
+    state, out, r = state0.clone(), out0.clone(), torch.zeros_like(rows0)
+    run(counts, 2, state, out, r, 64)
+    results.append((state, out, r))
+  monkeypatch.delenv('SRL_RASTER_WARP')
+  for a, b in zip(results[0], results[1]):
+    assert torch.equal(a, b)
+  full_state, full_out = torch.empty_like(state0), torch.empty_like(out0)
+  run(counts, 0, full_state, full_out, torch.zeros_like(rows0), 2048)
+  assert torch.equal(results[0][0], full_state)
+  assert torch.equal(results[0][1], full_out)
+  changed = (full_state != state0).any(dim=2).cpu().numpy()
+  r = results[0][2].cpu().numpy()
+  for k in range(len(scenes)):
+    idx = np.nonzero(changed[k])[0]
+    if len(idx):
+      assert r[k, 0] <= idx[0] and idx[-1] < r[k, 1], k
+    if not scenes[k]:
+      assert r[k, 0] >= r[k, 1]
+  assert tuple(r[21]) == (0, rows) and r[3, 1] - r[3, 0] > 70 and changed.sum() > 300
+  if mode == capi.RASTER_DEPTH:
+    for k in (3, 5, 8, 13, 17, 21, 30):
+      want = R.render_depth(geo.overhead_view, geo.overhead_projection, rows, cols, scenes[k])
+      assert np.array_equal(full_state[k].cpu().numpy(), want), k
