@@ -531,6 +531,27 @@ mask_select_kernel(const V* __restrict__ values, const In* __restrict__ walls,
 // IADD with no footprint traffic, and all eight warps work on all views at once.
 // GEO = (H << 20 | W << 10 | h) << 6 | R fixes the geometry at compile time (0:
 // run-time geometry from the parameters): all index arithmetic folds.
+// Order-preserving float -> uint key (-0 and +0 share a key) and back.
+__device__ __forceinline__ uint32_t ord_key(float v) {
+  const uint32_t b = __float_as_uint(__fadd_rn(v, 0.f));
+  return b ^ ((b >> 31) != 0u ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ uint32_t ord_key(double) { return 0u; }      // (float maps only)
+__device__ __forceinline__ float ord_val(uint32_t k) {
+  return __uint_as_float(k ^ ((k >> 31) != 0u ? 0x80000000u : 0xffffffffu));
+}
+// Arg-min candidate of the whole warp: smallest value, then smallest index (what the
+// shuffle rounds of take() give), in every lane.
+template <typename V>
+__device__ __forceinline__ void warp_cand_redux(Cand<V>& c) {
+  const uint32_t key = c.idx >= 0 ? ord_key(c.v) : 0xffffffffu;
+  const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+  const uint32_t imin = __reduce_min_sync(
+      0xffffffffu, (c.idx >= 0 && key == kmin) ? (uint32_t)c.idx : 0x7fffffffu);
+  c.idx = imin == 0x7fffffffu ? -1 : (int)imin;
+  c.v = (V)ord_val(kmin);
+}
+
 template <typename V, typename In, int M, int NG, long long GEO = 0>
 __global__ void __launch_bounds__(kSelThreads)
 mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ walls,
@@ -641,18 +662,43 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
   }
   __syncthreads();
   }
-  // one warp per wall row, lanes along the output columns: no index division, and the
-  // two words of a window are the same (or neighbouring) words for the whole warp
-  for (int row = warp; row < H; row += NW) {
-    for (int j = lane; j < Pw; j += 32) {
-      const uint32_t* b = below + row * g_nW + (j >> 5);
-      uint32_t packed = 0;
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        if (s < g_pf && row + s < H)
-          packed |= (__funnelshift_r(b[s * g_nW], b[s * g_nW + 1], j & 31) & hmask) << (s * g_hb);
+  // Row-packed windows win[row][j] = x(row) | x(row + 1) << hb | ... (pf rows per word), where
+  // x(row) is the h-bit window of wall row `row` at column j.  A thread walks down one
+  // column segment and slides the packed word (x(row) is extracted once, not once per packed
+  // word it is part of); the threads of a warp are consecutive columns, so the two words of a
+  // window are the same (or neighbouring) words for the whole warp and the stores are dense.
+  const int nseg = kSelThreads / Pw;
+  if (nseg > 0) {
+    const int seglen = (H + nseg - 1) / nseg;
+    const int seg = tid / Pw, j = tid - seg * Pw;
+    const int r_lo = seg * seglen, r_hi = min(H, r_lo + seglen);
+    if (seg < nseg && r_lo < r_hi) {
+      const uint32_t* b = below + (j >> 5);
+      const int sh = j & 31, top = (g_pf - 1) * g_hb;
+      auto x = [&](int row) -> uint32_t {
+        return row < H ? __funnelshift_r(b[row * g_nW], b[row * g_nW + 1], sh) & hmask : 0u;
+      };
+      uint32_t acc = 0;
+      for (int s2 = 0; s2 + 1 < g_pf; ++s2) acc |= x(r_lo + s2) << ((s2 + 1) * g_hb);
+      for (int row = r_lo; row < r_hi; ++row) {
+        const uint32_t in = x(row + g_pf - 1);
+        acc = g_pf == 1 ? in : ((acc >> g_hb) | (in << top));
+        win[row * Pw + j] = acc;
       }
-      win[row * Pw + j] = packed;
+    }
+  } else {
+    // (more output columns than threads: one warp per wall row, lanes along the columns)
+    for (int row = warp; row < H; row += NW) {
+      for (int j = lane; j < Pw; j += 32) {
+        const uint32_t* b = below + row * g_nW + (j >> 5);
+        uint32_t packed = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          if (s < g_pf && row + s < H)
+            packed |= (__funnelshift_r(b[s * g_nW], b[s * g_nW + 1], j & 31) & hmask) << (s * g_hb);
+        }
+        win[row * Pw + j] = packed;
+      }
     }
   }
   __syncthreads();
@@ -720,7 +766,18 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
         }
       }
     }
-    for (int o = RCH; o < 32; o <<= 1) {
+    if constexpr (sizeof(V) == 4) {
+      // one view per warp pass (every single-view geometry): the three reductions over the
+      // lanes are REDUX on order-preserving integer keys instead of five shuffle rounds each
+      if (RCH == 1) {
+        warp_cand_redux(bmin);
+        warp_cand_redux(bmask);
+        const uint32_t kmax = __reduce_max_sync(0xffffffffu, any ? ord_key(vm) : 0u);
+        any = kmax != 0u;
+        vm = any ? ord_val(kmax) : V(0);
+      }
+    }
+    for (int o = (sizeof(V) == 4 && RCH == 1) ? 32 : RCH; o < 32; o <<= 1) {
       const V xv = __shfl_xor_sync(0xffffffffu, bmin.v, o);
       const int xi = __shfl_xor_sync(0xffffffffu, bmin.idx, o);
       if (xi >= 0) take(bmin, xv, xi);
