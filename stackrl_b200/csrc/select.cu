@@ -210,7 +210,12 @@ __device__ __forceinline__ void stage_bytes(void* dst, const void* src, size_t n
 // (dst = base16 + (src & 15)): head and tail element-wise, the body as 16-byte vectors
 // whatever the alignment of src (a [E, P] map with odd P starts 4, 8 or 12 bytes off
 // for three environments in four).  base16 must have 16 spare bytes.  Returns dst.
-template <typename T>
+// kAsync: the body travels as cp.async copies that the caller waits for (stage_wait(), then
+// a barrier) before the first read -- the copy overlaps whatever the block does until then.
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+template <typename T, bool kAsync = false>
 __device__ __forceinline__ T* stage_phased(void* base16, const T* src, size_t count, int tid,
                                            int nthreads) {
   const int phase = (int)(reinterpret_cast<uintptr_t>(src) & 15);
@@ -222,8 +227,16 @@ __device__ __forceinline__ T* stage_phased(void* base16, const T* src, size_t co
   for (size_t k = tid; k < head; k += nthreads) dst[k] = src[k];
   const int4* s4 = reinterpret_cast<const int4*>(src + head);
   int4* d4 = reinterpret_cast<int4*>(dst + head);
+  if constexpr (kAsync) {
+    for (int k = tid; k < (int)n4; k += nthreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(d4 + k)),
+                   "l"(s4 + k)
+                   : "memory");
+  } else {
 #pragma unroll 4
-  for (int k = tid; k < (int)n4; k += nthreads) d4[k] = __ldg(s4 + k);
+    for (int k = tid; k < (int)n4; k += nthreads) d4[k] = __ldg(s4 + k);
+  }
   for (size_t k = head + body + tid; k < count; k += nthreads) dst[k] = src[k];
   return dst;
 }
@@ -601,8 +614,10 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
     // Every thread turns 4 consecutive pixels into 4 bits and ORs them into the
     // packed word; only the score maps are staged in shared memory.
     for (int k = tid; k < H * g_nW + R * g_ng; k += kSelThreads) below[k] = 0u;
+    // (asynchronously: the score maps are first read after the overlap counts)
     if (q.stage_values)
-      vals = stage_phased(vals, values + (size_t)e * R * P, (size_t)R * P, tid, kSelThreads);
+      vals = stage_phased<V, true>(vals, values + (size_t)e * R * P, (size_t)R * P, tid,
+                                   kSelThreads);
     if (tid < 32) s_cmax[tid] = 0;
     __syncthreads();
     const In* wsrc = walls + (size_t)e * H * W;
@@ -739,6 +754,7 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
     }
     for (int o = RCH; o < 32; o <<= 1) cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, o));
     if (qpos == 0) atomicMax(s_cmax + rl, cm);
+    stage_wait();
     __syncthreads();
 
     // ---- mask cut, masked maximum, arg-min candidates ------------------------------- //
