@@ -920,10 +920,12 @@ int launch(const MaxPlusParams& p, bool staged, int blocks, int threads, size_t 
 
 }  // namespace
 
+constexpr int kStreamNotTaken = 1;   // stream_only: the call does not fit the stream kernel
+
 static int maxplus_f32_impl(const float* walls, const float* rocks, const float* level,
                             float* out, int E, int R, int H, int W, int h, float threshold,
                             int variant, int quantum_log2, int forced_T,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, bool stream_only = false) {
   SRL_REQUIRE(E >= 0 && R >= 1 && h >= 1 && H >= h && W >= h, SRL_E_INVALID,
               "maxplus_f32: bad shape E=%d R=%d H=%d W=%d h=%d", E, R, H, W, h);
   if (E == 0) return SRL_OK;
@@ -955,6 +957,23 @@ static int maxplus_f32_impl(const float* walls, const float* rocks, const float*
         c.T = t;
         tile_fixed = true;
       }
+  }
+  // The widest tile with 16-column chunks is outside choose_tile's register budget (the
+  // staged / direct kernels), but the stream kernel's consumers hold it: where it wastes fewer
+  // columns (49 output columns are two strips of 25 instead of three of 17: config 4, 1.60 ->
+  // 1.56 ms) the stream kernel is tried with it first.
+  if (!tile_fixed && !stream_only && c.VC == 16 && c.T != 25) {
+    auto cost_of = [&](int TT) {
+      const double waste = (double)strips_for(p.Pw, TT) * TT / p.Pw;
+      const double loads = ((TT + c.VC + 2) / 4 + c.VC / 2) / (double)(TT * c.VC);
+      return waste * (1.03 + loads);
+    };
+    if (cost_of(25) < 0.985 * cost_of(c.T) &&
+        (long long)E * R * strips_for(p.Pw, 25) * p.Ph >= (long long)sms * 256) {
+      const int rc = maxplus_f32_impl(walls, rocks, level, out, E, R, H, W, h, threshold,
+                                      variant, quantum_log2, 25, stream, true);
+      if (rc != kStreamNotTaken) return rc;
+    }
   }
   const int T = c.T, VC = c.VC;
   const int paired = variant != 0;   // 0: FADD + FMNMX, 1: FADD2 + FMNMX3 (default)
@@ -1074,6 +1093,7 @@ static int maxplus_f32_impl(const float* walls, const float* rocks, const float*
 #undef SRL_MP_CASE
     }
   }
+  if (stream_only) return kStreamNotTaken;
 
   int G = 1, RC = R, blocks, threads;
   size_t smem;

@@ -260,7 +260,8 @@ def _quantised_batch(seed, E, R, H, W, h, qlog2=-14, wall_top=0.3):
 
 
 @pytest.mark.parametrize('shape', [(64, 8, 32, 32, 16), (700, 8, 32, 32, 16), (150, 2, 64, 64, 16),
-                                   (33, 3, 48, 40, 8)])
+                                   (33, 3, 48, 40, 8),
+                                   (450, 1, 64, 64, 16)])   # config-4 geometry, wide-tile batch
 def test_fixed_point_sweep_is_bit_exact(capi, shape):
   """srl_maxplus_f32_q: quantised heightmaps with a power-of-two level are swept
   in 16-bit fixed point (VIADDMNMX.S16x2) -- same bits as numpy's float32."""
@@ -273,6 +274,25 @@ def test_fixed_point_sweep_is_bit_exact(capi, shape):
   pick = np.random.default_rng(2).choice(E, min(E, 40), replace=False)
   want = _numpy_maps(walls[pick], rocks[pick], level[pick])
   assert np.array_equal(got[torch.from_numpy(pick).to(dev)].cpu().numpy(), want)
+
+
+def test_wide_tile_of_the_stream_kernel_equals_the_default_tile(capi, monkeypatch):
+  """49 output columns (config 4): a batch big enough for the stream kernel is swept with two
+  strips of 25 columns instead of three of 17 -- same bits as the forced 17-column tile, float
+  and fixed-point sweeps."""
+  dev = torch.device('cuda')
+  walls, rocks, level = _quantised_batch(9, 600, 1, 64, 64, 16)
+  fw, fr, _ = synth.placement_batch(10, 600, 1, 64, 64, 16)
+  walls[::3], rocks[::3] = fw[::3], fr[::3]              # a third of the batch is not quantised
+  args = [torch.from_numpy(x).to(dev) for x in (walls, rocks, level)]
+  got_q, got_f = capi.maxplus_f32(*args, quantum_log2=-14), capi.maxplus_f32(*args)
+  monkeypatch.setenv('SRL_MP_T', '17')
+  assert torch.equal(got_q, capi.maxplus_f32(*args, quantum_log2=-14))
+  assert torch.equal(got_f, capi.maxplus_f32(*args))
+  assert torch.equal(got_q, got_f)
+  pick = np.arange(0, 600, 25)
+  assert np.array_equal(got_q[torch.from_numpy(pick).to(dev)].cpu().numpy(),
+                        _numpy_maps(walls[pick], rocks[pick], level[pick]))
 
 
 def test_fixed_point_sweep_falls_back_per_environment(capi):
