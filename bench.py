@@ -1012,6 +1012,56 @@ def c1_reference_episode():
                   'camera: pybullet is not installable here'}
 
 
+def c1_gpu_episode(torch, dev):
+  """The same configuration on this repo's path: BatchedStackEnv at the Stack-v0 defaults
+  (128x128 wall, 32x32 rock, uint8 observations, 30 rocks, reward_params=2) + HeightPolicy,
+  for config.gin's n_parallel = 2 environments and for a batch of 256 -- one warm-up episode,
+  then one timed episode on the host clock (the small case is launch-latency bound: seven
+  kernels and no device->host read per step).  Rocks: the reference's generated set where it
+  is staged (data files only), else synthetic ones."""
+  import glob
+  from stackrl_b200 import envs, meshes
+  d = os.path.join(ROOT, 'oracle', '_ref', 'stackrl', 'envs', 'data', 'generated')
+  urdfs = sorted(glob.glob(os.path.join(d, '[5-9]?_*.urdf')))
+  if urdfs:
+    bank = meshes.MeshBank.from_urdfs(urdfs)
+    rocks = '{} reference rocks ([5-9]?_*.urdf)'.format(len(bank))
+  else:
+    bank = meshes.MeshBank()
+    v, t = meshes.synthetic_rocks(5, 64, 1, max_dimension=0.12)
+    for k in range(64):
+      bank.add(v[k], t)
+    rocks = '64 synthetic rocks of 80 triangles'
+  out = {'workload': 'C1: Stack-v0 defaults (128x128 wall, 32x32 rock, uint8, 30 rocks), '
+                     'HeightPolicy, one episode', 'rocks': rocks, 'runs': []}
+  for E in (2, 256):
+    env = envs.BatchedStackEnv(bank, E, episode_length=30, reward_params=2, dtype='uint8',
+                               seed=11, device=dev)
+    policy = envs.HeightPolicy()
+    for timed in (False, True):
+      env.reset()
+      torch.cuda.synchronize()
+      t0 = time.perf_counter()
+      total = torch.zeros(E, dtype=torch.float64, device=dev)
+      steps, done = 0, False
+      while not done:
+        obs, reward, terminal = env.step(policy(env))
+        total += reward
+        steps += 1
+        done = steps >= 30
+      ret = total.cpu().numpy()                      # the one device->host read of the episode
+      dt = time.perf_counter() - t0
+    assert bool(terminal.all())
+    out['runs'].append({'envs': E, 'steps': steps, 'seconds': dt,
+                        'env_steps_per_s': steps * E / dt, 'ms_per_step': 1e3 * dt / steps,
+                        'placement_evals_per_s': steps * E * 97 * 97 / dt,
+                        'mean_episode_return': float(ret.mean()),
+                        # environment 0 is seeded like the reference run below (seed 11): same
+                        # rock order, goal and static physics, so the same episode
+                        'episode_return_env0': float(ret[0])})
+  return out
+
+
 # --------------------------------------------------------------------------- #
 def run_graft(args, rank, local_rank, world):
   su = Setup(args, rank, local_rank, world)
@@ -1033,6 +1083,10 @@ def run_graft(args, rank, local_rank, world):
       head['extra'] = extra_metrics(su.torch, su.dev, cpu_baseline=not args.no_cpu_baseline)
     except Exception as exc:   # the headline must survive a failure of the extras
       head['extra'] = {'error': repr(exc)}
+    try:
+      head['extra']['c1_gpu_episode'] = c1_gpu_episode(su.torch, su.dev)
+    except Exception as exc:
+      head['extra']['c1_gpu_episode'] = {'error': repr(exc)}
     if not args.no_cpu_baseline:
       try:
         head['extra']['c1_reference_episode'] = c1_reference_episode()
