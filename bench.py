@@ -679,6 +679,35 @@ def run_c4(args, su):
   e2e_obs_ms = e2e_loop(True)
   obs_bytes = sum(x.numel() * x.element_size() for x in obs_pin)
 
+  # ---- the same step on uint8 observations (the registered environments' dtype) ---- #
+  # (N = 1 only: the policy then scores the quantised maps in float64, like the reference's)
+  u8_line = None
+  if world == 1:
+    del obs_pin
+    env8, policy8 = make('uint8')
+    env8.reset()
+    for _ in range(2):
+      env8.step(policy8(env8))
+    if not args.eager:
+      env8.capture(policy8)
+    run8 = (lambda: env8.step(policy8(env8))) if args.eager else env8.step_policy
+    for _ in range(3):
+      run8()
+    n8 = min(20, L - 8)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(n8):
+      run8()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms8 = ev0.elapsed_time(ev1) / n8
+    u8_line = {'value': E / (ms8 * 1e-3), 'unit': w['unit'], 'ms_per_step': ms8, 'steps': n8,
+               'what': 'the same step with dtype="uint8": uint8 packed observation, the height '
+                       'policy on the quantised maps (float64 max-plus values, env.py:171-178 / '
+                       'baselines.py:21-26), steps 6..{} of an episode'.format(5 + n8)}
+    del env8, policy8
+
   stats = su.sharding.gather_stats([elapsed_ms, e2e_ms, e2e_obs_ms, float(E), n_inst], dev)
   if rank != 0:
     return None
@@ -712,9 +741,11 @@ def run_c4(args, su):
       'value': total_E / (float(stats[:, 2].max()) * 1e-3), 'unit': w['unit'],
       'd2h_bytes_per_step': obs_bytes + 13 * E,
       'api': 'same, plus the packed float32 observation copied to pinned host memory'},
+    'uint8_observations': u8_line,
     'gpu_launches': 7 * args.steps,
     'kernels_per_step': ['maxplus_stream_kernel', 'mask_select_packed_kernel',
-                         'place_poses_kernel', 'env_advance_kernel', 'raster_kernel (walls)',
+                         'place_poses_kernel', 'env_advance_kernel',
+                         'raster_warp_kernel (walls)',
                          'gather_rows_kernel (rock images)', 'pack_rewards_kernel'],
     'roofline': {
       'bound': 'hbm', 'kernel': 'env observation chain (pose, append, wall raster, rock '
