@@ -50,3 +50,23 @@ values = capi.maxplus_f32(walls, rocks, level, quantum_log2=envs.HEIGHT_QUANTUM_
 ms = timed(lambda: capi.mask_select(values, walls, goals, rocks, minorder=1,
                                     overlap_threshold=0.75, want_shown=False))
 print('mask_select: %.3f ms  %.2f ns/env' % (ms, ms * 1e6 / E))
+
+# uint8 observations (the registered environments' dtype): quantised planes, float64 values
+env8 = envs.BatchedStackEnv(bank, E, episode_length=30, observable_size_ratio=4,
+                            resolution_factor=4, dtype='uint8', rewarder='iou', seed=5,
+                            device=dev, vector_rng=True)
+env8.reset()
+for _ in range(steps):
+  env8.step(policy(env8))
+ms = timed(lambda: env8.planes_u8())
+print('planes_u8: %.3f ms' % ms)
+w8, g8, r8 = env8.planes_u8()
+l8 = env8._level8_d
+out8 = torch.empty(out.shape, dtype=torch.float64, device=dev)
+ms = timed(lambda: capi.maxplus_u8(w8, r8, l8, out=out8))
+print('maxplus_u8: %.3f ms  %.3e evals/s' % (ms, E * P / ms * 1e3))
+ms = timed(lambda: capi.mask_select(out8, w8, g8, r8, minorder=1, overlap_threshold=0.75,
+                                    want_shown=False))
+print('mask_select f64/u8: %.3f ms' % ms)
+ms = timed(lambda: policy(env8))
+print('HeightPolicy(uint8 env): %.3f ms' % ms)
