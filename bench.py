@@ -1070,6 +1070,7 @@ def c1_gpu_episode(torch, dev):
                                seed=11, device=dev)
     policy = envs.HeightPolicy()
     for timed in (False, True):
+      env.seed(11)                 # both passes play the first episode of seed 11
       env.reset()
       torch.cuda.synchronize()
       t0 = time.perf_counter()
@@ -1123,6 +1124,12 @@ def run_graft(args, rank, local_rank, world):
         head['extra']['c1_reference_episode'] = c1_reference_episode()
       except Exception as exc:
         head['extra']['c1_reference_episode'] = {'error': repr(exc)}
+      # environment 0 of the GPU run and the reference run play the same seed-11 episode
+      ref_c1, gpu_c1 = head['extra']['c1_reference_episode'], head['extra']['c1_gpu_episode']
+      if 'episode_return' in ref_c1 and gpu_c1.get('runs'):
+        gpu_c1['reference_episode_return'] = ref_c1['episode_return']
+        gpu_c1['abs_difference_env0'] = abs(gpu_c1['runs'][0]['episode_return_env0'] -
+                                            ref_c1['episode_return'])
   if world == 1 and not args.no_cpu_baseline:
     cores = os.cpu_count() or 1
     v, s_per_step, sample, kind = cpu_arm(args.workload, 2, 1, cores)
