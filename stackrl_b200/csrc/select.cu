@@ -613,6 +613,17 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
     // ---- bit images straight from global memory (baselines.py:153-154) --------- //
     // Every thread turns 4 consecutive pixels into 4 bits and ORs them into the
     // packed word; only the score maps are staged in shared memory.
+    // The thread's first wall / goal / rock quads are requested before the shared-memory
+    // set-up and its barrier (one DRAM round trip less in the CTA's dependent chain).
+    const In* wsrc = walls + (size_t)e * H * W;
+    const In* gsrc = goals + (size_t)e * H * W;
+    const In* rsrc = rocks + (size_t)e * R * h * h;
+    In a0[4], b0[4], r0[4];
+    if ((uint32_t)tid < (uint32_t)(H * W) / 4) {
+      load4(wsrc + 4 * tid, a0);
+      load4(gsrc + 4 * tid, b0);
+    }
+    if ((uint32_t)tid < (uint32_t)(R * h * h) / 4) load4(rsrc + 4 * tid, r0);
     for (int k = tid; k < H * g_nW + R * g_ng; k += kSelThreads) below[k] = 0u;
     // (asynchronously: the score maps are first read after the overlap counts)
     if (q.stage_values)
@@ -620,21 +631,28 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
                                    kSelThreads);
     if (tid < 32) s_cmax[tid] = 0;
     __syncthreads();
-    const In* wsrc = walls + (size_t)e * H * W;
-    const In* gsrc = goals + (size_t)e * H * W;
     for (uint32_t k = tid; k < (uint32_t)(H * W) / 4; k += kSelThreads) {
       In a[4], b[4];
-      load4(wsrc + 4 * k, a);
-      load4(gsrc + 4 * k, b);
+      if (k == (uint32_t)tid) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { a[t] = a0[t]; b[t] = b0[t]; }
+      } else {
+        load4(wsrc + 4 * k, a);
+        load4(gsrc + 4 * k, b);
+      }
       const uint32_t bits = (a[0] < b[0] ? 1u : 0u) | (a[1] < b[1] ? 2u : 0u) |
                             (a[2] < b[2] ? 4u : 0u) | (a[3] < b[3] ? 8u : 0u);
       const uint32_t row = kFixed ? k / (uint32_t)(W / 4) : udiv_mul(k, q.mulW4), col = 4 * (k - row * (W / 4));
       if (bits) atomicOr(below + row * g_nW + (col >> 5), bits << (col & 31));
     }
-    const In* rsrc = rocks + (size_t)e * R * h * h;
     for (uint32_t k = tid; k < (uint32_t)(R * h * h) / 4; k += kSelThreads) {
       In a[4];
-      load4(rsrc + 4 * k, a);
+      if (k == (uint32_t)tid) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) a[t] = r0[t];
+      } else {
+        load4(rsrc + 4 * k, a);
+      }
       const uint32_t bits = (a[0] > In(0) ? 1u : 0u) | (a[1] > In(0) ? 2u : 0u) |
                             (a[2] > In(0) ? 4u : 0u) | (a[3] > In(0) ? 8u : 0u);
       const uint32_t rr = kFixed ? k / (uint32_t)(h * h / 4) : udiv_mul(k, q.mulhh4), rem = k - rr * (h * h / 4);
