@@ -1036,3 +1036,37 @@ def test_warp_per_image_kernel_equals_cta_kernel_and_redraw(mods, monkeypatch, m
     for k in (3, 5, 8, 13, 17, 21, 30):
       want = R.render_depth(geo.overhead_view, geo.overhead_projection, rows, cols, scenes[k])
       assert np.array_equal(full_state[k].cpu().numpy(), want), k
+
+
+@pytest.mark.parametrize('scale', [0.375, 0.125, 0.16, 0.3, 1.0, 0.0078125])
+def test_quantise_planes_is_the_exact_float32_cast(mods, scale):
+  """srl_quantise_planes_u8 hoists the reciprocal part of the float32 division out of the
+  per-pixel work; the bytes are those of numpy's `np.array(x * 255 / scale, 'uint8')` in
+  float32 (env.py:171-178), also where x * 255 / scale lies within a few ulps of an integer,
+  for zeros, subnormals and a value that needs the general division."""
+  capi = mods['capi']
+  s32 = np.float32(scale)
+  k = np.arange(256, dtype='float64')
+  exact = (k * float(s32) / 255.0).astype('float32')                # quotient ~ an integer
+  near = np.concatenate([np.nextafter(exact, np.float32(np.inf), dtype='float32'),
+                         np.nextafter(exact, np.float32(-np.inf), dtype='float32'), exact])
+  for _ in range(3):
+    near = np.concatenate([near, np.nextafter(near, np.float32(np.inf), dtype='float32'),
+                           np.nextafter(near, np.float32(-np.inf), dtype='float32')])
+  rng = np.random.default_rng(4)
+  vals = np.concatenate([near, rng.uniform(0, float(s32), 20000).astype('float32'),
+                         np.array([0., 1e-42, 1e-38, 3e-33, float(s32)], 'float32')])
+  vals = vals[(vals >= 0) & (vals <= s32)]
+  H = W = 64
+  n = (len(vals) // (H * W)) * H * W
+  walls = vals[:n].reshape(-1, H, W)
+  E = len(walls)
+  goals = np.ascontiguousarray(walls[::-1])
+  rocks = np.ascontiguousarray(walls[:, :16, :16].reshape(E, 1, 16, 16))
+  dev = torch.device('cuda')
+  got = capi.quantise_planes(*(torch.from_numpy(x).to(dev) for x in (walls, goals, rocks)),
+                             float(s32))
+  with np.errstate(over='ignore'):
+    want = [np.array(x * np.float32(255) / s32, dtype='uint8') for x in (walls, goals, rocks)]
+  for g, w in zip(got, want):
+    assert np.array_equal(g.cpu().numpy(), w)
