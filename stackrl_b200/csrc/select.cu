@@ -618,12 +618,16 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
     const In* wsrc = walls + (size_t)e * H * W;
     const In* gsrc = goals + (size_t)e * H * W;
     const In* rsrc = rocks + (size_t)e * R * h * h;
+    // (fixed geometries only: in the generic instantiation the twelve extra live registers
+    // spill -- the heat-map sweep's launch got 26 % slower with it)
     In a0[4], b0[4], r0[4];
-    if ((uint32_t)tid < (uint32_t)(H * W) / 4) {
-      load4(wsrc + 4 * tid, a0);
-      load4(gsrc + 4 * tid, b0);
+    if constexpr (kFixed) {
+      if ((uint32_t)tid < (uint32_t)(H * W) / 4) {
+        load4(wsrc + 4 * tid, a0);
+        load4(gsrc + 4 * tid, b0);
+      }
+      if ((uint32_t)tid < (uint32_t)(R * h * h) / 4) load4(rsrc + 4 * tid, r0);
     }
-    if ((uint32_t)tid < (uint32_t)(R * h * h) / 4) load4(rsrc + 4 * tid, r0);
     for (int k = tid; k < H * g_nW + R * g_ng; k += kSelThreads) below[k] = 0u;
     // (asynchronously: the score maps are first read after the overlap counts)
     if (q.stage_values)
@@ -633,7 +637,7 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
     __syncthreads();
     for (uint32_t k = tid; k < (uint32_t)(H * W) / 4; k += kSelThreads) {
       In a[4], b[4];
-      if (k == (uint32_t)tid) {
+      if (kFixed && k == (uint32_t)tid) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) { a[t] = a0[t]; b[t] = b0[t]; }
       } else {
@@ -647,7 +651,7 @@ mask_select_packed_kernel(const V* __restrict__ values, const In* __restrict__ w
     }
     for (uint32_t k = tid; k < (uint32_t)(R * h * h) / 4; k += kSelThreads) {
       In a[4];
-      if (k == (uint32_t)tid) {
+      if (kFixed && k == (uint32_t)tid) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) a[t] = r0[t];
       } else {
